@@ -1,0 +1,301 @@
+// Colour-blocked heat-bath (Gibbs / annealing) sweeps for Ising graphs on sm_100a.
+//
+// Replaces the QPU / classical-annealer call  sampler.sample_ising(h, J, num_reads, ...)
+// that GraphRestrictedBoltzmannMachine.sample makes (reference call sites
+// src/model_wrapper.py:309-316, :369-376, src/utils/persistent_qpu_sampler.py:71-78;
+// sampler built at src/utils/common.py:123-138).  Numerical contract:
+// include/b200grbm_spec.h.
+//
+// Layout (why this is not "one int8 per spin"):
+//   * One CTA owns a *group* of CPL <= 32 chains for the whole launch.  The group's state
+//     is bit-packed: word W[p] in shared memory holds spin p of all CPL chains
+//     (bit c = chain c is +1).  P16: 5640 words = 22.5 KB; Z15: 29.8 KB.
+//   * Lanes are spins of the colour block being updated; each lane carries CPL fp32 local
+//     fields in registers.  For neighbour slot k the lane loads ONE (2J, nbr) entry and ONE
+//     state word, then does CPL predicated adds  f[c] += 2J  if bit c of the word is set
+//     (f starts at f0 = h - sum J).  Table and state traffic is therefore amortised over
+//     CPL chains; the kernel is bound by instruction issue (predicate extract + FADD per
+//     neighbour-chain pair, Philox + acceptance per update), not by shared-memory or HBM
+//     bytes.  HBM sees one read and one write of the state per launch.
+//   * Same-colour spins are never adjacent, so the parallel colour step equals the
+//     sequential sweep in visit order; W[p] is written in place and __syncthreads()
+//     separates colours.
+//   * Uniforms: Philox4x32-10 keyed by (seed; visit position, sweep, global chain / 4) --
+//     one call feeds 4 chains of the lane -- so trajectories do not depend on CPL, CTA
+//     size, grid or GPU count.  Round keys are precomputed on the host into the kernel
+//     parameter block (constant bank operands).
+#include "common.cuh"
+
+namespace b200grbm {
+
+enum { MODE_PHILOX_EXACT = 0, MODE_PHILOX_FAST = 1, MODE_SUPPLIED_EXACT = 2 };
+
+struct SweepParams {
+    const uint2 *ell;
+    const float *f0;
+    const int32_t *order;
+    const float *coef;
+    const float *uniforms;
+    const int8_t *state_in;
+    const uint32_t *packed_in;
+    int8_t *state_out;
+    uint32_t *packed_out;
+    int n, n_pad, width, n_colours;
+    int colour_start[B200GRBM_MAX_COLOURS + 1];
+    int chains, num_sweeps;
+    uint32_t sweep_offset;
+    uint32_t chain_block0;  // (chain_offset >> 2)
+    uint32_t rk[2 * B200GRBM_PHILOX_ROUNDS];
+};
+
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                           const SweepParams &p, uint32_t (&out)[4])
+{
+#pragma unroll
+    for (int r = 0; r < B200GRBM_PHILOX_ROUNDS; ++r) {
+        const uint64_t p0 = (uint64_t)B200GRBM_PHILOX_M0 * c0;
+        const uint64_t p1 = (uint64_t)B200GRBM_PHILOX_M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ p.rk[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ p.rk[2 * r + 1];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float uniform_from_bits(uint32_t bits)
+{
+    // (bits >> 9) | 0x3f800000 as one IMAD.HI on the FMA pipe; the add is exact (spec header)
+    const float one_to_two = u2f(__umulhi(bits, 1u << 23) + 0x3f800000u);
+    return __fadd_rn(one_to_two, -1.0f + B200GRBM_UNIFORM_HALF_ULP);
+}
+
+template <bool FAST>
+__device__ __forceinline__ bool accept_plus(float f, float coef, float v)
+{
+    float x = __fmul_rn(f, coef);
+    float e;
+    if (FAST) {
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+    } else {
+        x = fminf(fmaxf(x, -B200GRBM_EXP2_CLAMP), B200GRBM_EXP2_CLAMP);
+        const float t = __fadd_rn(x, B200GRBM_EXP2_MAGIC);
+        const float nn = __fadd_rn(t, -B200GRBM_EXP2_MAGIC);
+        const float r = __fadd_rn(x, -nn);
+        float q = B200GRBM_EXP2_C5;
+        q = __fmaf_rn(q, r, B200GRBM_EXP2_C4);
+        q = __fmaf_rn(q, r, B200GRBM_EXP2_C3);
+        q = __fmaf_rn(q, r, B200GRBM_EXP2_C2);
+        q = __fmaf_rn(q, r, B200GRBM_EXP2_C1);
+        q = __fmaf_rn(q, r, B200GRBM_EXP2_C0);
+        e = u2f(f2u(q) + (f2u(t) << 23));
+    }
+    return __fmaf_rn(v, e, v) < 1.0f;
+}
+
+template <int CPL, int MODE>
+__global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ SweepParams p)
+{
+    extern __shared__ uint32_t W[];
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    const int g = blockIdx.x;
+    const int chain0 = g * CPL;  // first chain of this group, local to the call
+    const int nvalid = min(CPL, p.chains - chain0);
+    const uint32_t valid_mask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+    const uint32_t blk0 = p.chain_block0 + (uint32_t)(chain0 >> 2);
+
+    // ---- load / initialise the group's packed state
+    for (int pp = tid; pp < p.n; pp += nthr) {
+        uint32_t w = 0;
+        if (p.state_in != nullptr) {
+            const int node = p.order[pp];
+            for (int c = 0; c < nvalid; ++c)
+                w |= (p.state_in[(size_t)(chain0 + c) * p.n + node] > 0 ? 1u : 0u) << c;
+        } else if (p.packed_in != nullptr) {
+            w = p.packed_in[(size_t)g * p.n_pad + pp];
+        } else {
+#pragma unroll
+            for (int c4 = 0; c4 < CPL / 4; ++c4) {
+                uint32_t r[4];
+                philox4x32((uint32_t)pp, 0u, blk0 + c4, B200GRBM_STREAM_INIT, p, r);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w |= (r[j] >> 31) << (4 * c4 + j);
+            }
+        }
+        W[pp] = w & valid_mask;
+    }
+    __syncthreads();
+
+    for (int t = 0; t < p.num_sweeps; ++t) {
+        const float coef = __ldg(p.coef + t);
+        const uint32_t sweep = p.sweep_offset + (uint32_t)t;
+        for (int col = 0; col < p.n_colours; ++col) {
+            const int c_end = p.colour_start[col + 1];
+            for (int pp = p.colour_start[col] + tid; pp < c_end; pp += nthr) {
+                float f[CPL];
+                const float fz = __ldg(p.f0 + pp);
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) f[c] = fz;
+
+                const uint2 *ep = p.ell + pp;
+                uint2 e = __ldg(ep);
+                for (int k = 0; k < p.width; ++k) {
+                    uint2 en = e;
+                    if (k + 1 < p.width) en = __ldg(ep + (size_t)(k + 1) * p.n_pad);
+                    const uint32_t w = W[e.y];
+                    const float j2 = u2f(e.x);
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c)
+                        if (w & (1u << c)) f[c] = __fadd_rn(f[c], j2);
+                    e = en;
+                }
+
+                uint32_t neww = 0;
+#pragma unroll
+                for (int c4 = 0; c4 < CPL / 4; ++c4) {
+                    uint32_t r[4];
+                    if (MODE != MODE_SUPPLIED_EXACT)
+                        philox4x32((uint32_t)pp, sweep, blk0 + c4, B200GRBM_STREAM_SWEEP, p, r);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = 4 * c4 + j;
+                        float v;
+                        if (MODE == MODE_SUPPLIED_EXACT) {
+                            const int cc = min(chain0 + c, p.chains - 1);
+                            v = __ldg(p.uniforms + ((size_t)t * p.chains + cc) * p.n + pp);
+                        } else {
+                            v = uniform_from_bits(r[j]);
+                        }
+                        if (accept_plus<MODE == MODE_PHILOX_FAST>(f[c], coef, v)) neww |= 1u << c;
+                    }
+                }
+                W[pp] = neww & valid_mask;
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- write back
+    for (int pp = tid; pp < p.n; pp += nthr) {
+        const uint32_t w = W[pp];
+        if (p.packed_out != nullptr) p.packed_out[(size_t)g * p.n_pad + pp] = w;
+        if (p.state_out != nullptr) {
+            const int node = p.order[pp];
+            for (int c = 0; c < nvalid; ++c)
+                p.state_out[(size_t)(chain0 + c) * p.n + node] = (w >> c) & 1u ? (int8_t)1 : (int8_t)-1;
+        }
+    }
+}
+
+typedef void (*gibbs_fn)(const SweepParams);
+
+template <int CPL>
+static gibbs_fn pick_mode(int mode)
+{
+    switch (mode) {
+        case MODE_PHILOX_EXACT: return gibbs_kernel<CPL, MODE_PHILOX_EXACT>;
+        case MODE_PHILOX_FAST: return gibbs_kernel<CPL, MODE_PHILOX_FAST>;
+        default: return gibbs_kernel<CPL, MODE_SUPPLIED_EXACT>;
+    }
+}
+
+static gibbs_fn pick(int cpl, int mode)
+{
+    switch (cpl) {
+        case 16: return pick_mode<16>(mode);
+        case 24: return pick_mode<24>(mode);
+        case 28: return pick_mode<28>(mode);
+        case 32: return pick_mode<32>(mode);
+        default: return nullptr;
+    }
+}
+
+static thread_local int32_t g_last_launches = 0;
+
+}  // namespace b200grbm
+
+using namespace b200grbm;
+
+extern "C" int32_t b200grbm_last_launch_count(void) { return g_last_launches; }
+
+extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *stream)
+{
+    g_last_launches = 0;
+    if (a == nullptr || a->struct_size != sizeof(b200grbm_sweep_args))
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: args is NULL or struct_size mismatch (ABI %d)",
+                    B200GRBM_ABI_VERSION);
+    if (a->n <= 0 || a->chains <= 0 || a->num_sweeps < 0)
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: n=%d chains=%d num_sweeps=%d", a->n, a->chains, a->num_sweeps);
+    if (a->n_pad < a->n || a->ell_width <= 0)
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: n_pad=%d < n=%d or ell_width=%d", a->n_pad, a->n, a->ell_width);
+    if (a->n_colours <= 0 || a->n_colours > B200GRBM_MAX_COLOURS)
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: n_colours=%d not in [1,%d]", a->n_colours, B200GRBM_MAX_COLOURS);
+    if (a->colour_start[0] != 0 || a->colour_start[a->n_colours] != a->n)
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: colour_start must run from 0 to n");
+    for (int c = 0; c < a->n_colours; ++c)
+        if (a->colour_start[c + 1] < a->colour_start[c])
+            return fail(B200GRBM_EINVAL, "gibbs_sweeps: colour_start not monotone at %d", c);
+    if (a->ell_dev == nullptr || a->f0_dev == nullptr || (a->num_sweeps > 0 && a->coef_dev == nullptr))
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: ell_dev / f0_dev / coef_dev must not be NULL");
+    if ((a->state_in_dev != nullptr || a->state_out_dev != nullptr) && a->order_dev == nullptr)
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: order_dev is required for int8 state I/O");
+    if (a->threads < 64 || a->threads > 768 || a->threads % 32 != 0)
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: threads=%d must be a multiple of 32 in [64,768]", a->threads);
+    if (a->chain_offset % 4 != 0)
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: chain_offset must be a multiple of 4");
+    if (a->accept != B200GRBM_ACCEPT_EXACT && a->accept != B200GRBM_ACCEPT_FAST)
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: unknown accept rule %d", a->accept);
+    if (a->uniforms_dev != nullptr && a->accept != B200GRBM_ACCEPT_EXACT)
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: supplied uniforms use the exact acceptance rule");
+    const int mode = a->uniforms_dev != nullptr ? MODE_SUPPLIED_EXACT
+                     : (a->accept == B200GRBM_ACCEPT_FAST ? MODE_PHILOX_FAST : MODE_PHILOX_EXACT);
+    gibbs_fn fn = pick(a->chains_per_lane, mode);
+    if (fn == nullptr)
+        return fail(B200GRBM_EUNSUPPORTED, "gibbs_sweeps: chains_per_lane=%d not in {16,24,28,32}",
+                    a->chains_per_lane);
+    B200_TRY(require_device());
+
+    SweepParams p;
+    p.ell = reinterpret_cast<const uint2 *>(a->ell_dev);
+    p.f0 = a->f0_dev;
+    p.order = a->order_dev;
+    p.coef = a->coef_dev;
+    p.uniforms = a->uniforms_dev;
+    p.state_in = a->state_in_dev;
+    p.packed_in = a->packed_in_dev;
+    p.state_out = a->state_out_dev;
+    p.packed_out = a->packed_out_dev;
+    p.n = a->n;
+    p.n_pad = a->n_pad;
+    p.width = a->ell_width;
+    p.n_colours = a->n_colours;
+    for (int c = 0; c <= B200GRBM_MAX_COLOURS; ++c) p.colour_start[c] = c <= a->n_colours ? a->colour_start[c] : a->n;
+    p.chains = a->chains;
+    p.num_sweeps = a->num_sweeps;
+    p.sweep_offset = a->sweep_offset;
+    p.chain_block0 = (uint32_t)(a->chain_offset >> 2);
+    uint32_t k0 = (uint32_t)a->seed, k1 = (uint32_t)(a->seed >> 32);
+    for (int r = 0; r < B200GRBM_PHILOX_ROUNDS; ++r) {
+        p.rk[2 * r] = k0;
+        p.rk[2 * r + 1] = k1;
+        k0 += B200GRBM_PHILOX_W0;
+        k1 += B200GRBM_PHILOX_W1;
+    }
+
+    const size_t smem = sizeof(uint32_t) * (size_t)a->n;
+    int dev = 0, smem_optin = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem > (size_t)smem_optin)
+        return fail(B200GRBM_EUNSUPPORTED, "gibbs_sweeps: n=%d spins need %zu B of shared memory (> %d)", a->n, smem,
+                    smem_optin);
+    B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int groups = (a->chains + a->chains_per_lane - 1) / a->chains_per_lane;
+    fn<<<groups, a->threads, smem, (cudaStream_t)stream>>>(p);
+    B200_CUDA(cudaGetLastError());
+    g_last_launches = 1;
+    return 0;
+}

@@ -1,0 +1,388 @@
+"""Block-Gibbs / annealing sampler behind the reference's sampler boundary.
+
+The reference draws negative-phase samples with
+``sampler.sample_ising(h, J, **sample_params)`` where ``sampler`` is
+``FixedEmbeddingComposite(DWaveSampler(...))`` (src/utils/common.py:123-128) and
+``sample_params`` are ``num_reads, answer_mode, auto_scale, annealing_time, label``
+(src/utils/common.py:130-138); the call is made inside
+``GraphRestrictedBoltzmannMachine.sample`` (call sites src/model_wrapper.py:309-316,
+:369-376, src/utils/persistent_qpu_sampler.py:71-78).
+
+:class:`BlockGibbsSampler` is the classical stand-in for that object: same method, same
+keyword tolerance, a :class:`SampleSet` shaped like dimod's (``record.sample`` int8
+``(reads, n)``, ``record.energy`` float64, ``variables``, ``vartype``; used at
+src/utils/persistent_qpu_sampler.py:84-88).  All arithmetic runs in the sm_100a kernels of
+``csrc/gibbs.cu`` through the C ABI (include/b200grbm.h); there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Mapping, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .topology import IsingGraph
+
+__all__ = ["BlockGibbsSampler", "SampleSet", "DeviceGraph", "plan_launch", "beta_schedule"]
+
+_LOG2E = 1.4426950408889634
+SUPPORTED_CPL = (16, 24, 28, 32)
+#: QPU-only keyword arguments the reference passes (src/utils/common.py:130-138); accepted and ignored
+_IGNORED_QPU_KWARGS = {"answer_mode", "auto_scale", "annealing_time", "label", "anneal_schedule",
+                       "programming_thermalization", "readout_thermalization", "reduce_intersample_correlation",
+                       "num_spin_reversal_transforms", "flux_drift_compensation", "chain_strength"}
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
+def plan_launch(chains: int, colour_sizes: Sequence[int], sm_count: int = 148) -> tuple[int, int]:
+    """Pick ``(chains_per_lane, threads)`` for a sweep launch.
+
+    One CTA owns ``chains_per_lane`` chains and an SM runs one CTA at a time, so the launch
+    takes ``ceil(groups / sm_count)`` waves of work proportional to ``chains_per_lane``;
+    minimise their product (4096 chains on 148 SMs: 28 -> 147 CTAs in one wave, 12.5 % less
+    work per SM than 32 -> 128 CTAs).  ``threads`` maximises lane occupancy of the
+    colour-block loop (P16: 1410 spins per colour -> 480 threads, 3 rounds, 97.9 %).
+    """
+    best = None
+    for cpl in SUPPORTED_CPL:
+        groups = -(-chains // cpl)
+        cost = -(-groups // max(sm_count, 1)) * cpl
+        if best is None or cost < best[0] or (cost == best[0] and cpl > best[1]):
+            best = (cost, cpl)
+    cpl = best[1]
+    sizes = [s for s in colour_sizes if s > 0] or [1]
+    best_t = None
+    for t in range(128, 768 + 1, 32):
+        eff = min(s / (-(-s // t) * t) for s in sizes)
+        if best_t is None or eff > best_t[0] + 1e-9 or (abs(eff - best_t[0]) <= 1e-9 and t > best_t[1]):
+            best_t = (eff, t)
+    return cpl, best_t[1]
+
+
+def beta_schedule(num_sweeps: int, beta_range: Optional[Sequence[float]] = None,
+                  beta_schedule_type: str = "geometric") -> np.ndarray:
+    """One inverse temperature per sweep.  ``beta_range=None`` is plain Gibbs at beta = 1
+    (the Boltzmann law of static/eq5.png at the GRBM's own temperature); otherwise a
+    geometric / linear ramp like the reference-style annealer."""
+    if num_sweeps < 0:
+        raise ValueError("num_sweeps must be non-negative")
+    if beta_range is None:
+        return np.ones(num_sweeps, dtype=np.float64)
+    b0, b1 = float(beta_range[0]), float(beta_range[1])
+    if b0 < 0 or b1 < 0:
+        raise ValueError("beta_range must be non-negative")
+    if beta_schedule_type == "geometric":
+        if b0 <= 0 or b1 <= 0:
+            raise ValueError("geometric schedule needs positive beta_range")
+        return np.geomspace(b0, b1, num_sweeps)
+    if beta_schedule_type == "linear":
+        return np.linspace(b0, b1, num_sweeps)
+    raise ValueError(f"unknown beta_schedule_type {beta_schedule_type!r}")
+
+
+class _Record:
+    def __init__(self, sample: np.ndarray, energy: np.ndarray):
+        self.sample = sample
+        self.energy = energy
+        self.num_occurrences = np.ones(sample.shape[0], dtype=np.int64)
+
+    def __len__(self) -> int:
+        return self.sample.shape[0]
+
+
+class SampleSet:
+    """Minimal stand-in for ``dimod.SampleSet`` that keeps the
+    samples on the device; the host ``record`` is materialised on first access."""
+
+    vartype = "SPIN"
+
+    def __init__(self, variables: Sequence, samples: Optional[torch.Tensor] = None,
+                 energies: Optional[torch.Tensor] = None, record: Optional[_Record] = None, info: Optional[dict] = None):
+        self.variables = list(variables)
+        self.samples_tensor = samples      # int8 (reads, n), node order, on the sampling device
+        self.energies_tensor = energies    # float64 (reads,)
+        self._record = record
+        self.info = info or {}
+
+    @property
+    def record(self) -> _Record:
+        if self._record is None:
+            self._record = _Record(self.samples_tensor.cpu().numpy(), self.energies_tensor.cpu().numpy())
+        return self._record
+
+    def __len__(self) -> int:
+        return int(self.samples_tensor.shape[0]) if self.samples_tensor is not None else len(self._record)
+
+    @classmethod
+    def from_samples(cls, samples_like, vartype="SPIN", energy=None, variables=None) -> "SampleSet":
+        arr = np.asarray(samples_like[0] if isinstance(samples_like, tuple) else samples_like, dtype=np.int8)
+        if variables is None:
+            variables = samples_like[1] if isinstance(samples_like, tuple) else list(range(arr.shape[1]))
+        energy = np.zeros(arr.shape[0]) if energy is None else np.asarray(energy, dtype=np.float64)
+        return cls(variables, record=_Record(arr, energy))
+
+
+class DeviceGraph:
+    """Device-resident sampler tables of one :class:`IsingGraph` (see include/b200grbm.h)."""
+
+    def __init__(self, graph: IsingGraph, device: torch.device):
+        self.graph = graph
+        self.device = torch.device(device)
+        g = graph
+        ell = np.zeros((g.ell_width, g.n_pad, 2), dtype=np.int32)
+        ell[:, :, 1] = g.ell_nbr
+        dev = self.device
+        self.ell_nbr_template = torch.from_numpy(ell).to(dev)
+        self.ell = self.ell_nbr_template.clone()
+        self.f0 = torch.zeros(g.n, dtype=torch.float32, device=dev)
+        self.h_eff = torch.zeros(g.n, dtype=torch.float32, device=dev)
+        self.j_eff = torch.zeros(max(g.n_edges, 1), dtype=torch.float32, device=dev)
+        i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+        self.order, self.pos = i32(g.order), i32(g.pos)
+        self.slot_a, self.slot_b = i32(g.slot_a), i32(g.slot_b)
+        self.edge_i, self.edge_j = i32(g.edge_i), i32(g.edge_j)
+        self.edge_pi, self.edge_pj = i32(g.pos[g.edge_i]), i32(g.pos[g.edge_j])
+
+    def set_weights(self, linear: torch.Tensor, quadratic: torch.Tensor, prefactor: float = 1.0,
+                    linear_range: Optional[Sequence[float]] = None,
+                    quadratic_range: Optional[Sequence[float]] = None) -> None:
+        g = self.graph
+        if linear.shape != (g.n,) or quadratic.shape != (g.n_edges,):
+            raise ValueError(f"expected linear ({g.n},) and quadratic ({g.n_edges},), got "
+                             f"{tuple(linear.shape)} and {tuple(quadratic.shape)}")
+        linear = linear.detach().to(self.device, torch.float32).contiguous()
+        quadratic = quadratic.detach().to(self.device, torch.float32).contiguous()
+        inf = float("inf")
+        h_lo, h_hi = (-inf, inf) if linear_range is None else map(float, linear_range)
+        j_lo, j_hi = (-inf, inf) if quadratic_range is None else map(float, quadratic_range)
+        self.ell.copy_(self.ell_nbr_template)
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.b200grbm_set_weights(
+                _lib.ptr(linear), _lib.ptr(quadratic) if g.n_edges else None, g.n, g.n_edges, float(prefactor),
+                h_lo, h_hi, j_lo, j_hi, _lib.ptr(self.order), _lib.ptr(self.slot_a) if g.n_edges else None,
+                _lib.ptr(self.slot_b) if g.n_edges else None, g.ell_width, g.n_pad, _lib.ptr(self.ell),
+                _lib.ptr(self.f0), _lib.ptr(self.h_eff), _lib.ptr(self.j_eff), _lib.current_stream(self.device)))
+
+
+class BlockGibbsSampler:
+    """``dimod.Sampler``-shaped sampler over a fixed qubit graph, running on one B200.
+
+    Args:
+        graph: the :class:`IsingGraph` (or ``(nodes, edges)``) whose structure every
+            ``sample_ising`` problem must follow -- the role of the fixed embedding at
+            src/utils/common.py:128.
+        device: CUDA device.  Nothing is allocated until the first call.
+        num_sweeps / beta_range / beta_schedule_type: defaults for ``sample_ising``.
+        seed: base Philox seed; call ``k`` uses ``splitmix64(seed + k)`` unless ``seed=`` is
+            passed to the call.
+        accept: ``"exact"`` (contract polynomial, bit-reproducible by the CPU oracle) or
+            ``"fast"`` (MUFU.EX2; statistical parity).
+        chain_offset / so that ranks of a sharded run draw disjoint global chains.
+    """
+
+    _b200_native = True
+
+    def __init__(self, graph: Union[IsingGraph, tuple], device: Union[str, torch.device, None] = None,
+                 num_sweeps: int = 1000, beta_range: Optional[Sequence[float]] = None,
+                 beta_schedule_type: str = "geometric", seed: int = 0, accept: str = "exact",
+                 variables: Optional[Sequence] = None, chain_offset: int = 0):
+        if not isinstance(graph, IsingGraph):
+            nodes, edges = graph
+            nodes = list(nodes)
+            index = {v: k for k, v in enumerate(nodes)}
+            edges = list(edges)
+            graph = IsingGraph.build(len(nodes), [index[u] for u, _ in edges], [index[v] for _, v in edges])
+            variables = nodes if variables is None else variables
+        if accept not in ("exact", "fast"):
+            raise ValueError("accept must be 'exact' or 'fast'")
+        self.graph = graph
+        self.device = torch.device("cuda" if device is None else device)
+        self.variables = list(range(graph.n)) if variables is None else list(variables)
+        if len(self.variables) != graph.n:
+            raise ValueError("variables must label every node")
+        self.num_sweeps = num_sweeps
+        self.beta_range = beta_range
+        self.beta_schedule_type = beta_schedule_type
+        self.seed = int(seed)
+        self.accept = accept
+        self.chain_offset = int(chain_offset)
+        self._calls = 0
+        self._dg: Optional[DeviceGraph] = None
+        self._edge_index: Optional[dict] = None
+        self._coef_cache: dict = {}
+        self.last_launches = 0
+        self.last_plan: tuple[int, int] = (0, 0)
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def device_graph(self) -> DeviceGraph:
+        if self._dg is None:
+            if self.device.type != "cuda":
+                raise RuntimeError("BlockGibbsSampler needs a CUDA device; there is no CPU fallback")
+            self._dg = DeviceGraph(self.graph, self.device)
+        return self._dg
+
+    @property
+    def properties(self) -> dict:
+        return {"h_range": [-4.0, 4.0], "j_range": [-1.0, 1.0], "category": "b200-block-gibbs"}
+
+    @property
+    def parameters(self) -> dict:
+        return {k: [] for k in ("num_reads", "num_sweeps", "beta_range", "beta_schedule_type", "beta_schedule",
+                                "seed", "initial_states", *sorted(_IGNORED_QPU_KWARGS))}
+
+    def _coef(self, num_sweeps, beta_range, beta_schedule_type, beta_sched) -> torch.Tensor:
+        if beta_sched is not None:
+            betas = np.asarray(beta_sched, dtype=np.float64).reshape(-1)
+            key = None
+        else:
+            key = (num_sweeps, None if beta_range is None else tuple(map(float, beta_range)), beta_schedule_type)
+            if key in self._coef_cache:
+                return self._coef_cache[key]
+            betas = beta_schedule(num_sweeps, beta_range, beta_schedule_type)
+        coef = torch.from_numpy((2.0 * betas * _LOG2E).astype(np.float32)).to(self.device)
+        if key is not None:
+            self._coef_cache[key] = coef
+        return coef
+
+    def _arrays_from_problem(self, h, J) -> tuple[np.ndarray, np.ndarray]:
+        g = self.graph
+        if isinstance(h, Mapping):
+            idx = {v: k for k, v in enumerate(self.variables)}
+            hv = np.zeros(g.n, dtype=np.float32)
+            for k, v in h.items():
+                if k not in idx:
+                    raise ValueError(f"variable {k!r} is not a node of the sampler's graph")
+                hv[idx[k]] = v
+        else:
+            hv = np.asarray(h, dtype=np.float32).reshape(-1)
+            if hv.shape[0] != g.n:
+                raise ValueError(f"h has {hv.shape[0]} entries, graph has {g.n} nodes")
+        if isinstance(J, Mapping):
+            if self._edge_index is None:
+                var = self.variables
+                self._edge_index = {}
+                for e, (a, b) in enumerate(zip(g.edge_i.tolist(), g.edge_j.tolist())):
+                    self._edge_index[(var[a], var[b])] = e
+                    self._edge_index[(var[b], var[a])] = e
+            jv = np.zeros(g.n_edges, dtype=np.float32)
+            ei = self._edge_index
+            for k, v in J.items():
+                e = ei.get(k)
+                if e is None:
+                    raise ValueError(f"coupler {k!r} is not an edge of the sampler's graph")
+                jv[e] += v
+        else:
+            jv = np.asarray(J, dtype=np.float32).reshape(-1)
+            if jv.shape[0] != g.n_edges:
+                raise ValueError(f"J has {jv.shape[0]} entries, graph has {g.n_edges} edges")
+        return hv, jv
+
+    # ------------------------------------------------------------------ sampling
+    def sample_ising(self, h, J, num_reads: int = 1, num_sweeps: Optional[int] = None,
+                     beta_range: Optional[Sequence[float]] = None, beta_schedule_type: Optional[str] = None,
+                     beta_schedule: Optional[Sequence[float]] = None, seed: Optional[int] = None,
+                     initial_states: Optional[Union[np.ndarray, torch.Tensor]] = None,
+                     uniforms: Optional[torch.Tensor] = None, **kwargs) -> SampleSet:
+        """Draw ``num_reads`` spin configurations ~ exp(-beta E) for the Ising problem
+        ``(h, J)`` given as dicts keyed by node / edge (dimod style) or as arrays in the
+        graph's node / edge order.  QPU-only keyword arguments are accepted and ignored."""
+        unknown = set(kwargs) - _IGNORED_QPU_KWARGS
+        if unknown:
+            raise TypeError(f"sample_ising() got unexpected keyword arguments {sorted(unknown)}")
+        hv, jv = self._arrays_from_problem(h, J)
+        dev = self.device
+        h_t = torch.from_numpy(hv).pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else torch.from_numpy(hv)
+        j_t = torch.from_numpy(jv).pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else torch.from_numpy(jv)
+        self.device_graph.set_weights(h_t, j_t)
+        return self._run(num_reads, num_sweeps, beta_range, beta_schedule_type, beta_schedule, seed, initial_states,
+                         uniforms)
+
+    def sample_grbm(self, linear: torch.Tensor, quadratic: torch.Tensor, prefactor: float,
+                    linear_range=None, quadratic_range=None, num_reads: int = 1, **kwargs) -> SampleSet:
+        """Device-resident variant used by ``GraphRestrictedBoltzmannMachine.sample``: scales and
+        clips the parameters on the GPU (no Python dict round trip) and samples."""
+        run_kw = {k: kwargs.pop(k) for k in ("num_sweeps", "beta_range", "beta_schedule_type", "beta_schedule",
+                                             "seed", "initial_states", "uniforms") if k in kwargs}
+        unknown = set(kwargs) - _IGNORED_QPU_KWARGS
+        if unknown:
+            raise TypeError(f"sample_grbm() got unexpected keyword arguments {sorted(unknown)}")
+        self.device_graph.set_weights(linear, quadratic, prefactor, linear_range, quadratic_range)
+        return self._run(num_reads, run_kw.get("num_sweeps"), run_kw.get("beta_range"),
+                         run_kw.get("beta_schedule_type"), run_kw.get("beta_schedule"), run_kw.get("seed"),
+                         run_kw.get("initial_states"), run_kw.get("uniforms"))
+
+    def _run(self, num_reads, num_sweeps, beta_range, beta_schedule_type, beta_sched, seed, initial_states,
+             uniforms, packed_io: Optional[torch.Tensor] = None, want_int8: bool = True,
+             sweep_offset: int = 0, plan: Optional[tuple[int, int]] = None) -> SampleSet:
+        if num_reads <= 0:
+            raise ValueError("num_reads must be positive")
+        g, dg, dev = self.graph, self.device_graph, self.device
+        num_sweeps = self.num_sweeps if num_sweeps is None else int(num_sweeps)
+        beta_range = self.beta_range if beta_range is None else beta_range
+        beta_schedule_type = self.beta_schedule_type if beta_schedule_type is None else beta_schedule_type
+        coef = self._coef(num_sweeps, beta_range, beta_schedule_type, beta_sched)
+        num_sweeps = int(coef.shape[0])
+        if seed is None:
+            seed = _splitmix64(self.seed + self._calls)
+        self._calls += 1
+        sizes = np.diff(g.colour_start).tolist()
+        cpl, threads = plan if plan is not None else plan_launch(num_reads, sizes, _lib.device_info()["sm_count"])
+        self.last_plan = (cpl, threads)
+
+        a = _lib.SweepArgs()
+        a.struct_size = C.sizeof(_lib.SweepArgs)
+        a.n, a.n_pad, a.ell_width, a.n_colours = g.n, g.n_pad, g.ell_width, g.n_colours
+        for k, v in enumerate(g.colour_start.tolist()):
+            a.colour_start[k] = v
+        a.ell_dev, a.f0_dev, a.order_dev = _lib.ptr(dg.ell), _lib.ptr(dg.f0), _lib.ptr(dg.order)
+        a.chains, a.chains_per_lane, a.threads = int(num_reads), cpl, threads
+        a.accept = _lib.ACCEPT_FAST if self.accept == "fast" else _lib.ACCEPT_EXACT
+        a.chain_offset, a.seed = self.chain_offset, int(seed) & 0xFFFFFFFFFFFFFFFF
+        a.sweep_offset, a.num_sweeps = int(sweep_offset), num_sweeps
+        a.coef_dev = _lib.ptr(coef)
+        keep = [coef]
+        if uniforms is not None:
+            if tuple(uniforms.shape) != (num_sweeps, num_reads, g.n) or uniforms.dtype != torch.float32:
+                raise ValueError("uniforms must be float32 of shape (num_sweeps, num_reads, n) in visit order")
+            uniforms = uniforms.to(dev).contiguous()
+            a.uniforms_dev = _lib.ptr(uniforms)
+            a.accept = _lib.ACCEPT_EXACT
+            keep.append(uniforms)
+        if initial_states is not None:
+            init = torch.as_tensor(initial_states).to(dev, torch.int8).contiguous()
+            if tuple(init.shape) != (num_reads, g.n):
+                raise ValueError("initial_states must have shape (num_reads, n)")
+            a.state_in_dev = _lib.ptr(init)
+            keep.append(init)
+        elif packed_io is not None:
+            a.packed_in_dev = _lib.ptr(packed_io)
+        samples = None
+        if want_int8:
+            samples = torch.empty((num_reads, g.n), dtype=torch.int8, device=dev)
+            a.state_out_dev = _lib.ptr(samples)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            _lib.check(lib.b200grbm_gibbs_sweeps(C.byref(a), _lib.current_stream(dev)))
+            self.last_launches = lib.b200grbm_last_launch_count()
+            energies = None
+            if samples is not None:
+                energies = torch.empty(num_reads, dtype=torch.float64, device=dev)
+                _lib.check(lib.b200grbm_energy_i8(_lib.ptr(samples), num_reads, g.n, g.n_edges,
+                                                  _lib.ptr(dg.edge_i), _lib.ptr(dg.edge_j), _lib.ptr(dg.h_eff),
+                                                  _lib.ptr(dg.j_eff), _lib.ptr(energies), _lib.current_stream(dev)))
+                self.last_launches += 1
+        return SampleSet(self.variables, samples, energies,
+                         info={"seed": int(seed), "chains_per_lane": cpl, "threads": threads,
+                               "num_sweeps": num_sweeps, "accept": self.accept})

@@ -1,0 +1,67 @@
+/*
+ * b200grbm_spec.h -- the NUMERICAL CONTRACT of the GRBM heat-bath sampler.
+ *
+ * Everything in this header is arithmetic that must be reproduced bit-for-bit
+ * by every implementation of the sampler (the sm_100a kernels in
+ * image-generation_b200/csrc and the CPU oracle in oracle/).  It contains
+ * constants and plain-C inline helpers only; it is included by both sides so
+ * that there is exactly one statement of the rule.
+ *
+ * What is being restated: the classical stand-in for the QPU call
+ *   sampler.sample_ising(h, J, **sample_params)
+ * reached from the reference at src/model_wrapper.py:309-316 and
+ * src/utils/persistent_qpu_sampler.py:71-78.
+ * The reference delegates the arithmetic to dwave-samplers' simulated annealer
+ * (un-vendored, not installed): single-spin heat-bath
+ * ("Gibbs") updates visiting spins in index order, one inverse temperature per
+ * sweep.  PARITY UNPINNED: the reference holds no test or golden vector for
+ * this path, so this header *is* the pinned definition.
+ *
+ * Ising convention (static/eq6.png, README.md:140-142):
+ *   E(s) = sum_i h_i s_i + sum_(i<j) J_ij s_i s_j,     P(s) ~ exp(-beta E(s))
+ *   local field  f_i = h_i + sum_j J_ij s_j
+ *   heat bath    P(s_i = +1 | rest) = 1 / (1 + exp(2 beta f_i))
+ *
+ * Reproducible evaluation order (fp32, no FMA contraction in the field sum):
+ *   f0_i = h_i;  for k in row(i) ascending neighbour position: f0_i -= J_ik
+ *   f    = f0_i; for k in row(i) ascending neighbour position:
+ *                    if s_k == +1: f += (2 * J_ik)
+ *   x    = clamp(f * coef, -120, 120)         coef = (float)(2 beta log2 e)
+ *   e    = exp2_poly(x)                        (degree-5, below; ~2.4e-7 rel)
+ *   s_i  = +1  iff  fmaf(v, e, v) < 1.0f       v in (0,1), 23-bit uniform
+ *
+ * Uniforms: either supplied by the caller (float in (0,1)) or drawn from
+ * Philox4x32-10 with
+ *   key     = (seed_lo, seed_hi)
+ *   counter = (visit position, sweep index, global chain id >> 2, stream)
+ *   word    = global chain id & 3
+ *   v       = as_float((bits >> 9) | 0x3f800000) - 1.0f + 2^-24   (exact)
+ * stream 0 = sweep uniforms, stream 1 = initial state (bit 31 set -> +1).
+ * The result therefore does not depend on launch geometry or GPU count.
+ */
+#ifndef B200GRBM_SPEC_H
+#define B200GRBM_SPEC_H
+
+#include <stdint.h>
+
+#define B200GRBM_PHILOX_M0 0xD2511F53u
+#define B200GRBM_PHILOX_M1 0xCD9E8D57u
+#define B200GRBM_PHILOX_W0 0x9E3779B9u
+#define B200GRBM_PHILOX_W1 0xBB67AE85u
+#define B200GRBM_PHILOX_ROUNDS 10
+
+#define B200GRBM_STREAM_SWEEP 0u
+#define B200GRBM_STREAM_INIT 1u
+
+/* exp2 on [-0.5, 0.5], Remez fit of relative error, coefficients rounded to fp32 */
+#define B200GRBM_EXP2_C0 0x1.000002p+0f
+#define B200GRBM_EXP2_C1 0x1.62e428p-1f
+#define B200GRBM_EXP2_C2 0x1.ebf918p-3f
+#define B200GRBM_EXP2_C3 0x1.c6b6e4p-5f
+#define B200GRBM_EXP2_C4 0x1.3d0c52p-7f
+#define B200GRBM_EXP2_C5 0x1.5c08e6p-10f
+#define B200GRBM_EXP2_MAGIC 12582912.0f /* 1.5 * 2^23 */
+#define B200GRBM_EXP2_CLAMP 120.0f
+#define B200GRBM_UNIFORM_HALF_ULP 0x1.0p-24f
+
+#endif /* B200GRBM_SPEC_H */

@@ -1,0 +1,73 @@
+"""The C-ABI library loads and exports every symbol include/b200grbm.h declares; without a
+GPU every compute entry point fails loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from image_generation_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "b200grbm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200grbm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_table_agree():
+    assert _declared() == sorted(_lib.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    for name in _declared():
+        assert hasattr(lib, name), name
+    assert lib.b200grbm_abi_version() == _lib.ABI_VERSION
+
+
+def test_sweep_args_layout_matches_header():
+    # struct_size is checked by the library at run time; here: field order / count vs the header
+    text = open(os.path.join(ROOT, "include", "b200grbm.h")).read()
+    body = text[text.index("typedef struct b200grbm_sweep_args"):text.index("} b200grbm_sweep_args;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"(\w+)(?:\[[^\]]*\])?;", body)
+    assert names == [f[0] for f in _lib.SweepArgs._fields_]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_calls_fail_loudly_without_a_gpu():
+    lib = _lib.load()
+    a = _lib.SweepArgs()
+    a.struct_size = C.sizeof(_lib.SweepArgs)
+    a.n = a.n_pad = 32
+    a.ell_width = 1
+    a.n_colours = 1
+    a.colour_start[1] = 32
+    a.ell_dev = a.f0_dev = a.coef_dev = 1  # never dereferenced: device check comes first
+    a.chains, a.chains_per_lane, a.threads, a.num_sweeps = 4, 32, 128, 1
+    rc = lib.b200grbm_gibbs_sweeps(C.byref(a), None)
+    assert rc != 0
+    assert b"fallback" in lib.b200grbm_last_error() or b"CUDA" in lib.b200grbm_last_error()
+    with pytest.raises(_lib.B200Error):
+        _lib.check(rc)
+
+
+def test_argument_validation_happens_before_any_launch():
+    lib = _lib.load()
+    a = _lib.SweepArgs()
+    a.struct_size = 3
+    assert lib.b200grbm_gibbs_sweeps(C.byref(a), None) == -1
+    a.struct_size = C.sizeof(_lib.SweepArgs)
+    a.n, a.n_pad, a.ell_width, a.n_colours, a.chains, a.num_sweeps = 8, 8, 1, 1, 4, 1
+    a.colour_start[1] = 8
+    a.ell_dev = a.f0_dev = a.coef_dev = 1
+    a.chains_per_lane, a.threads = 30, 128
+    assert lib.b200grbm_gibbs_sweeps(C.byref(a), None) == -2      # unsupported chains_per_lane
+    a.chains_per_lane, a.threads = 32, 100
+    assert lib.b200grbm_gibbs_sweeps(C.byref(a), None) == -1      # threads not a multiple of 32
+    a.threads, a.chain_offset = 128, 2
+    assert lib.b200grbm_gibbs_sweeps(C.byref(a), None) == -1      # chain_offset not a multiple of 4

@@ -1,0 +1,220 @@
+"""Parity of the sm_100a sweep kernel with the CPU oracle, through the C ABI.
+
+(a) supplied uniforms  -> trajectories bit-exact          (north_star check a)
+(a') native Philox, exact acceptance -> also bit-exact, at BASELINE.json's full cfg2 shape
+(b) native Philox, fast acceptance -> marginals / correlations within standard errors
+"""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+import image_generation_b200 as B
+from image_generation_b200 import _lib
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(graph, seed, h_scale=0.3, j_scale=0.4):
+    rng = np.random.default_rng(seed)
+    h = rng.uniform(-h_scale, h_scale, graph.n).astype(np.float32)
+    J = rng.uniform(-j_scale, j_scale, graph.n_edges).astype(np.float32)
+    return h, J
+
+
+def _oracle_csr(graph):
+    return O.PositionCSR(graph.n, graph.edge_i, graph.edge_j, graph.order)
+
+
+@pytest.mark.parametrize("cpl,threads", [(16, 64), (24, 128), (28, 480), (32, 768)])
+def test_supplied_uniforms_bit_exact(cuda_device, cpl, threads):
+    g = B.IsingGraph.pegasus(4)
+    h, J = _problem(g, 1)
+    chains, sweeps = 70, 6                      # ragged against every chains_per_lane
+    rng = np.random.default_rng(2)
+    U = rng.uniform(1e-6, 1 - 1e-6, size=(sweeps, chains, g.n)).astype(np.float32)
+    init = rng.choice([-1, 1], size=(chains, g.n)).astype(np.int8)
+    beta = np.geomspace(0.1, 1.5, sweeps)
+    want = O.gibbs(_oracle_csr(g), h, J, init, beta, uniforms=U)
+    s = B.BlockGibbsSampler(g, device=cuda_device)
+    s.device_graph.set_weights(torch.from_numpy(h), torch.from_numpy(J))
+    ss = s._run(chains, None, None, None, beta, 0, init, torch.from_numpy(U), plan=(cpl, threads))
+    got = ss.record.sample
+    assert got.dtype == np.int8 and got.shape == (chains, g.n)
+    assert np.array_equal(got, want)
+    np.testing.assert_allclose(ss.record.energy, O.energies(g.n, g.edge_i, g.edge_j, h, J, want), rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("cpl,threads", [(16, 96), (28, 256), (32, 480)])
+def test_philox_exact_mode_bit_exact_and_geometry_independent(cuda_device, cpl, threads):
+    g = B.IsingGraph.pegasus(5)
+    h, J = _problem(g, 3)
+    chains, sweeps, seed = 100, 8, 0xC0FFEE1234
+    csr = _oracle_csr(g)
+    beta = np.linspace(0.3, 1.2, sweeps)
+    want = O.gibbs(csr, h, J, O.init_state(csr, chains, seed), beta, seed=seed)
+    s = B.BlockGibbsSampler(g, device=cuda_device)
+    ss = s.sample_ising(h, J, num_reads=chains, beta_schedule=beta, seed=seed)
+    assert np.array_equal(ss.record.sample, want)
+    s.device_graph.set_weights(torch.from_numpy(h), torch.from_numpy(J))
+    ss2 = s._run(chains, None, None, None, beta, seed, None, None, plan=(cpl, threads))
+    assert np.array_equal(ss2.record.sample, want)
+
+
+def test_chain_offset_shards_reproduce_the_single_launch(cuda_device):
+    g = B.IsingGraph.zephyr(2)
+    h, J = _problem(g, 4)
+    seed, sweeps = 77, 5
+    full = B.BlockGibbsSampler(g, device=cuda_device).sample_ising(h, J, num_reads=96, num_sweeps=sweeps, seed=seed)
+    parts = []
+    for off, cnt in ((0, 40), (40, 56)):
+        s = B.BlockGibbsSampler(g, device=cuda_device, chain_offset=off)
+        parts.append(s.sample_ising(h, J, num_reads=cnt, num_sweeps=sweeps, seed=seed).record.sample)
+    assert np.array_equal(np.concatenate(parts), full.record.sample)
+
+
+def test_checkpoint_graph_greedy_colouring_bit_exact(cuda_device, golden):
+    z, meta = golden
+    name = "Advantage2_system1_10_epochs"
+    lin, quad = z[name + "/linear"], z[name + "/quadratic"]
+    g = B.IsingGraph.build(256, z[name + "/edge_i"], z[name + "/edge_j"])
+    prefactor = 0.05
+    dg_s = B.BlockGibbsSampler(g, device=cuda_device)
+    dg_s.device_graph.set_weights(torch.from_numpy(lin), torch.from_numpy(quad), prefactor, (-4.0, 4.0), (-1.0, 1.0))
+    h = np.clip(np.float32(prefactor) * lin, -4, 4).astype(np.float32)
+    J = np.clip(np.float32(prefactor) * quad, -1, 1).astype(np.float32)
+    assert np.array_equal(dg_s.device_graph.h_eff.cpu().numpy(), h)
+    assert np.array_equal(dg_s.device_graph.j_eff.cpu().numpy()[: g.n_edges], J)
+    csr = _oracle_csr(g)
+    seed, sweeps, chains = 5, 10, 256                      # cfg1: num_reads 256
+    want = O.gibbs(csr, h, J, O.init_state(csr, chains, seed), [1.0] * sweeps, seed=seed)
+    got = dg_s._run(chains, sweeps, None, None, None, seed, None, None).record.sample
+    assert np.array_equal(got, want)
+
+
+def test_clipping_ranges_are_applied(cuda_device):
+    g = B.IsingGraph.pegasus(2)
+    lin = np.linspace(-200, 200, g.n).astype(np.float32)
+    quad = np.linspace(-50, 50, g.n_edges).astype(np.float32)
+    s = B.BlockGibbsSampler(g, device=cuda_device)
+    s.device_graph.set_weights(torch.from_numpy(lin), torch.from_numpy(quad), 0.05, (-4.0, 4.0), (-1.0, 1.0))
+    assert np.array_equal(s.device_graph.h_eff.cpu().numpy(), np.clip(np.float32(0.05) * lin, -4, 4))
+    assert np.array_equal(s.device_graph.j_eff.cpu().numpy()[: g.n_edges], np.clip(np.float32(0.05) * quad, -1, 1))
+
+
+def test_edge_cases(cuda_device):
+    # single chain, isolated node, n not a multiple of 32, zero sweeps
+    ei, ej = np.array([0, 1, 2, 5]), np.array([1, 2, 3, 6])
+    g = B.IsingGraph.build(9, ei, ej)                      # nodes 4, 7, 8 isolated
+    h, J = _problem(g, 6, 1.0, 1.0)
+    csr = _oracle_csr(g)
+    s = B.BlockGibbsSampler(g, device=cuda_device)
+    for chains in (1, 3, 33):
+        want0 = O.init_state(csr, chains, 9)
+        got0 = s.sample_ising(h, J, num_reads=chains, num_sweeps=0, seed=9).record.sample
+        assert np.array_equal(got0, want0)
+        want = O.gibbs(csr, h, J, want0, [0.7] * 4, seed=9)
+        got = s.sample_ising(h, J, num_reads=chains, beta_schedule=[0.7] * 4, seed=9).record.sample
+        assert np.array_equal(got, want)
+    with pytest.raises(ValueError):
+        s.sample_ising(h, J, num_reads=0)
+    with pytest.raises(ValueError):
+        s.sample_ising(h[:-1], J, num_reads=1)
+    with pytest.raises(ValueError):
+        s.sample_ising({0: 1.0}, {(0, 8): 1.0}, num_reads=1)    # not an edge of the graph
+    with pytest.raises(TypeError):
+        s.sample_ising(h, J, num_reads=1, bogus=1)
+    # QPU kwargs from src/utils/common.py:130-138 are tolerated
+    s.sample_ising(h, J, num_reads=2, num_sweeps=1, answer_mode="raw", auto_scale=False, annealing_time=1,
+                   label="Examples - ML MNIST Image Gen")
+
+
+def test_dict_problem_matches_array_problem(cuda_device):
+    g = B.IsingGraph.pegasus(2)
+    h, J = _problem(g, 7)
+    labels = [f"q{i}" for i in range(g.n)]
+    s = B.BlockGibbsSampler(g, device=cuda_device, variables=labels)
+    hd = {labels[i]: float(h[i]) for i in range(g.n)}
+    Jd = {(labels[b], labels[a]) if k % 2 else (labels[a], labels[b]): float(J[k])
+          for k, (a, b) in enumerate(zip(g.edge_i, g.edge_j))}
+    a = s.sample_ising(hd, Jd, num_reads=8, num_sweeps=3, seed=1)
+    b = s.sample_ising(h, J, num_reads=8, num_sweeps=3, seed=1)
+    assert np.array_equal(a.record.sample, b.record.sample)
+    assert a.variables == labels and a.vartype == "SPIN"
+    assert a.record.num_occurrences.tolist() == [1] * 8
+
+
+def test_full_size_cfg2_shape_bit_exact_on_sampled_chains(cuda_device):
+    """BASELINE.json cfg2 shape (Pegasus P16, 5640 spins, 4096 chains); the oracle replays
+    a handful of chains (chain_offset makes any chain block addressable)."""
+    g = B.IsingGraph.pegasus(16)
+    rng = np.random.default_rng(8)
+    h = (0.05 * rng.uniform(-0.05, 0.05, g.n)).astype(np.float32)
+    J = (0.05 * rng.uniform(-5, 5, g.n_edges)).astype(np.float32)
+    seed, sweeps, chains = 2024, 6, 4096
+    beta = np.geomspace(0.1, 1.0, sweeps)
+    s = B.BlockGibbsSampler(g, device=cuda_device)
+    got = s.sample_ising(h, J, num_reads=chains, beta_schedule=beta, seed=seed).record.sample
+    assert s.last_plan[0] == 28
+    csr = _oracle_csr(g)
+    for block in (0, 27, 28, 1000, 4092):                   # includes a CTA boundary (28) and the ragged tail
+        want = O.gibbs(csr, h, J, O.init_state(csr, 4, seed, chain_offset=block), beta, seed=seed, chain_offset=block)
+        assert np.array_equal(got[block:block + 4], want), block
+    # size-independent property: energies recorded by the sampler equal a recomputation
+    e = O.energies(g.n, g.edge_i, g.edge_j, h, J, got[:64])
+    np.testing.assert_allclose(s.sample_ising(h, J, num_reads=chains, beta_schedule=beta, seed=seed).record.energy[:64],
+                               e, rtol=1e-12, atol=1e-9)
+
+
+def _exact(n, ei, ej, h, J, beta):
+    states = np.array(list(itertools.product([-1, 1], repeat=n)), dtype=np.int8)
+    E = O.energies(n, ei, ej, h, J, states)
+    w = np.exp(-beta * (E - E.min()))
+    w /= w.sum()
+    sf = states.astype(np.float64)
+    return (w[:, None] * sf).sum(0), np.array([(w * sf[:, a] * sf[:, b]).sum() for a, b in zip(ei, ej)])
+
+
+@pytest.mark.parametrize("accept", ["exact", "fast"])
+def test_statistics_match_exact_boltzmann(cuda_device, accept):
+    """north_star check (b): native Philox marginals and edge correlations within 3 s.e.
+    (here against exact enumeration; many independent chains, one retained sample each)."""
+    rng = np.random.default_rng(10)
+    n = 12
+    ei, ej = np.array([(a, b) for a in range(n) for b in range(a + 1, n) if rng.random() < 0.35]).T
+    g = B.IsingGraph.build(n, ei, ej)
+    h = rng.uniform(-0.5, 0.5, n).astype(np.float32)
+    J = rng.uniform(-0.6, 0.6, ei.size).astype(np.float32)
+    chains = 200_000
+    s = B.BlockGibbsSampler(g, device=cuda_device, accept=accept, seed=31)
+    x = s.sample_ising(h, J, num_reads=chains, num_sweeps=60).samples_tensor.to(torch.float64)
+    m1 = x.mean(0).cpu().numpy()
+    m2 = (x[:, torch.as_tensor(ei, device=x.device)] * x[:, torch.as_tensor(ej, device=x.device)]).mean(0).cpu().numpy()
+    e1, e2 = _exact(n, ei, ej, h, J, 1.0)
+    se1 = np.sqrt((1 - e1 ** 2) / chains)
+    se2 = np.sqrt((1 - e2 ** 2) / chains)
+    # 3 s.e. per statistic is exceeded by chance ~0.3 % of the time; with 12 + |E| statistics
+    # use the Bonferroni-safe 4.2 and require the bulk inside 3
+    assert np.all(np.abs(m1 - e1) < 4.2 * se1) and np.mean(np.abs(m1 - e1) < 3 * se1) > 0.9
+    assert np.all(np.abs(m2 - e2) < 4.2 * se2) and np.mean(np.abs(m2 - e2) < 3 * se2) > 0.9
+
+
+def test_fast_acceptance_matches_oracle_statistics_on_pegasus(cuda_device):
+    """Energy histogram / magnetisation of the fast rule vs the CPU oracle on a Pegasus graph."""
+    g = B.IsingGraph.pegasus(3)
+    h, J = _problem(g, 12, 0.1, 0.3)
+    chains, sweeps = 4096, 40
+    fast = B.BlockGibbsSampler(g, device=cuda_device, accept="fast", seed=1).sample_ising(
+        h, J, num_reads=chains, num_sweeps=sweeps)
+    csr = _oracle_csr(g)
+    ref = O.gibbs(csr, h, J, O.init_state(csr, 1024, 5), [1.0] * sweeps, seed=5)
+    e_fast = fast.record.energy
+    e_ref = O.energies(g.n, g.edge_i, g.edge_j, h, J, ref)
+    se = np.sqrt(e_fast.var() / chains + e_ref.var() / 1024)
+    assert abs(e_fast.mean() - e_ref.mean()) < 3.5 * se
+    assert abs(e_fast.std() / e_ref.std() - 1.0) < 0.12
+    m_fast = fast.record.sample.astype(np.float64).mean()
+    m_ref = ref.astype(np.float64).mean()
+    assert abs(m_fast - m_ref) < 4 * np.sqrt(1.0 / (chains * g.n) + 1.0 / (1024 * g.n)) * 3  # spins are correlated

@@ -1,0 +1,106 @@
+"""Host-side graph logic: generators, colourings, ELL tables, launch planning."""
+import numpy as np
+import pytest
+
+import image_generation_b200 as B
+from image_generation_b200.topology import greedy_colouring
+
+
+def test_pegasus_p16_counts_and_colouring():
+    n, ei, ej, col = B.pegasus_graph(16)
+    assert (n, ei.size) == (5640, 40484)          # BASELINE.json cfg2
+    deg = np.bincount(np.concatenate([ei, ej]), minlength=n)
+    assert (deg.min(), deg.max()) == (6, 15) and abs(deg.mean() - 14.356) < 1e-3
+    assert not np.any(col[ei] == col[ej])
+    assert np.bincount(col).tolist() == [1410] * 4
+
+
+def test_zephyr_z15_counts_and_colouring():
+    n, ei, ej, col = B.zephyr_graph(15)
+    assert (n, ei.size) == (7440, 71736)          # BASELINE.json cfg4
+    deg = np.bincount(np.concatenate([ei, ej]), minlength=n)
+    assert (deg.min(), deg.max()) == (10, 20)
+    assert not np.any(col[ei] == col[ej])
+    assert np.bincount(col).tolist() == [1860] * 4
+
+
+def test_ell_tables_are_consistent():
+    g = B.IsingGraph.pegasus(3)
+    assert g.n_pad % 32 == 0 and g.ell_width == g.degree.max()
+    for e in range(g.n_edges):
+        ka, pa = divmod(int(g.slot_a[e]), g.n_pad)
+        kb, pb = divmod(int(g.slot_b[e]), g.n_pad)
+        assert pa == g.pos[g.edge_i[e]] and g.ell_nbr[ka, pa] == g.pos[g.edge_j[e]]
+        assert pb == g.pos[g.edge_j[e]] and g.ell_nbr[kb, pb] == g.pos[g.edge_i[e]]
+    for p in range(g.n):
+        row = g.ell_nbr[: g.degree[p], p]
+        assert np.all(np.diff(row) > 0)                       # contract order: ascending position
+        assert np.all(g.ell_nbr[g.degree[p]:, p] == p)        # padding points at self
+    # colour blocks are contiguous and proper
+    c_of_pos = g.colour[g.order]
+    assert np.all(np.diff(c_of_pos) >= 0)
+    assert g.colour_start.tolist() == [0] + np.cumsum(np.bincount(g.colour)).tolist()
+
+
+def test_checkpoint_graphs_colour_with_few_colours(golden):
+    z, meta = golden
+    for name in meta:
+        ei, ej = z[name + "/edge_i"], z[name + "/edge_j"]
+        col = greedy_colouring(256, ei, ej)
+        assert not np.any(col[ei] == col[ej])
+        assert col.max() + 1 <= 6                  # 4-5 with smallest-last
+        g = B.IsingGraph.build(256, ei, ej)
+        assert g.n_colours <= 6 and g.ell_width == np.bincount(np.concatenate([ei, ej])).max()
+
+
+def test_build_rejects_bad_graphs():
+    with pytest.raises(ValueError):
+        B.IsingGraph.build(3, [0, 1], [1, 1])                 # self loop
+    with pytest.raises(ValueError):
+        B.IsingGraph.build(3, [0, 1], [1, 0])                 # duplicate edge
+    with pytest.raises(ValueError):
+        B.IsingGraph.build(3, [0], [5])                       # out of range
+    with pytest.raises(ValueError):
+        B.IsingGraph.build(3, [0], [1], colour=[0, 0, 1])     # improper colouring
+
+
+def test_plan_launch():
+    # cfg2: 4096 chains on 148 SMs -> 28 chains per CTA fills 147 SMs in one wave
+    assert B.plan_launch(4096, [1410] * 4, 148) == (28, 480)
+    cpl, threads = B.plan_launch(32768, [1860] * 4, 148)
+    assert cpl == 32 and threads % 32 == 0
+    for chains in (1, 5, 100, 4096, 262144):
+        cpl, threads = B.plan_launch(chains, [7, 9], 148)
+        assert cpl in (16, 24, 28, 32) and 64 <= threads <= 768
+
+
+def test_beta_schedule():
+    assert np.all(B.beta_schedule(5) == 1.0)
+    s = B.beta_schedule(4, (0.1, 1.0))
+    assert s[0] == pytest.approx(0.1) and s[-1] == pytest.approx(1.0) and np.all(np.diff(np.log(s)) > 0)
+    with pytest.raises(ValueError):
+        B.beta_schedule(4, (0.0, 1.0), "geometric")
+    with pytest.raises(ValueError):
+        B.beta_schedule(4, (0.1, 1.0), "cubic")
+
+
+def test_greedy_get_subgraph_is_deterministic_and_connected():
+    n, ei, ej, _ = B.pegasus_graph(4)
+    adj = {v: [] for v in range(n)}
+    for a, b in zip(ei.tolist(), ej.tolist()):
+        adj[a].append(b)
+        adj[b].append(a)
+    a = B.greedy_get_subgraph(40, 775321899904, range(n), adj)
+    b = B.greedy_get_subgraph(40, 775321899904, range(n), adj)
+    assert a == b and len(set(a)) == 40
+    chosen = set(a)
+    seen, stack = {a[0]}, [a[0]]
+    while stack:
+        v = stack.pop()
+        for u in adj[v]:
+            if u in chosen and u not in seen:
+                seen.add(u)
+                stack.append(u)
+    assert seen == chosen
+    mapping = B.get_graph_mapping(a)
+    assert sorted(mapping.values()) == list(range(40))
