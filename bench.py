@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- GRBM spin-updates/s on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N ...            # CPU arm: the oracle port on host cores
+
+Workload (config.workload): BASELINE.json configs[1] -- block-Gibbs sampling on the Pegasus
+P16 fabric graph (5 640 spins, 40 484 couplers), 4 096 chains x 1 000 sweeps at beta = 1 per
+GPU, synthetic h ~ U(-0.05, 0.05) * prefactor, J ~ U(-5, 5) * prefactor, prefactor 0.05
+(SURVEY.md section 8d cfg2).  A *step* is one pass of the hot path over one batch of chains:
+sampler.sample (sweeps + sample energies) followed by the integer edge statistics of the
+samples; at N > 1 each rank owns 4 096 chains of the global chain-id space (weak scaling, no
+data-path collective) and the step ends with the path's one exchange, an NCCL all-reduce of
+the N + E int64 counters.
+
+`value`  : device-resident throughput (h/J and state in HBM; CUDA events, max over ranks).
+`e2e`    : the same metric through the reference-facing call sampler.sample_ising(h, J, num_reads, ...)
+           with HOST h/J arrays in and HOST samples out (pinned H2D + D2H inside the timed region).
+`roofline`: dominant kernel b200grbm::gibbs_kernel.  SURVEY.md section 8(d): the sweep is not HBM bound (one
+           state read + write per launch); algorithmic bytes are (mean degree + 1) per update against the
+           shared-memory roof n_SM x 128 B/clk x f_SM; the HBM view is reported next to it.
+`cpu_baseline`: the oracle port's textbook double-precision sequential heat bath on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+P16_MEAN_DEGREE = 2 * 40484 / 5640.0
+CFG = dict(pegasus_m=16, chains=4096, sweeps=1000, prefactor=0.05, beta=1.0, seed=775321899904)
+
+
+def make_problem(cfg):
+    import image_generation_b200 as B
+
+    g = B.IsingGraph.pegasus(cfg["pegasus_m"])
+    rng = np.random.default_rng(cfg["seed"] % (2 ** 32))
+    h = (cfg["prefactor"] * rng.uniform(-0.05, 0.05, g.n)).astype(np.float32)
+    J = (cfg["prefactor"] * rng.uniform(-5.0, 5.0, g.n_edges)).astype(np.float32)
+    return g, h, J
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def cpu_port_rate(g, h, J, beta, target_seconds, threads=None):
+    """Oracle port (textbook double heat bath, all host threads) on a bounded sample of the workload."""
+    from oracle import oracle as O
+
+    if threads:
+        O.set_num_threads(threads)
+    cores = O.num_threads()
+    csr = O.PositionCSR(g.n, g.edge_i, g.edge_j, g.order)
+    chains = 4 * cores
+    st = O.init_state(csr, chains, 1)
+    t = time.perf_counter()
+    O.gibbs(csr, h, J, st, [beta] * 4, seed=1, f64=True)                       # calibration pass
+    rate = chains * 4 * g.n / (time.perf_counter() - t)
+    sweeps = max(4, int(target_seconds * rate / (chains * g.n)))
+    t = time.perf_counter()
+    O.gibbs(csr, h, J, st, [beta] * sweeps, seed=2, f64=True)
+    dt = time.perf_counter() - t
+    return chains * sweeps * g.n / dt, cores, f"Pegasus P16, {chains} chains x {sweeps} sweeps ({dt:.1f} s), oracle_gibbs_f64"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    g, h, J = make_problem(CFG)
+    rates, sample, cores = [], "", 1
+    per_step = max(1.0, min(15.0, 120.0 / max(1, args.steps + args.warmup)))
+    for k in range(args.warmup + args.steps):
+        r, cores, sample = cpu_port_rate(g, h, J, CFG["beta"], per_step)
+        if k >= args.warmup:
+            rates.append(r)
+    val = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": "grbm_spin_updates_per_s", "value": val, "unit": "spin-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * CFG["chains"] * CFG["sweeps"] * g.n / val, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "GRBM block-Gibbs, Pegasus P16 (5640 spins, 40484 couplers), 4096 chains x 1000 sweeps, beta=1"},
+        "cpu_baseline": {"value": val, "unit": "spin-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "spin-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference ships no CPU sampler source (arithmetic in un-vendored dwave-samplers); this is the oracle port "
+                "of the reference-style sequential heat bath on all host threads, each step a bounded sample",
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import image_generation_b200 as B
+    from image_generation_b200.dist import allreduce_statistics
+    from image_generation_b200.stats import edge_statistics, pack_spins
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    g, h, J = make_problem(CFG)
+    chains, sweeps = args.chains or CFG["chains"], args.sweeps or CFG["sweeps"]
+    sampler = B.BlockGibbsSampler(g, device=dev, num_sweeps=sweeps, seed=CFG["seed"], accept=args.accept,
+                                  chain_offset=rank * chains)
+    dg = sampler.device_graph
+    h_d, J_d = torch.from_numpy(h).to(dev), torch.from_numpy(J).to(dev)
+    dg.set_weights(h_d, J_d)
+    sum_s = torch.zeros(g.n, dtype=torch.int64, device=dev)
+    sum_ss = torch.zeros(g.n_edges, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    plan = (args.cpl, args.threads) if args.cpl and args.threads else None
+    launches = {"n": 0}
+
+    def step_device():
+        ss = sampler._run(chains, sweeps, None, None, None, None, None, None, plan=plan)
+        n_l = sampler.last_launches
+        packed = pack_spins(ss.samples_tensor, dg)
+        sum_s.zero_(); sum_ss.zero_()
+        edge_statistics(packed, chains, dg, out=(sum_s, sum_ss))
+        n_l += 3                                    # pack + edge + node statistics kernels
+        if world > 1:
+            a, b = allreduce_statistics([sum_s, sum_ss])
+            sum_s.copy_(a); sum_ss.copy_(b)
+        launches["n"] += n_l
+        return ss
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step_device()
+    sync_all()
+    launches["n"] = 0
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.3)
+    t_wall0 = time.time()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                       # L2 flush between timed steps (256 MB write > 126 MB L2)
+        sync_all()
+        ev[k][0].record()
+        # the dominant kernel alone, on the stream it is launched on (torch's current stream)
+        kev[k][0].record()
+        ss = sampler._run(chains, sweeps, None, None, None, None, None, None, plan=plan, want_int8=True)
+        kev[k][1].record()
+        n_l = sampler.last_launches
+        packed = pack_spins(ss.samples_tensor, dg)
+        sum_s.zero_(); sum_ss.zero_()
+        edge_statistics(packed, chains, dg, out=(sum_s, sum_ss))
+        if world > 1:
+            a, b = allreduce_statistics([sum_s, sum_ss])
+            sum_s.copy_(a); sum_ss.copy_(b)
+        ev[k][1].record()
+        launches["n"] += n_l + 3
+    sync_all()
+    t_wall1 = time.time()
+    clk = clocks.stop(t_wall0, t_wall1)
+    step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device=dev)
+    kern_ms = torch.tensor([a.elapsed_time(b) for a, b in kev], dtype=torch.float64, device=dev)
+    total_ms = step_ms.sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms) / 1e3
+    updates_per_step = chains * sweeps * g.n * world
+    value = updates_per_step * args.steps / total_s
+
+    # ---- end to end through the reference-facing call, host buffers in and out
+    h_pin, J_pin = torch.from_numpy(h).pin_memory(), torch.from_numpy(J).pin_memory()
+    out_pin = torch.empty((chains, g.n), dtype=torch.int8).pin_memory()
+    e_pin = torch.empty(chains, dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        ss = sampler.sample_ising(h_pin.numpy(), J_pin.numpy(), num_reads=chains, num_sweeps=sweeps, answer_mode="raw",
+                                  auto_scale=False, annealing_time=1, label="bench")
+        out_pin.copy_(ss.samples_tensor, non_blocking=True)
+        e_pin.copy_(ss.energies_tensor, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out_pin
+
+    step_e2e()
+    sync_all()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    sync_all()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = updates_per_step * e2e_steps / float(e2e_s)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    kernel_s = float(kern_ms.mean()) / 1e3            # gibbs_kernel + the small energy kernel behind it
+    upd_per_launch = chains * sweeps * g.n
+    alg_bytes = (P16_MEAN_DEGREE + 1.0) * upd_per_launch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    f_sm = (clk.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
+    smem_peak = sms * 128 * f_sm / 1e9
+    achieved = alg_bytes / kernel_s / 1e9
+    hbm_bytes = 2.0 * chains * g.n                      # int8 state written once (+ read when resuming chains)
+    roofline = {
+        "bound": "smem", "kernel": "b200grbm::gibbs_kernel", "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
+        "frac": achieved / smem_peak, "traffic": None,
+        "algorithmic_bytes_per_update": P16_MEAN_DEGREE + 1.0, "updates_per_launch": upd_per_launch,
+        "kernel_ms": kernel_s * 1e3,
+        "peak_source": f"SURVEY.md 8(d): n_SM({sms}) x 128 B/clk x SM clock sampled under load ({f_sm / 1e6:.0f} MHz)",
+        "hbm": {"achieved": hbm_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": hbm_bytes / kernel_s / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+        "note": "state is bit-packed (32 chains per word) so the kernel is issue-bound, not byte-bound; see DESIGN.md",
+    }
+    cpu_rate, cores, sample = cpu_port_rate(g, h, J, CFG["beta"], args.cpu_seconds)
+    line = {
+        "metric": "grbm_spin_updates_per_s", "value": value, "unit": "spin-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"GRBM block-Gibbs, Pegasus P16 ({g.n} spins, {g.n_edges} couplers), {chains} chains x "
+                               f"{sweeps} sweeps per GPU, beta=1, prefactor 0.05 (BASELINE.json configs[1])",
+                   "chains_per_gpu": chains, "sweeps": sweeps, "accept": args.accept,
+                   "chains_per_lane": sampler.last_plan[0], "threads": sampler.last_plan[1],
+                   "l2": "256 MB buffer written between timed steps", "parallelism": f"chains sharded x{world}",
+                   "exchange": "int64 all-reduce of N+E counters per step" if world > 1 else "none"},
+        "e2e": {"value": e2e_val, "unit": "spin-updates/s", "h2d_bytes_per_step": int(4 * (g.n + g.n_edges)),
+                "d2h_bytes_per_step": int(chains * g.n + 8 * chains), "steps": e2e_steps},
+        "gpu_launches": launches["n"], "clocks": clk, "roofline": roofline,
+        "cpu_baseline": {"value": cpu_rate, "unit": "spin-updates/s", "cores": cores, "kind": "port", "sample": sample},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--accept", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--chains", type=int, default=0)
+    ap.add_argument("--sweeps", type=int, default=0)
+    ap.add_argument("--cpl", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

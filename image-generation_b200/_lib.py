@@ -13,7 +13,6 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb200grbm.so")
 
-MAX_COLOURS = 16
 ACCEPT_EXACT = 0
 ACCEPT_FAST = 1
 ABI_VERSION = 1
@@ -35,10 +34,9 @@ class SweepArgs(C.Structure):
         ("n", C.c_int32),
         ("n_pad", C.c_int32),
         ("ell_width", C.c_int32),
-        ("n_colours", C.c_int32),
-        ("colour_start", C.c_int32 * (MAX_COLOURS + 1)),
-        ("ell_dev", C.c_void_p),
-        ("f0_dev", C.c_void_p),
+        ("n_tiles", C.c_int32),
+        ("tiles_dev", C.c_void_p),
+        ("tile_info_dev", C.c_void_p),
         ("order_dev", C.c_void_p),
         ("chains", C.c_int32),
         ("chains_per_lane", C.c_int32),
@@ -65,8 +63,9 @@ SIGNATURES = {
     "b200grbm_last_error": ([], C.c_char_p),
     "b200grbm_abi_version": ([], _i32),
     "b200grbm_device_info": ([C.POINTER(_i32)] * 4, _i32),
-    "b200grbm_set_weights": ([_vp, _vp, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _i32, _i32,
-                              _vp, _vp, _vp, _vp, _vp], _i32),
+    "b200grbm_set_weights": ([_vp, _vp, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _i32, _i32,
+                              _vp, _vp, _vp, _vp], _i32),
+    "b200grbm_sweep_smem_bytes": ([_i32, _i32, _i32], C.c_int64),
     "b200grbm_gibbs_sweeps": ([C.POINTER(SweepArgs), _vp], _i32),
     "b200grbm_last_launch_count": ([], _i32),
     "b200grbm_pack_f32": ([_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp], _i32),
@@ -75,6 +74,9 @@ SIGNATURES = {
     "b200grbm_energy_forward": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
     "b200grbm_energy_backward": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
     "b200grbm_energy_i8": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
+    "b200grbm_mmd_forward_f32": ([_vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _vp], _i32),
+    "b200grbm_mmd_backward_f32": ([_vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _f32, _f32, _vp, _vp, _vp,
+                                   _vp], _i32),
 }
 
 _lib: Optional[C.CDLL] = None

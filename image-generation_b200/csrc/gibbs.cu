@@ -8,22 +8,28 @@
 //
 // Layout (why this is not "one int8 per spin"):
 //   * One CTA owns a *group* of CPL <= 32 chains for the whole launch.  The group's state
-//     is bit-packed: word W[p] in shared memory holds spin p of all CPL chains
-//     (bit c = chain c is +1).  P16: 5640 words = 22.5 KB; Z15: 29.8 KB.
+//     is bit-packed: word W[p] in shared memory holds spin p of all CPL chains.  P16:
+//     5640 words = 22.5 KB; Z15: 29.8 KB.
 //   * Lanes are spins of the colour block being updated; each lane carries CPL fp32 local
-//     fields in registers.  For neighbour slot k the lane loads ONE (2J, nbr) entry and ONE
-//     state word, then does CPL predicated adds  f[c] += 2J  if bit c of the word is set
-//     (f starts at f0 = h - sum J).  Table and state traffic is therefore amortised over
-//     CPL chains; the kernel is bound by instruction issue (predicate extract + FADD per
-//     neighbour-chain pair, Philox + acceptance per update), not by shared-memory or HBM
-//     bytes.  HBM sees one read and one write of the state per launch.
+//     fields in registers.  For neighbour slot k the lane reads ONE (2J, nbr) entry and ONE
+//     state word, moves the word's bits into predicates (R2P, 7 per instruction) and does
+//     CPL predicated adds  f[c] += 2J  (f starts at f0 = h - sum J).  Table and state
+//     traffic is amortised over CPL chains; the kernel is bound by instruction issue
+//     (one FADD per neighbour-chain pair, Philox + acceptance per update), not by
+//     shared-memory or HBM bytes.  HBM sees one read and one write of the state per launch.
+//     CPL = 28 keeps bit 7 of every byte free so four R2Ps cover the word exactly.
+//   * The (2J, nbr, f0) tables are tiled per colour round -- tile = threads x (width + 1)
+//     8-byte entries, contiguous in global memory -- and streamed through a 2-stage
+//     shared-memory ring by the bulk-copy engine (cp.async.bulk + mbarrier complete_tx,
+//     SASS UBLKCP): the copy of round q+1 overlaps the arithmetic of round q, so no warp
+//     ever waits on an L2 load inside the neighbour loop.
 //   * Same-colour spins are never adjacent, so the parallel colour step equals the
 //     sequential sweep in visit order; W[p] is written in place and __syncthreads()
-//     separates colours.
+//     separates rounds.
 //   * Uniforms: Philox4x32-10 keyed by (seed; visit position, sweep, global chain / 4) --
 //     one call feeds 4 chains of the lane -- so trajectories do not depend on CPL, CTA
 //     size, grid or GPU count.  Round keys are precomputed on the host into the kernel
-//     parameter block (constant bank operands).
+//     parameter block (uniform-register operands).
 #include "common.cuh"
 
 namespace b200grbm {
@@ -31,8 +37,8 @@ namespace b200grbm {
 enum { MODE_PHILOX_EXACT = 0, MODE_PHILOX_FAST = 1, MODE_SUPPLIED_EXACT = 2 };
 
 struct SweepParams {
-    const uint2 *ell;
-    const float *f0;
+    const uint2 *tiles;       // [n_tiles][width + 1][threads] entries {2J bits | f0 bits, nbr}
+    const int2 *tile_info;    // [n_tiles] {first visit position, spins in this round}
     const int32_t *order;
     const float *coef;
     const float *uniforms;
@@ -40,13 +46,52 @@ struct SweepParams {
     const uint32_t *packed_in;
     int8_t *state_out;
     uint32_t *packed_out;
-    int n, n_pad, width, n_colours;
-    int colour_start[B200GRBM_MAX_COLOURS + 1];
+    int n, n_pad, width, n_tiles;
     int chains, num_sweeps;
     uint32_t sweep_offset;
     uint32_t chain_block0;  // (chain_offset >> 2)
+    uint32_t state_bytes;   // shared-memory bytes reserved for W (multiple of 128)
+    uint32_t tile_bytes;    // (width + 1) * threads * 8
     uint32_t rk[2 * B200GRBM_PHILOX_ROUNDS];
 };
+
+// ---------------------------------------------------------------- bulk copy + mbarrier (PTX)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 24)) __trap();   // a lost copy must fail the launch, never hang the GPU
+    }
+}
+
+// ---------------------------------------------------------------- contract arithmetic
 
 __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                            const SweepParams &p, uint32_t (&out)[4])
@@ -67,8 +112,8 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
 
 __device__ __forceinline__ float uniform_from_bits(uint32_t bits)
 {
-    // (bits >> 9) | 0x3f800000 as one IMAD.HI on the FMA pipe; the add is exact (spec header)
-    const float one_to_two = u2f(__umulhi(bits, 1u << 23) + 0x3f800000u);
+    // (bits >> 9) | 0x3f800000, then one exact add (spec header)
+    const float one_to_two = u2f((bits >> 9) | 0x3f800000u);
     return __fadd_rn(one_to_two, -1.0f + B200GRBM_UNIFORM_HALF_ULP);
 }
 
@@ -95,17 +140,53 @@ __device__ __forceinline__ bool accept_plus(float f, float coef, float v)
     return __fmaf_rn(v, e, v) < 1.0f;
 }
 
+// Bit of the in-kernel state word that holds chain c.  CPL = 28 leaves bit 7 of every byte
+// unused so that R2P (7 predicates from one byte) covers the word with four instructions.
+template <int CPL>
+__device__ __forceinline__ constexpr int bitpos(int c) { return CPL == 28 ? c + c / 7 : c; }
+
+template <int CPL>
+__device__ __forceinline__ uint32_t dense_to_kernel(uint32_t w)
+{
+    if (CPL != 28) return w;
+    return (w & 0x7fu) | ((w & 0x3f80u) << 1) | ((w & 0x1fc000u) << 2) | ((w & 0xfe00000u) << 3);
+}
+
+template <int CPL>
+__device__ __forceinline__ uint32_t kernel_to_dense(uint32_t w)
+{
+    if (CPL != 28) return w;
+    return (w & 0x7fu) | ((w >> 1) & 0x3f80u) | ((w >> 2) & 0x1fc000u) | ((w >> 3) & 0xfe00000u);
+}
+
 template <int CPL, int MODE>
 __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ SweepParams p)
 {
-    extern __shared__ uint32_t W[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);                 // 2 mbarriers (16 B, padded to 128)
+    uint32_t *W = reinterpret_cast<uint32_t *>(smem_raw + 128);
+    unsigned char *stage0 = smem_raw + 128 + p.state_bytes;
+
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
     const int g = blockIdx.x;
     const int chain0 = g * CPL;  // first chain of this group, local to the call
     const int nvalid = min(CPL, p.chains - chain0);
-    const uint32_t valid_mask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+    const uint32_t dense_mask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
     const uint32_t blk0 = p.chain_block0 + (uint32_t)(chain0 >> 2);
+    const uint32_t bar_addr = smem_u32(bars);
+    const uint32_t stage_addr = smem_u32(stage0);
+    const long long total_tiles = (long long)p.num_sweeps * p.n_tiles;
+
+    if (tid == 0) {
+        mbar_init(bar_addr, 1);
+        mbar_init(bar_addr + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (total_tiles > 0) {   // prologue: round 0 into stage 0
+            mbar_expect_tx(bar_addr, p.tile_bytes);
+            bulk_g2s(stage_addr, p.tiles, p.tile_bytes, bar_addr);
+        }
+    }
 
     // ---- load / initialise the group's packed state
     for (int pp = tid; pp < p.n; pp += nthr) {
@@ -125,62 +206,85 @@ __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ S
                 for (int j = 0; j < 4; ++j) w |= (r[j] >> 31) << (4 * c4 + j);
             }
         }
-        W[pp] = w & valid_mask;
+        W[pp] = dense_to_kernel<CPL>(w & dense_mask);
     }
     __syncthreads();
 
-    for (int t = 0; t < p.num_sweeps; ++t) {
-        const float coef = __ldg(p.coef + t);
-        const uint32_t sweep = p.sweep_offset + (uint32_t)t;
-        for (int col = 0; col < p.n_colours; ++col) {
-            const int c_end = p.colour_start[col + 1];
-            for (int pp = p.colour_start[col] + tid; pp < c_end; pp += nthr) {
-                float f[CPL];
-                const float fz = __ldg(p.f0 + pp);
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) f[c] = fz;
+    int tile = 0, t = 0;
+    float coef = total_tiles > 0 ? __ldg(p.coef) : 0.f;
+    for (long long q = 0; q < total_tiles; ++q) {
+        const uint32_t s = (uint32_t)q & 1u;
+        // stage s^1 was last read in round q-1, which every thread left through the
+        // __syncthreads() below -> safe to refill it now while round q computes
+        if (tid == 0 && q + 1 < total_tiles) {
+            const int next_tile = tile + 1 == p.n_tiles ? 0 : tile + 1;
+            const uint32_t nb = bar_addr + 8u * (s ^ 1u);
+            mbar_expect_tx(nb, p.tile_bytes);
+            bulk_g2s(stage_addr + (s ^ 1u) * p.tile_bytes,
+                     reinterpret_cast<const unsigned char *>(p.tiles) + (size_t)next_tile * p.tile_bytes, p.tile_bytes, nb);
+        }
+        const int2 info = __ldg(p.tile_info + tile);
+        mbar_wait(bar_addr + 8u * s, (uint32_t)(q >> 1) & 1u);
 
-                const uint2 *ep = p.ell + pp;
-                uint2 e = __ldg(ep);
-                for (int k = 0; k < p.width; ++k) {
-                    uint2 en = e;
-                    if (k + 1 < p.width) en = __ldg(ep + (size_t)(k + 1) * p.n_pad);
-                    const uint32_t w = W[e.y];
-                    const float j2 = u2f(e.x);
+        if (tid < info.y) {
+            const int pp = info.x + tid;
+            const uint32_t sweep = p.sweep_offset + (uint32_t)t;
+            const uint2 *ep = reinterpret_cast<const uint2 *>(stage0 + s * p.tile_bytes) + tid;
+            float f[CPL];
+            const float fz = u2f(ep[(size_t)p.width * nthr].x);
 #pragma unroll
-                    for (int c = 0; c < CPL; ++c)
-                        if (w & (1u << c)) f[c] = __fadd_rn(f[c], j2);
-                    e = en;
-                }
+            for (int c = 0; c < CPL; ++c) f[c] = fz;
 
-                uint32_t neww = 0;
+            // software pipeline: entry / state word of slot k+1 are fetched while slot k's adds
+            // issue (slot `width` is the f0 row, whose nbr field is 0 -> a harmless read)
+            uint2 e = *ep;
+            ep += nthr;
+            uint32_t w = W[e.y];
+#pragma unroll 1
+            for (int k = 0; k < p.width; ++k) {
+                const uint2 en = *ep;
+                ep += nthr;
+                const uint32_t wn = W[en.y];
+                const float j2 = u2f(e.x);
 #pragma unroll
-                for (int c4 = 0; c4 < CPL / 4; ++c4) {
-                    uint32_t r[4];
-                    if (MODE != MODE_SUPPLIED_EXACT)
-                        philox4x32((uint32_t)pp, sweep, blk0 + c4, B200GRBM_STREAM_SWEEP, p, r);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int c = 4 * c4 + j;
-                        float v;
-                        if (MODE == MODE_SUPPLIED_EXACT) {
-                            const int cc = min(chain0 + c, p.chains - 1);
-                            v = __ldg(p.uniforms + ((size_t)t * p.chains + cc) * p.n + pp);
-                        } else {
-                            v = uniform_from_bits(r[j]);
-                        }
-                        if (accept_plus<MODE == MODE_PHILOX_FAST>(f[c], coef, v)) neww |= 1u << c;
-                    }
-                }
-                W[pp] = neww & valid_mask;
+                for (int c = 0; c < CPL; ++c)
+                    if (w & (1u << bitpos<CPL>(c))) f[c] = __fadd_rn(f[c], j2);
+                e = en;
+                w = wn;
             }
-            __syncthreads();
+
+            uint32_t neww = 0;
+#pragma unroll
+            for (int c4 = 0; c4 < CPL / 4; ++c4) {
+                uint32_t r[4];
+                if (MODE != MODE_SUPPLIED_EXACT)
+                    philox4x32((uint32_t)pp, sweep, blk0 + c4, B200GRBM_STREAM_SWEEP, p, r);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = 4 * c4 + j;
+                    float v;
+                    if (MODE == MODE_SUPPLIED_EXACT) {
+                        const int cc = min(chain0 + c, p.chains - 1);
+                        v = __ldg(p.uniforms + ((size_t)t * p.chains + cc) * p.n + pp);
+                    } else {
+                        v = uniform_from_bits(r[j]);
+                    }
+                    if (accept_plus<MODE == MODE_PHILOX_FAST>(f[c], coef, v)) neww |= 1u << bitpos<CPL>(c);
+                }
+            }
+            W[pp] = neww;   // bits of chains beyond nvalid are masked at write-back
+        }
+        __syncthreads();
+        if (++tile == p.n_tiles) {
+            tile = 0;
+            ++t;
+            if (t < p.num_sweeps) coef = __ldg(p.coef + t);
         }
     }
 
     // ---- write back
     for (int pp = tid; pp < p.n; pp += nthr) {
-        const uint32_t w = W[pp];
+        const uint32_t w = kernel_to_dense<CPL>(W[pp]) & dense_mask;
         if (p.packed_out != nullptr) p.packed_out[(size_t)g * p.n_pad + pp] = w;
         if (p.state_out != nullptr) {
             const int node = p.order[pp];
@@ -221,6 +325,12 @@ using namespace b200grbm;
 
 extern "C" int32_t b200grbm_last_launch_count(void) { return g_last_launches; }
 
+extern "C" int64_t b200grbm_sweep_smem_bytes(int32_t n, int32_t ell_width, int32_t threads)
+{
+    const int64_t state = ((int64_t)n * 4 + 127) / 128 * 128;
+    return 128 + state + 2 * (int64_t)(ell_width + 1) * threads * 8;
+}
+
 extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *stream)
 {
     g_last_launches = 0;
@@ -231,15 +341,12 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
         return fail(B200GRBM_EINVAL, "gibbs_sweeps: n=%d chains=%d num_sweeps=%d", a->n, a->chains, a->num_sweeps);
     if (a->n_pad < a->n || a->ell_width <= 0)
         return fail(B200GRBM_EINVAL, "gibbs_sweeps: n_pad=%d < n=%d or ell_width=%d", a->n_pad, a->n, a->ell_width);
-    if (a->n_colours <= 0 || a->n_colours > B200GRBM_MAX_COLOURS)
-        return fail(B200GRBM_EINVAL, "gibbs_sweeps: n_colours=%d not in [1,%d]", a->n_colours, B200GRBM_MAX_COLOURS);
-    if (a->colour_start[0] != 0 || a->colour_start[a->n_colours] != a->n)
-        return fail(B200GRBM_EINVAL, "gibbs_sweeps: colour_start must run from 0 to n");
-    for (int c = 0; c < a->n_colours; ++c)
-        if (a->colour_start[c + 1] < a->colour_start[c])
-            return fail(B200GRBM_EINVAL, "gibbs_sweeps: colour_start not monotone at %d", c);
-    if (a->ell_dev == nullptr || a->f0_dev == nullptr || (a->num_sweeps > 0 && a->coef_dev == nullptr))
-        return fail(B200GRBM_EINVAL, "gibbs_sweeps: ell_dev / f0_dev / coef_dev must not be NULL");
+    if (a->n_tiles <= 0)
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: n_tiles=%d", a->n_tiles);
+    if (a->tiles_dev == nullptr || a->tile_info_dev == nullptr || (a->num_sweeps > 0 && a->coef_dev == nullptr))
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: tiles_dev / tile_info_dev / coef_dev must not be NULL");
+    if ((reinterpret_cast<uintptr_t>(a->tiles_dev) & 15u) != 0)
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: tiles_dev must be 16-byte aligned (bulk copy source)");
     if ((a->state_in_dev != nullptr || a->state_out_dev != nullptr) && a->order_dev == nullptr)
         return fail(B200GRBM_EINVAL, "gibbs_sweeps: order_dev is required for int8 state I/O");
     if (a->threads < 64 || a->threads > 768 || a->threads % 32 != 0)
@@ -259,8 +366,8 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
     B200_TRY(require_device());
 
     SweepParams p;
-    p.ell = reinterpret_cast<const uint2 *>(a->ell_dev);
-    p.f0 = a->f0_dev;
+    p.tiles = reinterpret_cast<const uint2 *>(a->tiles_dev);
+    p.tile_info = reinterpret_cast<const int2 *>(a->tile_info_dev);
     p.order = a->order_dev;
     p.coef = a->coef_dev;
     p.uniforms = a->uniforms_dev;
@@ -271,12 +378,13 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
     p.n = a->n;
     p.n_pad = a->n_pad;
     p.width = a->ell_width;
-    p.n_colours = a->n_colours;
-    for (int c = 0; c <= B200GRBM_MAX_COLOURS; ++c) p.colour_start[c] = c <= a->n_colours ? a->colour_start[c] : a->n;
+    p.n_tiles = a->n_tiles;
     p.chains = a->chains;
     p.num_sweeps = a->num_sweeps;
     p.sweep_offset = a->sweep_offset;
     p.chain_block0 = (uint32_t)(a->chain_offset >> 2);
+    p.state_bytes = (uint32_t)(((size_t)a->n * 4 + 127) / 128 * 128);
+    p.tile_bytes = (uint32_t)((size_t)(a->ell_width + 1) * a->threads * 8);
     uint32_t k0 = (uint32_t)a->seed, k1 = (uint32_t)(a->seed >> 32);
     for (int r = 0; r < B200GRBM_PHILOX_ROUNDS; ++r) {
         p.rk[2 * r] = k0;
@@ -285,13 +393,14 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
         k1 += B200GRBM_PHILOX_W1;
     }
 
-    const size_t smem = sizeof(uint32_t) * (size_t)a->n;
+    const size_t smem = (size_t)b200grbm_sweep_smem_bytes(a->n, a->ell_width, a->threads);
     int dev = 0, smem_optin = 0;
     B200_CUDA(cudaGetDevice(&dev));
     B200_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     if (smem > (size_t)smem_optin)
-        return fail(B200GRBM_EUNSUPPORTED, "gibbs_sweeps: n=%d spins need %zu B of shared memory (> %d)", a->n, smem,
-                    smem_optin);
+        return fail(B200GRBM_EUNSUPPORTED,
+                    "gibbs_sweeps: n=%d width=%d threads=%d need %zu B of shared memory (> %d); use fewer threads",
+                    a->n, a->ell_width, a->threads, smem, smem_optin);
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int groups = (a->chains + a->chains_per_lane - 1) / a->chains_per_lane;
     fn<<<groups, a->threads, smem, (cudaStream_t)stream>>>(p);

@@ -18,7 +18,7 @@ namespace b200grbm {
 
 __global__ void set_edge_weights_kernel(const float *__restrict__ quadratic, int n_edges, float prefactor, float lo,
                                         float hi, const int32_t *__restrict__ slot_a,
-                                        const int32_t *__restrict__ slot_b, uint2 *__restrict__ ell,
+                                        const int32_t *__restrict__ slot_b, uint2 *__restrict__ tiles,
                                         float *__restrict__ j_eff)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -26,14 +26,13 @@ __global__ void set_edge_weights_kernel(const float *__restrict__ quadratic, int
     const float j = fminf(fmaxf(__fmul_rn(prefactor, quadratic[e]), lo), hi);
     if (j_eff != nullptr) j_eff[e] = j;
     const uint32_t j2 = f2u(__fmul_rn(2.0f, j));
-    ell[slot_a[e]].x = j2;
-    ell[slot_b[e]].x = j2;
+    tiles[slot_a[e]].x = j2;
+    tiles[slot_b[e]].x = j2;
 }
 
 __global__ void set_node_weights_kernel(const float *__restrict__ linear, int n, float prefactor, float lo, float hi,
-                                        const int32_t *__restrict__ order, int width, int n_pad,
-                                        const uint2 *__restrict__ ell, float *__restrict__ f0,
-                                        float *__restrict__ h_eff)
+                                        const int32_t *__restrict__ order, const int32_t *__restrict__ row_base,
+                                        int width, int stride, uint2 *__restrict__ tiles, float *__restrict__ h_eff)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -41,9 +40,10 @@ __global__ void set_node_weights_kernel(const float *__restrict__ linear, int n,
     const float h = fminf(fmaxf(__fmul_rn(prefactor, linear[node]), lo), hi);
     if (h_eff != nullptr) h_eff[node] = h;
     float a = h;
+    uint2 *row = tiles + row_base[p];
     // contract order: subtract J_k for k ascending; padded slots hold 2J = 0
-    for (int k = 0; k < width; ++k) a = __fsub_rn(a, __fmul_rn(0.5f, u2f(ell[(size_t)k * n_pad + p].x)));
-    f0[p] = a;
+    for (int k = 0; k < width; ++k) a = __fsub_rn(a, __fmul_rn(0.5f, u2f(row[(size_t)k * stride].x)));
+    row[(size_t)width * stride].x = f2u(a);
 }
 
 // ------------------------------------------------------------------ sign packing
@@ -189,25 +189,25 @@ using namespace b200grbm;
 extern "C" int32_t b200grbm_set_weights(const float *linear_dev, const float *quadratic_dev, int32_t n, int32_t n_edges,
                                         float prefactor, float h_lo, float h_hi, float j_lo, float j_hi,
                                         const int32_t *order_dev, const int32_t *slot_a_dev, const int32_t *slot_b_dev,
-                                        int32_t ell_width, int32_t n_pad, b200grbm_ell_entry *ell_dev, float *f0_dev,
-                                        float *h_eff_dev, float *j_eff_dev, void *stream)
+                                        const int32_t *row_base_dev, int32_t ell_width, int32_t threads,
+                                        b200grbm_ell_entry *tiles_dev, float *h_eff_dev, float *j_eff_dev, void *stream)
 {
-    if (n <= 0 || n_edges < 0 || ell_width <= 0 || n_pad < n)
-        return fail(B200GRBM_EINVAL, "set_weights: n=%d n_edges=%d ell_width=%d n_pad=%d", n, n_edges, ell_width, n_pad);
-    if (!linear_dev || !order_dev || !ell_dev || !f0_dev || (n_edges > 0 && (!quadratic_dev || !slot_a_dev || !slot_b_dev)))
+    if (n <= 0 || n_edges < 0 || ell_width <= 0 || threads <= 0)
+        return fail(B200GRBM_EINVAL, "set_weights: n=%d n_edges=%d ell_width=%d threads=%d", n, n_edges, ell_width, threads);
+    if (!linear_dev || !order_dev || !row_base_dev || !tiles_dev ||
+        (n_edges > 0 && (!quadratic_dev || !slot_a_dev || !slot_b_dev)))
         return fail(B200GRBM_EINVAL, "set_weights: NULL pointer argument");
     if (!(h_lo <= h_hi) || !(j_lo <= j_hi)) return fail(B200GRBM_EINVAL, "set_weights: empty clipping range");
     B200_TRY(require_device());
     cudaStream_t st = (cudaStream_t)stream;
+    uint2 *tiles = reinterpret_cast<uint2 *>(tiles_dev);
     if (n_edges > 0) {
         set_edge_weights_kernel<<<(n_edges + 255) / 256, 256, 0, st>>>(quadratic_dev, n_edges, prefactor, j_lo, j_hi,
-                                                                      slot_a_dev, slot_b_dev,
-                                                                      reinterpret_cast<uint2 *>(ell_dev), j_eff_dev);
+                                                                      slot_a_dev, slot_b_dev, tiles, j_eff_dev);
         B200_CUDA(cudaGetLastError());
     }
-    set_node_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(linear_dev, n, prefactor, h_lo, h_hi, order_dev, ell_width,
-                                                            n_pad, reinterpret_cast<const uint2 *>(ell_dev), f0_dev,
-                                                            h_eff_dev);
+    set_node_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(linear_dev, n, prefactor, h_lo, h_hi, order_dev,
+                                                            row_base_dev, ell_width, threads, tiles, h_eff_dev);
     B200_CUDA(cudaGetLastError());
     return 0;
 }

@@ -26,7 +26,8 @@ import torch
 from . import _lib
 from .topology import IsingGraph
 
-__all__ = ["BlockGibbsSampler", "SampleSet", "DeviceGraph", "plan_launch", "beta_schedule"]
+__all__ = ["BlockGibbsSampler", "SampleSet", "DeviceGraph", "plan_launch", "plan_threads", "sweep_smem_bytes",
+           "beta_schedule"]
 
 _LOG2E = 1.4426950408889634
 SUPPORTED_CPL = (16, 24, 28, 32)
@@ -44,29 +45,52 @@ def _splitmix64(x: int) -> int:
     return z ^ (z >> 31)
 
 
-def plan_launch(chains: int, colour_sizes: Sequence[int], sm_count: int = 148) -> tuple[int, int]:
+SMEM_LIMIT = 227 * 1024  # opt-in shared memory per CTA on sm_100
+
+
+def sweep_smem_bytes(n: int, ell_width: int, threads: int) -> int:
+    """Dynamic shared memory of one sweep CTA: 2 mbarriers + state words + 2 tile stages
+    (mirrors b200grbm_sweep_smem_bytes, include/b200grbm.h)."""
+    return 128 + (n * 4 + 127) // 128 * 128 + 2 * (ell_width + 1) * threads * 8
+
+
+def plan_threads(colour_sizes: Sequence[int], n: int, ell_width: int, smem_limit: int = SMEM_LIMIT) -> int:
+    """CTA size for the colour-round loop: the multiple of 32 in [64, 768] that maximises lane
+    occupancy ``min_c n_c / (ceil(n_c / T) T)`` among those whose two tile stages fit in shared
+    memory (P16: 1410 spins per colour -> 736 threads, 2 rounds, 95.8 %; ties -> more threads,
+    which hides more latency)."""
+    sizes = [s for s in colour_sizes if s > 0] or [1]
+    best = None
+    for t in range(64, 768 + 1, 32):
+        if sweep_smem_bytes(n, ell_width, t) > smem_limit:
+            break
+        eff = min(s / (-(-s // t) * t) for s in sizes)
+        # prefer >= 256 threads unless the graph is tiny; then efficiency, then size
+        score = (min(t, 256), round(eff, 2), t)
+        if best is None or score > best[0]:
+            best = (score, t)
+    if best is None:
+        raise ValueError(f"graph with {n} spins and degree {ell_width} does not fit the sweep kernel's shared memory")
+    return best[1]
+
+
+def plan_launch(chains: int, colour_sizes: Sequence[int], sm_count: int = 148, n: int = 0,
+                ell_width: int = 15) -> tuple[int, int]:
     """Pick ``(chains_per_lane, threads)`` for a sweep launch.
 
     One CTA owns ``chains_per_lane`` chains and an SM runs one CTA at a time, so the launch
     takes ``ceil(groups / sm_count)`` waves of work proportional to ``chains_per_lane``;
     minimise their product (4096 chains on 148 SMs: 28 -> 147 CTAs in one wave, 12.5 % less
-    work per SM than 32 -> 128 CTAs).  ``threads`` maximises lane occupancy of the
-    colour-block loop (P16: 1410 spins per colour -> 480 threads, 3 rounds, 97.9 %).
+    work per SM than 32 -> 128 CTAs).  Ties go to 28, whose 7-bits-per-byte state layout
+    needs the fewest predicate moves per neighbour.
     """
     best = None
-    for cpl in SUPPORTED_CPL:
+    for cpl in (28, 32, 24, 16):
         groups = -(-chains // cpl)
         cost = -(-groups // max(sm_count, 1)) * cpl
-        if best is None or cost < best[0] or (cost == best[0] and cpl > best[1]):
+        if best is None or cost < best[0]:
             best = (cost, cpl)
-    cpl = best[1]
-    sizes = [s for s in colour_sizes if s > 0] or [1]
-    best_t = None
-    for t in range(128, 768 + 1, 32):
-        eff = min(s / (-(-s // t) * t) for s in sizes)
-        if best_t is None or eff > best_t[0] + 1e-9 or (abs(eff - best_t[0]) <= 1e-9 and t > best_t[1]):
-            best_t = (eff, t)
-    return cpl, best_t[1]
+    return best[1], plan_threads(colour_sizes, n or sum(colour_sizes), ell_width)
 
 
 def beta_schedule(num_sweeps: int, beta_range: Optional[Sequence[float]] = None,
@@ -132,30 +156,78 @@ class SampleSet:
         return cls(variables, record=_Record(arr, energy))
 
 
+class _TileSet:
+    """Sampler tables of one graph for one CTA size (layout: include/b200grbm.h)."""
+
+    def __init__(self, graph: IsingGraph, threads: int, device: torch.device):
+        g, T, W = graph, threads, graph.ell_width
+        info = []
+        for c in range(g.n_colours):
+            lo, hi = int(g.colour_start[c]), int(g.colour_start[c + 1])
+            for first in range(lo, hi, T):
+                info.append((first, min(T, hi - first)))
+        self.threads = T
+        self.n_tiles = len(info)
+        tile_of = np.empty(g.n, dtype=np.int64)
+        lane_of = np.empty(g.n, dtype=np.int64)
+        for t, (first, cnt) in enumerate(info):
+            tile_of[first:first + cnt] = t
+            lane_of[first:first + cnt] = np.arange(cnt)
+        row_base = tile_of * (W + 1) * T + lane_of                      # entry index of slot k = 0
+        tiles = np.zeros((self.n_tiles, W + 1, T, 2), dtype=np.int32)
+        p = np.arange(g.n)
+        for k in range(W):
+            tiles[tile_of, k, lane_of, 1] = g.ell_nbr[k, p]
+        ka, pa = np.divmod(g.slot_a.astype(np.int64), g.n_pad)
+        kb, pb = np.divmod(g.slot_b.astype(np.int64), g.n_pad)
+        i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
+        self.tiles = torch.from_numpy(tiles).to(device)
+        self.tile_info = i32(np.asarray(info, dtype=np.int32).reshape(-1, 2))
+        self.row_base = i32(row_base)
+        self.slot_a = i32(row_base[pa] + ka * T)
+        self.slot_b = i32(row_base[pb] + kb * T)
+        self.version = -1
+        assert self.tiles.data_ptr() % 16 == 0
+
+
 class DeviceGraph:
-    """Device-resident sampler tables of one :class:`IsingGraph` (see include/b200grbm.h)."""
+    """Device-resident structure and weights of one :class:`IsingGraph`."""
 
     def __init__(self, graph: IsingGraph, device: torch.device):
         self.graph = graph
         self.device = torch.device(device)
-        g = graph
-        ell = np.zeros((g.ell_width, g.n_pad, 2), dtype=np.int32)
-        ell[:, :, 1] = g.ell_nbr
-        dev = self.device
-        self.ell_nbr_template = torch.from_numpy(ell).to(dev)
-        self.ell = self.ell_nbr_template.clone()
-        self.f0 = torch.zeros(g.n, dtype=torch.float32, device=dev)
+        g, dev = graph, self.device
+        self.default_threads = plan_threads(np.diff(g.colour_start).tolist(), g.n, g.ell_width)
         self.h_eff = torch.zeros(g.n, dtype=torch.float32, device=dev)
         self.j_eff = torch.zeros(max(g.n_edges, 1), dtype=torch.float32, device=dev)
         i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
         self.order, self.pos = i32(g.order), i32(g.pos)
-        self.slot_a, self.slot_b = i32(g.slot_a), i32(g.slot_b)
         self.edge_i, self.edge_j = i32(g.edge_i), i32(g.edge_j)
         self.edge_pi, self.edge_pj = i32(g.pos[g.edge_i]), i32(g.pos[g.edge_j])
+        self._tilesets: dict[int, _TileSet] = {}
+        self._version = 0
+
+    def _tileset(self, threads: int) -> _TileSet:
+        ts = self._tilesets.get(threads)
+        if ts is None:
+            ts = self._tilesets[threads] = _TileSet(self.graph, threads, self.device)
+        return ts
+
+    def _write(self, ts: _TileSet, linear, quadratic, prefactor, h_lo, h_hi, j_lo, j_hi, h_out, j_out) -> None:
+        g = self.graph
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.b200grbm_set_weights(
+                _lib.ptr(linear), _lib.ptr(quadratic) if g.n_edges else None, g.n, g.n_edges, float(prefactor),
+                h_lo, h_hi, j_lo, j_hi, _lib.ptr(self.order), _lib.ptr(ts.slot_a) if g.n_edges else None,
+                _lib.ptr(ts.slot_b) if g.n_edges else None, _lib.ptr(ts.row_base), g.ell_width, ts.threads,
+                _lib.ptr(ts.tiles), _lib.ptr(h_out), _lib.ptr(j_out), _lib.current_stream(self.device)))
 
     def set_weights(self, linear: torch.Tensor, quadratic: torch.Tensor, prefactor: float = 1.0,
                     linear_range: Optional[Sequence[float]] = None,
                     quadratic_range: Optional[Sequence[float]] = None) -> None:
+        """h_eff = clip(prefactor * linear), J_eff = clip(prefactor * quadratic) on the device,
+        written into the tables of the default CTA size."""
         g = self.graph
         if linear.shape != (g.n,) or quadratic.shape != (g.n_edges,):
             raise ValueError(f"expected linear ({g.n},) and quadratic ({g.n_edges},), got "
@@ -165,14 +237,20 @@ class DeviceGraph:
         inf = float("inf")
         h_lo, h_hi = (-inf, inf) if linear_range is None else map(float, linear_range)
         j_lo, j_hi = (-inf, inf) if quadratic_range is None else map(float, quadratic_range)
-        self.ell.copy_(self.ell_nbr_template)
-        lib = _lib.load()
-        with torch.cuda.device(self.device):
-            _lib.check(lib.b200grbm_set_weights(
-                _lib.ptr(linear), _lib.ptr(quadratic) if g.n_edges else None, g.n, g.n_edges, float(prefactor),
-                h_lo, h_hi, j_lo, j_hi, _lib.ptr(self.order), _lib.ptr(self.slot_a) if g.n_edges else None,
-                _lib.ptr(self.slot_b) if g.n_edges else None, g.ell_width, g.n_pad, _lib.ptr(self.ell),
-                _lib.ptr(self.f0), _lib.ptr(self.h_eff), _lib.ptr(self.j_eff), _lib.current_stream(self.device)))
+        ts = self._tileset(self.default_threads)
+        self._write(ts, linear, quadratic, prefactor, h_lo, h_hi, j_lo, j_hi, self.h_eff, self.j_eff)
+        self._version += 1
+        ts.version = self._version
+
+    def tiles(self, threads: Optional[int] = None) -> _TileSet:
+        """Tables for ``threads`` holding the current weights (other CTA sizes are refreshed
+        from h_eff / J_eff: prefactor 1 and no clipping reproduce the values bit for bit)."""
+        ts = self._tileset(threads or self.default_threads)
+        if ts.version != self._version:
+            inf = float("inf")
+            self._write(ts, self.h_eff, self.j_eff, 1.0, -inf, inf, -inf, inf, None, None)
+            ts.version = self._version
+        return ts
 
 
 class BlockGibbsSampler:
@@ -337,16 +415,19 @@ class BlockGibbsSampler:
         if seed is None:
             seed = _splitmix64(self.seed + self._calls)
         self._calls += 1
-        sizes = np.diff(g.colour_start).tolist()
-        cpl, threads = plan if plan is not None else plan_launch(num_reads, sizes, _lib.device_info()["sm_count"])
+        if plan is not None:
+            cpl, threads = plan
+        else:
+            cpl = plan_launch(num_reads, np.diff(g.colour_start).tolist(), _lib.device_info()["sm_count"], g.n,
+                              g.ell_width)[0]
+            threads = dg.default_threads
         self.last_plan = (cpl, threads)
+        ts = dg.tiles(threads)
 
         a = _lib.SweepArgs()
         a.struct_size = C.sizeof(_lib.SweepArgs)
-        a.n, a.n_pad, a.ell_width, a.n_colours = g.n, g.n_pad, g.ell_width, g.n_colours
-        for k, v in enumerate(g.colour_start.tolist()):
-            a.colour_start[k] = v
-        a.ell_dev, a.f0_dev, a.order_dev = _lib.ptr(dg.ell), _lib.ptr(dg.f0), _lib.ptr(dg.order)
+        a.n, a.n_pad, a.ell_width, a.n_tiles = g.n, g.n_pad, g.ell_width, ts.n_tiles
+        a.tiles_dev, a.tile_info_dev, a.order_dev = _lib.ptr(ts.tiles), _lib.ptr(ts.tile_info), _lib.ptr(dg.order)
         a.chains, a.chains_per_lane, a.threads = int(num_reads), cpl, threads
         a.accept = _lib.ACCEPT_FAST if self.accept == "fast" else _lib.ACCEPT_EXACT
         a.chain_offset, a.seed = self.chain_offset, int(seed) & 0xFFFFFFFFFFFFFFFF

@@ -32,8 +32,6 @@ extern "C" {
 #define B200GRBM_EUNSUPPORTED (-2) /* configuration not compiled in (e.g. chains_per_lane) */
 #define B200GRBM_ENODEVICE (-3) /* no sm_100 device */
 
-#define B200GRBM_MAX_COLOURS 16
-
 /* acceptance rule of the heat-bath draw (include/b200grbm_spec.h) */
 #define B200GRBM_ACCEPT_EXACT 0 /* contract polynomial: bit-reproducible on the CPU oracle */
 #define B200GRBM_ACCEPT_FAST 1  /* MUFU.EX2: same law, statistical parity only */
@@ -50,35 +48,43 @@ int32_t b200grbm_abi_version(void);
 int32_t b200grbm_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int32_t *smem_optin);
 
 /*
- * Effective Ising parameters and sampler tables from the GRBM parameters.
- * Replaces the parameter preparation inside GraphRestrictedBoltzmannMachine.sample
- * (third-party; call sites src/model_wrapper.py:309-316, :369-376,
- * src/utils/persistent_qpu_sampler.py:71-78): h = clip(prefactor * linear, linear_range),
- * J = clip(prefactor * quadratic, quadratic_range) -- done on device so the step never
- * round-trips the parameters through Python dicts.
- *   ell_dev    [ell_width][n_pad] entries, .nbr pre-filled by the host layer; .j2_bits written here
- *   f0_dev     [n]  h_eff - sum_k J_eff (contract order), visit-position order
- *   h_eff_dev  [n]  node order (optional, may be NULL);  j_eff_dev [n_edges] (optional)
+ * Sampler tables ("tiles").  The sweep kernel streams, per colour round, one contiguous tile
+ * of (ell_width + 1) x threads 8-byte entries through shared memory with the bulk-copy engine:
+ *   tile[k][lane]          k < ell_width : { fp32 bits of 2*J_eff, neighbour visit position }
+ *   tile[ell_width][lane]                : { fp32 bits of f0 = h_eff - sum_k J_eff, unused }
+ * where lane = (visit position - first position of the round).  tile_info[t] = { first visit
+ * position, number of spins } of round t; rounds never straddle a colour boundary.  The host
+ * layer builds the .nbr fields and tile_info once per (graph, threads); the values are written
+ * by b200grbm_set_weights.
+ *
+ * b200grbm_set_weights: effective Ising parameters from the GRBM parameters.  Replaces the
+ * parameter preparation inside GraphRestrictedBoltzmannMachine.sample (third-party; call
+ * sites src/model_wrapper.py:309-316, :369-376, src/utils/persistent_qpu_sampler.py:71-78):
+ * h = clip(prefactor * linear, linear_range), J = clip(prefactor * quadratic, quadratic_range)
+ * -- on device, so a training step never round-trips the parameters through Python dicts.
+ *   slot_a/slot_b [n_edges]  flat entry index of the two tile slots carrying edge e
+ *   row_base      [n]        flat entry index of slot k = 0 of visit position p (slot k is
+ *                            row_base[p] + k * threads)
+ *   h_eff_dev [n] node order (optional);  j_eff_dev [n_edges] (optional)
  */
 int32_t b200grbm_set_weights(const float *linear_dev, const float *quadratic_dev, int32_t n, int32_t n_edges,
                              float prefactor, float h_lo, float h_hi, float j_lo, float j_hi,
                              const int32_t *order_dev, const int32_t *slot_a_dev, const int32_t *slot_b_dev,
-                             int32_t ell_width, int32_t n_pad, b200grbm_ell_entry *ell_dev, float *f0_dev,
-                             float *h_eff_dev, float *j_eff_dev, void *stream);
+                             const int32_t *row_base_dev, int32_t ell_width, int32_t threads,
+                             b200grbm_ell_entry *tiles_dev, float *h_eff_dev, float *j_eff_dev, void *stream);
 
 typedef struct b200grbm_sweep_args {
     uint32_t struct_size;      /* sizeof(b200grbm_sweep_args) */
     int32_t n;                 /* spins */
-    int32_t n_pad;             /* row pitch of the ELL tables and of packed state */
-    int32_t ell_width;
-    int32_t n_colours;
-    int32_t colour_start[B200GRBM_MAX_COLOURS + 1]; /* visit positions of each colour block */
-    const b200grbm_ell_entry *ell_dev;
-    const float *f0_dev;
+    int32_t n_pad;             /* row pitch of packed state */
+    int32_t ell_width;         /* neighbour slots per spin (max degree) */
+    int32_t n_tiles;           /* colour rounds per sweep */
+    const b200grbm_ell_entry *tiles_dev; /* [n_tiles][ell_width + 1][threads], 16-byte aligned */
+    const int32_t *tile_info_dev;        /* [n_tiles][2] */
     const int32_t *order_dev;  /* [n] node visited at position p (for int8 node-order I/O) */
     int32_t chains;            /* chains in this call */
     int32_t chains_per_lane;   /* 16, 24, 28 or 32: chains bit-packed per state word */
-    int32_t threads;           /* CTA size, multiple of 32 in [64, 768] */
+    int32_t threads;           /* CTA size the tiles were built for, multiple of 32 in [64, 768] */
     int32_t accept;            /* B200GRBM_ACCEPT_* */
     uint64_t chain_offset;     /* global id of chain 0 of this call (multiple of 4) */
     uint64_t seed;
@@ -87,7 +93,7 @@ typedef struct b200grbm_sweep_args {
     const float *coef_dev;     /* [num_sweeps] (float)(2 beta log2 e) */
     const float *uniforms_dev; /* NULL -> Philox; else [num_sweeps][chains][n] visit-position order */
     const int8_t *state_in_dev;   /* [chains][n] node order, +-1; NULL -> packed_in or random init */
-    const uint32_t *packed_in_dev; /* [groups][n_pad] visit-position order; NULL -> random init */
+    const uint32_t *packed_in_dev; /* [groups][n_pad] visit-position order, bit c = chain c; NULL -> random init */
     int8_t *state_out_dev;     /* optional */
     uint32_t *packed_out_dev;  /* optional */
 } b200grbm_sweep_args;
@@ -98,6 +104,9 @@ typedef struct b200grbm_sweep_args {
  * Runs num_sweeps colour-blocked heat-bath sweeps on `chains` independent chains.
  */
 int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *args, void *stream);
+
+/* dynamic shared memory a sweep launch needs (state + 2 tile stages); must fit the device's opt-in limit */
+int64_t b200grbm_sweep_smem_bytes(int32_t n, int32_t ell_width, int32_t threads);
 
 /* number of kernel launches the last b200grbm_gibbs_sweeps call on this thread enqueued */
 int32_t b200grbm_last_launch_count(void);
@@ -139,6 +148,33 @@ int32_t b200grbm_energy_backward(const float *x_dev, const float *grad_energy_de
 int32_t b200grbm_energy_i8(const int8_t *s_dev, int32_t rows, int32_t n, int32_t n_edges,
                            const int32_t *edge_i_dev, const int32_t *edge_j_dev, const float *h_dev,
                            const float *j_dev, double *energy_dev, void *stream);
+
+/*
+ * maximum_mean_discrepancy_loss(x, y, GaussianKernel(n_kernels)) -- third-party
+ * dwave-pytorch-plugin; call site src/model_wrapper.py:320 (kernel built :273); formulas
+ * static/eq3.png / static/eq4.png (README.md:114-129); recollected code form SURVEY.md
+ * Appendix A.3.  z_dev holds the stacked rows [x; y] (m = m_x + m_y rows, d features).
+ *   t_ab  = ||z_a - z_b||  (squared != 0: ||.||^2)
+ *   bw    = bandwidth > 0 ? bandwidth : sum_ab t_ab / (m^2 - m)
+ *   k_ab  = sum_u exp(-t_ab / (bw * mul_factor^(u - n_kernels/2)))
+ * forward writes sums_dev[4] = { sum_{a,b in x} k, sum_{a,b in y} k, sum_{a in x, b in y} k,
+ * sum_ab t_ab } (diagonals included; the host layer forms the biased / unbiased estimate).
+ * The fp32 entry points run on CUDA cores with directly accumulated differences (any real
+ * input); the i8 entry point runs the Gram contraction of +-1 rows on tcgen05 tensor cores
+ * (int8 x int8 -> int32, exact).
+ */
+int32_t b200grbm_mmd_forward_f32(const float *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t n_kernels,
+                                 float mul_factor, int32_t squared, float bandwidth, double *sums_dev, void *stream);
+/*
+ * d(loss)/dx for loss = w_xx' * S_xx + ... : coef_dev [m_x][m] workspace receives
+ * grad_out * w * (dk/dt) * (dt/d||.||) per pair (w = w_xx for x-x pairs, w_xy for x-y pairs,
+ * both including the factor 2 of the symmetric sum), then
+ * grad_x[a] = sum_b coef_ab (x_a - z_b).  sums_dev[3] must still hold the forward's distance sum.
+ */
+int32_t b200grbm_mmd_backward_f32(const float *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t n_kernels,
+                                  float mul_factor, int32_t squared, float bandwidth, const double *sums_dev,
+                                  float w_xx, float w_xy, const float *grad_out_dev, float *coef_dev,
+                                  float *grad_x_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -45,9 +45,8 @@ def test_compute_calls_fail_loudly_without_a_gpu():
     a.struct_size = C.sizeof(_lib.SweepArgs)
     a.n = a.n_pad = 32
     a.ell_width = 1
-    a.n_colours = 1
-    a.colour_start[1] = 32
-    a.ell_dev = a.f0_dev = a.coef_dev = 1  # never dereferenced: device check comes first
+    a.n_tiles = 1
+    a.tiles_dev = a.tile_info_dev = a.coef_dev = 16  # never dereferenced: device check comes first
     a.chains, a.chains_per_lane, a.threads, a.num_sweeps = 4, 32, 128, 1
     rc = lib.b200grbm_gibbs_sweeps(C.byref(a), None)
     assert rc != 0
@@ -62,12 +61,25 @@ def test_argument_validation_happens_before_any_launch():
     a.struct_size = 3
     assert lib.b200grbm_gibbs_sweeps(C.byref(a), None) == -1
     a.struct_size = C.sizeof(_lib.SweepArgs)
-    a.n, a.n_pad, a.ell_width, a.n_colours, a.chains, a.num_sweeps = 8, 8, 1, 1, 4, 1
-    a.colour_start[1] = 8
-    a.ell_dev = a.f0_dev = a.coef_dev = 1
+    a.n, a.n_pad, a.ell_width, a.n_tiles, a.chains, a.num_sweeps = 8, 8, 1, 1, 4, 1
+    a.tiles_dev = a.tile_info_dev = a.coef_dev = 16
     a.chains_per_lane, a.threads = 30, 128
     assert lib.b200grbm_gibbs_sweeps(C.byref(a), None) == -2      # unsupported chains_per_lane
     a.chains_per_lane, a.threads = 32, 100
     assert lib.b200grbm_gibbs_sweeps(C.byref(a), None) == -1      # threads not a multiple of 32
     a.threads, a.chain_offset = 128, 2
     assert lib.b200grbm_gibbs_sweeps(C.byref(a), None) == -1      # chain_offset not a multiple of 4
+    a.chain_offset, a.tiles_dev = 0, 8
+    assert lib.b200grbm_gibbs_sweeps(C.byref(a), None) == -1      # bulk-copy source must be 16-byte aligned
+    assert b"16-byte" in lib.b200grbm_last_error()
+
+
+def test_sweep_smem_formula_matches_library():
+    from image_generation_b200.sampler import plan_threads, sweep_smem_bytes
+    lib = _lib.load()
+    for n, w, t in ((5640, 15, 736), (7440, 20, 480), (256, 20, 128), (9, 2, 64)):
+        assert lib.b200grbm_sweep_smem_bytes(n, w, t) == sweep_smem_bytes(n, w, t)
+    # the planner never exceeds the 227 KB opt-in limit
+    for n, w, sizes in ((5640, 15, [1410] * 4), (7440, 20, [1860] * 4), (50000, 20, [12500] * 4)):
+        t = plan_threads(sizes, n, w)
+        assert sweep_smem_bytes(n, w, t) <= 227 * 1024 and t % 32 == 0

@@ -31,7 +31,7 @@ def test_golden_energies_through_the_module(cuda_device, golden):
         grbm, ei, ej = _grbm_from_checkpoint(golden, name, cuda_device)
         idx = torch.arange(256)
         pats = torch.stack([torch.ones(256), torch.where(idx % 2 == 0, 1.0, -1.0), torch.where(idx % 3 == 0, 1.0, -1.0)])
-        got = grbm(pats.to(cuda_device)).cpu().numpy()
+        got = grbm(pats.to(cuda_device)).detach().cpu().numpy()
         want = [m["energies"]["all_plus"], m["energies"]["even_plus"], m["energies"]["mod3_plus"]]
         np.testing.assert_allclose(got, want, rtol=1e-5)
 
