@@ -1,0 +1,461 @@
+// Mixture-of-RBF MMD for +-1 rows: Gram contraction on tcgen05 tensor cores (sm_100a).
+//
+// Replaces the stock  cat -> cdist -> exp x 7 -> block means  behind
+// maximum_mean_discrepancy_loss(x, y, GaussianKernel(7))  (third-party dwave-pytorch-plugin,
+// call site src/model_wrapper.py:320; SURVEY.md section 8 rows a7/a8, config cfg3:
+// 8192 encoder latents vs 8192 GRBM samples, D = 5640).
+//
+// For +-1 rows  ||a - b||^2 = 4 * Hamming(a, b) = 2 (D - a.b),  so every kernel value is a
+// function of the integer Gram entry.  The kernel therefore
+//   * stages 128 x 128-byte boxes of the int8 sample matrix Z = [x; y] with TMA
+//     (cp.async.bulk.tensor, 128B swizzle) through a 4-stage mbarrier ring,
+//   * contracts them with tcgen05.mma.kind::i8 (int8 x int8 -> int32, exact) into a
+//     128 x 256 accumulator tile in TMEM (two accumulator stages = all 512 columns, so the
+//     epilogue of tile t overlaps the MMAs of tile t+1),
+//   * and in the epilogue maps each Gram entry through a (D+1)-entry look-up table held in
+//     shared memory -- LUT[h] = distance (pass 1, for the data-dependent bandwidth) or
+//     sum_u exp(-t_h / (bw * mult_u)) (pass 2), computed once in float64 -- and reduces the
+//     xx / yy / xy block sums in registers.  Nothing of size m^2 touches HBM.
+// Only the upper triangle of 128 x 256 tiles is visited (the kernel matrix is symmetric).
+//
+// Warp roles (320 threads, one persistent CTA per SM): warp 0 lane 0 = TMA producer,
+// warp 1 = TMEM allocator + (lane 0) MMA issuer, warps 2..9 = epilogue (two column halves x
+// four TMEM lane quarters).
+#include "common.cuh"
+
+#include <cuda.h>
+
+namespace b200grbm {
+
+constexpr int BM = 128;             // accumulator rows   (UMMA M)
+constexpr int BN = 256;             // accumulator columns (UMMA N)
+constexpr int BK = 128;             // bytes (= int8 elements) per k-block: one 128B swizzle row
+constexpr int UMMA_K = 32;          // int8 elements per tcgen05.mma
+constexpr int A_BYTES = BM * BK;    // 16 KB
+constexpr int B_BYTES = BN * BK;    // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int TC_THREADS = 320;
+constexpr int EPI_WARPS = 8;
+constexpr uint32_t TMEM_COLS = 512;
+
+enum { TC_PASS_DIST = 0, TC_PASS_KERNEL = 1 };
+
+struct TcParams {
+    int m_x, m, d;
+    int n_kblocks;
+    int tiles_m, tiles_n, j0, p0, total_tiles;
+    int stages;
+    int pass;
+    const float *lut;   // [d + 1]
+    double *sums;       // [4]
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();   // a broken pipeline must fail the launch, never hang the GPU
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+}
+
+// K-major operand, 128-byte swizzle: rows are 128 B apart, 8-row groups 1024 B apart (SBO),
+// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.  (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::i8: D = S32, A = B = signed int8, both K-major
+__device__ __forceinline__ constexpr uint32_t umma_idesc_i8(int m, int n)
+{
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// upper-triangle tile enumeration: column tile j ascending, row tiles i = 0 .. min(tiles_m, 2j+2) - 1
+__device__ __forceinline__ void tile_coords(const TcParams &p, int t, int &i, int &j)
+{
+    if (t < p.p0) {
+        j = (int)((sqrtf(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((j + 1) * (j + 2) <= t) ++j;
+        while (j * (j + 1) > t) --j;
+        i = t - j * (j + 1);
+    } else {
+        const int r = t - p.p0;
+        j = p.j0 + r / p.tiles_m;
+        i = r % p.tiles_m;
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                    const TcParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // 128B-swizzled TMA boxes / UMMA descriptors need 1024-byte aligned stages: align by hand
+    // (the launch reserves 1024 spare bytes)
+    unsigned char *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+    unsigned char *stage_base = smem;                                        // S x 48 KB, 1024-aligned
+    float *lut = reinterpret_cast<float *>(smem + (size_t)S * STAGE_BYTES);  // d + 1 floats
+    const size_t lut_bytes = ((size_t)(p.d + 1) * 4 + 15) / 16 * 16;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE_BYTES + lut_bytes);
+    // bars: full[S], empty[S], tmem_full[2], tmem_empty[2]; then the TMEM base address
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 4);
+    const uint32_t full0 = smem_addr(bars), empty0 = full0 + 8u * S, tfull0 = empty0 + 8u * S, tempty0 = tfull0 + 16u;
+    __shared__ double red[3][EPI_WARPS];
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { bar_init(full0 + 8u * s, 1); bar_init(empty0 + 8u * s, 1); }
+        for (int a = 0; a < 2; ++a) { bar_init(tfull0 + 8u * a, 1); bar_init(tempty0 + 8u * a, EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int k = threadIdx.x; k <= p.d; k += blockDim.x) lut[k] = p.lut[k];
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                int ti, tj;
+                tile_coords(p, t, ti, tj);
+                for (int kb = 0; kb < p.n_kblocks; ++kb) {
+                    bar_wait(empty0 + 8u * s, ph ^ 1u);
+                    const uint32_t fb = full0 + 8u * s;
+                    const uint32_t a_dst = smem_addr(stage_base + (size_t)s * STAGE_BYTES);
+                    bar_expect_tx(fb, STAGE_BYTES);
+                    tma_load_2d(a_dst, &tmap, kb * BK, ti * BM, fb);
+                    tma_load_2d(a_dst + A_BYTES, &tmap, kb * BK, tj * BN, fb);
+                    tma_load_2d(a_dst + A_BYTES + A_BYTES, &tmap, kb * BK, tj * BN + 128, fb);
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_i8(BM, BN);
+            int s = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+                const uint32_t acc = (uint32_t)it & 1u, acc_ph = ((uint32_t)it >> 1) & 1u;
+                bar_wait(tempty0 + 8u * acc, acc_ph ^ 1u);          // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.n_kblocks; ++kb) {
+                    bar_wait(full0 + 8u * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_addr(stage_base + (size_t)s * STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_sw128(a_addr);
+                    const uint64_t bdesc = umma_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)       // +32 bytes inside the swizzle row = +2 in the address field
+                        umma_i8(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(empty0 + 8u * s);                    // frees the smem stage when the MMAs retire
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(tfull0 + 8u * acc);                      // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> LUT -> block sums =====================
+        const int ew = warp - 2;                 // 0..7
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                // column half of the accumulator
+        double s_xx = 0.0, s_yy = 0.0, s_xy = 0.0;
+        const int two_d = 2 * p.d;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            int ti, tj;
+            tile_coords(p, t, ti, tj);
+            const uint32_t acc = (uint32_t)it & 1u, acc_ph = ((uint32_t)it >> 1) & 1u;
+            const int row0 = ti * BM, col0 = tj * BN;
+            const int row = row0 + quarter * 32 + lane;
+            const bool strict_upper = ti < 2 * tj;          // every column of the tile is right of every row
+            const bool rows_x = row0 + BM <= p.m_x, rows_y = row0 >= p.m_x;
+            const bool cols_x = col0 + BN <= p.m_x, cols_y = col0 >= p.m_x;
+            const bool pure = strict_upper && (row0 + BM <= p.m) && (col0 + BN <= p.m) && (rows_x || rows_y) &&
+                              (cols_x || cols_y);
+            bar_wait(tfull0 + 8u * acc, acc_ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float a_xx = 0.f, a_yy = 0.f, a_xy = 0.f;
+#pragma unroll 1
+            for (int chunk = 0; chunk < 4; ++chunk) {
+                uint32_t v[32];
+                const int cbase = half * 128 + chunk * 32;
+                __syncwarp();                                   // tcgen05.ld is .sync.aligned
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + (uint32_t)cbase, v);
+                if (pure) {
+                    float part = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) part += lut[(two_d - 2 * (int)v[c]) >> 2];
+                    a_xx += part;            // sorted into its block after the loop
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int col = col0 + cbase + c;
+                        if (row < p.m && col < p.m && col >= row) {
+                            const float kv = lut[(two_d - 2 * (int)v[c]) >> 2];
+                            const bool rx = row < p.m_x, cx = col < p.m_x;
+                            const float w = col == row ? 1.f : 2.f;
+                            if (p.pass == TC_PASS_DIST) a_xx += w * kv;
+                            else if (rx && cx) a_xx += w * kv;
+                            else if (!rx && !cx) a_yy += w * kv;
+                            else a_xy += kv;
+                        }
+                    }
+                }
+            }
+            // accumulator drained: hand the TMEM stage back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) bar_arrive(tempty0 + 8u * acc);
+            if (pure) {
+                const double v2 = 2.0 * (double)a_xx;
+                if (p.pass == TC_PASS_DIST) s_xx += v2;
+                else if (rows_x && cols_x) s_xx += v2;
+                else if (rows_y && cols_y) s_yy += v2;
+                else s_xy += (double)a_xx;
+            } else {
+                s_xx += (double)a_xx; s_yy += (double)a_yy; s_xy += (double)a_xy;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s_xx += __shfl_xor_sync(0xffffffffu, s_xx, o);
+            s_yy += __shfl_xor_sync(0xffffffffu, s_yy, o);
+            s_xy += __shfl_xor_sync(0xffffffffu, s_xy, o);
+        }
+        if (lane == 0) { red[0][ew] = s_xx; red[1][ew] = s_yy; red[2][ew] = s_xy; }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double tot = 0.0;
+        for (int w = 0; w < EPI_WARPS; ++w) tot += red[threadIdx.x][w];
+        if (p.pass == TC_PASS_DIST) { if (threadIdx.x == 0) atomicAdd(p.sums + 3, tot); }
+        else if (tot != 0.0) atomicAdd(p.sums + threadIdx.x, tot);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// LUT over the Hamming distance h = 0..d:  t_h = 2 sqrt(h) (or 4h when squared)
+__global__ void mmd_lut_kernel(int pass, int d, int m, int n_kernels, float mul_factor, int squared, float bandwidth,
+                               const double *sums, float *lut)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h > d) return;
+    const double t = squared ? 4.0 * (double)h : 2.0 * sqrt((double)h);
+    if (pass == TC_PASS_DIST) { lut[h] = (float)t; return; }
+    const double mm = (double)m;
+    const double bw = bandwidth > 0.f ? (double)bandwidth : sums[3] / (mm * mm - mm);
+    double k = 0.0;
+    for (int u = 0; u < n_kernels; ++u) k += exp(-t / (bw * pow((double)mul_factor, (double)(u - n_kernels / 2))));
+    lut[h] = (float)k;
+}
+
+// sign-pack fp32 rows into the zero-padded int8 matrix the TMA descriptor reads
+__global__ void mmd_pack_i8_kernel(const float *__restrict__ z, int m, int d, int d_pad, int8_t *__restrict__ out)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)m * d_pad;
+    if (idx >= total) return;
+    const int r = (int)(idx / d_pad), c = (int)(idx % d_pad);
+    out[idx] = c < d ? (z[(size_t)r * d + c] > 0.f ? (int8_t)1 : (int8_t)-1) : (int8_t)0;
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int32_t get_encode(encode_tiled_fn *out)
+{
+    static encode_tiled_fn cached = nullptr;
+    if (cached == nullptr) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        B200_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (fn == nullptr || qres != cudaDriverEntryPointSuccess)
+            return fail(B200GRBM_EUNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+        cached = reinterpret_cast<encode_tiled_fn>(fn);
+    }
+    *out = cached;
+    return 0;
+}
+
+}  // namespace b200grbm
+
+using namespace b200grbm;
+
+extern "C" int32_t b200grbm_mmd_pack_i8(const float *z_dev, int32_t m, int32_t d, int32_t d_pad, int8_t *out_dev,
+                                        void *stream)
+{
+    if (m <= 0 || d <= 0 || d_pad < d || d_pad % 16 != 0)
+        return fail(B200GRBM_EINVAL, "mmd_pack_i8: m=%d d=%d d_pad=%d (d_pad must be a multiple of 16 >= d)", m, d, d_pad);
+    if (!z_dev || !out_dev) return fail(B200GRBM_EINVAL, "mmd_pack_i8: NULL pointer argument");
+    B200_TRY(require_device());
+    const size_t total = (size_t)m * d_pad;
+    mmd_pack_i8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z_dev, m, d, d_pad, out_dev);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,
+                                           int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth,
+                                           float *lut_dev, double *sums_dev, void *stream)
+{
+    if (m_x <= 0 || m_y <= 0 || d <= 0 || d_pad < d || d_pad % 16 != 0)
+        return fail(B200GRBM_EINVAL, "mmd_forward_i8: m_x=%d m_y=%d d=%d d_pad=%d", m_x, m_y, d, d_pad);
+    if (n_kernels < 1 || n_kernels > 16 || !(mul_factor > 0.f))
+        return fail(B200GRBM_EINVAL, "mmd_forward_i8: n_kernels=%d mul_factor=%g", n_kernels, mul_factor);
+    if (!z_dev || !lut_dev || !sums_dev) return fail(B200GRBM_EINVAL, "mmd_forward_i8: NULL pointer argument");
+    if ((reinterpret_cast<uintptr_t>(z_dev) & 15u) != 0)
+        return fail(B200GRBM_EINVAL, "mmd_forward_i8: z_dev must be 16-byte aligned (TMA)");
+    B200_TRY(require_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    const int m = m_x + m_y;
+
+    int dev = 0, smem_optin = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t lut_bytes = ((size_t)(d + 1) * 4 + 15) / 16 * 16;
+    int stages = 4;
+    size_t smem = 0;
+    for (; stages >= 2; --stages) {
+        smem = (size_t)stages * STAGE_BYTES + lut_bytes + (2 * stages + 4) * 8 + 16;
+        if (smem + 1024 <= (size_t)smem_optin) break;
+    }
+    if (stages < 2)
+        return fail(B200GRBM_EUNSUPPORTED, "mmd_forward_i8: d=%d needs a %zu B look-up table, too large for shared memory", d,
+                    lut_bytes);
+
+    encode_tiled_fn encode = nullptr;
+    B200_TRY(get_encode(&encode));
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)d_pad, (cuuint64_t)m};
+    const cuuint64_t gstride[1] = {(cuuint64_t)d_pad};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, 128u};
+    const cuuint32_t estride[2] = {1u, 1u};
+    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(z_dev), gdim, gstride, box,
+                               estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(B200GRBM_EINVAL, "mmd_forward_i8: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+    TcParams p = {};
+    p.m_x = m_x; p.m = m; p.d = d;
+    p.n_kblocks = (d_pad + BK - 1) / BK;
+    p.tiles_m = (m + BM - 1) / BM;
+    p.tiles_n = (m + BN - 1) / BN;
+    p.j0 = p.tiles_m / 2 < p.tiles_n ? p.tiles_m / 2 : p.tiles_n;
+    p.p0 = p.j0 * (p.j0 + 1);
+    p.total_tiles = p.p0 + (p.tiles_n - p.j0) * p.tiles_m;
+    p.stages = stages;
+    p.lut = lut_dev;
+    p.sums = sums_dev;
+
+    B200_CUDA(cudaFuncSetAttribute(mmd_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + 1024)));
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    B200_CUDA(cudaMemsetAsync(sums_dev, 0, 4 * sizeof(double), st));
+    const int lut_blocks = (d + 1 + 255) / 256;
+    if (!(bandwidth > 0.f)) {
+        mmd_lut_kernel<<<lut_blocks, 256, 0, st>>>(TC_PASS_DIST, d, m, n_kernels, mul_factor, squared, bandwidth, sums_dev,
+                                                   lut_dev);
+        B200_CUDA(cudaGetLastError());
+        p.pass = TC_PASS_DIST;
+        mmd_gram_i8_kernel<<<grid, TC_THREADS, smem + 1024, st>>>(tmap, p);
+        B200_CUDA(cudaGetLastError());
+    }
+    mmd_lut_kernel<<<lut_blocks, 256, 0, st>>>(TC_PASS_KERNEL, d, m, n_kernels, mul_factor, squared, bandwidth, sums_dev,
+                                               lut_dev);
+    B200_CUDA(cudaGetLastError());
+    p.pass = TC_PASS_KERNEL;
+    mmd_gram_i8_kernel<<<grid, TC_THREADS, smem + 1024, st>>>(tmap, p);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}

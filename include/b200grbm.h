@@ -176,6 +176,17 @@ int32_t b200grbm_mmd_backward_f32(const float *z_dev, int32_t m_x, int32_t m_y, 
                                   float w_xx, float w_xy, const float *grad_out_dev, float *coef_dev,
                                   float *grad_x_dev, void *stream);
 
+/*
+ * tcgen05 path for +-1 rows (same contract as b200grbm_mmd_forward_f32; BASELINE.json cfg3).
+ * z_dev: int8 [m][d_pad] row-major, 16-byte aligned, d_pad a multiple of 16, columns >= d zero
+ * (b200grbm_mmd_pack_i8 produces it from real-valued spins by sign).  lut_dev: workspace of
+ * d + 1 floats.  ||a-b||^2 = 2 (d - a.b) exactly, from the int32 Gram accumulators.
+ */
+int32_t b200grbm_mmd_pack_i8(const float *z_dev, int32_t m, int32_t d, int32_t d_pad, int8_t *out_dev, void *stream);
+int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,
+                                int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth, float *lut_dev,
+                                double *sums_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

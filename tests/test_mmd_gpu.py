@@ -1,0 +1,146 @@
+"""Fused mixture-of-RBF MMD on the GPU against the float64 oracle (north_star check c:
+within 1e-5 relative, fp32), value and gradient wrt x, for every switch of SURVEY.md A.3."""
+import numpy as np
+import pytest
+import torch
+
+import image_generation_b200 as B
+from image_generation_b200.mmd import mmd_block_sums
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _spins(rng, rows, d, residue=0.0):
+    s = rng.choice([-1.0, 1.0], size=(rows, d))
+    return (s + residue * rng.normal(size=s.shape)).astype(np.float32)
+
+
+def _terms(x, y, **kw):
+    """Oracle value plus the magnitude of the three block terms (tolerance scale: the MMD is a
+    difference of O(1) block means, so 1e-5 relative applies to those)."""
+    val = O.mmd(x, y, **kw)
+    k, _, _ = O.gaussian_kernel_matrix(np.concatenate([x, y]).astype(np.float64), squared=kw.get("squared", False),
+                                       bandwidth=kw.get("bandwidth"), reduce=kw.get("reduce", "sum"),
+                                       n_kernels=kw.get("n_kernels", 7))
+    mx = x.shape[0]
+    scale = abs(k[:mx, :mx].mean()) + abs(k[mx:, mx:].mean()) + 2 * abs(k[:mx, mx:].mean())
+    return val, scale
+
+
+@pytest.mark.parametrize("squared", [False, True])
+@pytest.mark.parametrize("estimator", ["unbiased", "biased"])
+@pytest.mark.parametrize("reduce", ["sum", "mean"])
+def test_mmd_value_and_gradient_all_switches(cuda_device, squared, estimator, reduce):
+    rng = np.random.default_rng(0)
+    x = _spins(rng, 70, 100, residue=1e-3)
+    y = _spins(rng, 45, 100)
+    kern = B.GaussianKernel(7, squared=squared, reduce=reduce).to(cuda_device)
+    xt = torch.from_numpy(x).to(cuda_device).requires_grad_(True)
+    val = B.maximum_mean_discrepancy_loss(xt, torch.from_numpy(y).to(cuda_device), kern, estimator=estimator)
+    (3.0 * val).backward()
+    want, scale = _terms(x, y, squared=squared, estimator=estimator, reduce=reduce)
+    assert abs(float(val) - want) <= 1e-5 * scale
+    # gradient: oracle with the bandwidth frozen at its forward value (.detach())
+    bw = O.gaussian_kernel_matrix(np.concatenate([x, y]).astype(np.float64), squared=squared)[1]
+    _, grad = O.mmd(x, y, squared=squared, estimator=estimator, reduce=reduce, bandwidth=bw, return_grad=True)
+    got = xt.grad.cpu().numpy() / 3.0
+    np.testing.assert_allclose(got, grad, rtol=2e-4, atol=1e-5 * np.abs(grad).max())
+
+
+def test_mmd_cfg1_shapes_fixed_and_auto_bandwidth(cuda_device):
+    """Reference step shapes: x (1024, 256) encoder spins with grad, y (256, 256) samples, 7 kernels."""
+    rng = np.random.default_rng(1)
+    x = _spins(rng, 1024, 256, residue=1e-7)
+    y = _spins(rng, 256, 256)
+    y[:, :40] = 1.0                                        # make the two clouds differ
+    for bw in (None, 20.0):
+        kern = B.GaussianKernel(n_kernels=7, bandwidth=bw).to(cuda_device)
+        xt = torch.from_numpy(x).to(cuda_device).requires_grad_(True)
+        val = B.maximum_mean_discrepancy_loss(x=xt, y=torch.from_numpy(y).to(cuda_device), kernel=kern)
+        want, scale = _terms(x, y, bandwidth=bw)
+        assert abs(float(val) - want) <= 1e-5 * scale
+        assert float(val) == pytest.approx(want, rel=2e-3)          # and the small difference itself
+        val.backward()
+        assert xt.grad.shape == (1024, 256) and torch.isfinite(xt.grad).all()
+
+
+def test_mmd_block_sums_and_properties(cuda_device):
+    rng = np.random.default_rng(2)
+    x = _spins(rng, 33, 17)
+    y = _spins(rng, 65, 17)
+    z = torch.from_numpy(np.concatenate([x, y])).to(cuda_device)
+    kern = B.GaussianKernel(5).to(cuda_device)
+    sums = mmd_block_sums(z, 33, kern).cpu().numpy()
+    k, bw, dist = O.gaussian_kernel_matrix(np.concatenate([x, y]).astype(np.float64), n_kernels=5)
+    np.testing.assert_allclose(sums, [k[:33, :33].sum(), k[33:, 33:].sum(), k[:33, 33:].sum(), dist.sum()], rtol=2e-6)
+    # identical clouds -> biased MMD is exactly the xx+yy-2xy cancellation; swapping x and y keeps the value
+    kb = B.GaussianKernel(7, bandwidth=3.0).to(cuda_device)
+    xt, yt = torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device)
+    assert abs(float(B.maximum_mean_discrepancy_loss(xt, xt.clone(), kb, estimator="biased"))) < 1e-6
+    a = float(B.maximum_mean_discrepancy_loss(xt, yt, kb))
+    b = float(B.maximum_mean_discrepancy_loss(yt, xt, kb))
+    assert a == pytest.approx(b, rel=1e-5, abs=1e-7)
+
+
+def test_dense_kernel_module_matches_oracle(cuda_device):
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(20, 9)).astype(np.float32)
+    kern = B.GaussianKernel(7).to(cuda_device)
+    got = kern(torch.from_numpy(x).to(cuda_device), torch.from_numpy(x).to(cuda_device)).cpu().numpy()
+    want, _, _ = O.gaussian_kernel_matrix(x)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_mmd_argument_errors(cuda_device):
+    kern = B.GaussianKernel(7).to(cuda_device)
+    x = torch.ones(4, 8, device=cuda_device)
+    with pytest.raises(ValueError):
+        B.maximum_mean_discrepancy_loss(x, torch.ones(4, 9, device=cuda_device), kern)
+    with pytest.raises(ValueError):
+        B.maximum_mean_discrepancy_loss(x, x, kern, estimator="median")
+    with pytest.raises(ValueError):
+        B.maximum_mean_discrepancy_loss(x[:1], x, kern)               # unbiased needs >= 2 rows
+    with pytest.raises(TypeError):
+        B.maximum_mean_discrepancy_loss(x, x, kernel=None)
+    with pytest.raises(ValueError):
+        B.GaussianKernel(0)
+    with pytest.raises(RuntimeError):
+        B.maximum_mean_discrepancy_loss(x.cpu(), x.cpu(), B.GaussianKernel(7))   # no CPU fallback
+
+
+# ------------------------------------------------------------------ tcgen05 int8 path
+
+@pytest.mark.parametrize("m_x,m_y,d", [(256, 256, 128), (128, 384, 256), (70, 45, 100), (300, 515, 333),
+                                       (1024, 256, 256)])
+@pytest.mark.parametrize("bandwidth", [None, 25.0])
+def test_tensor_core_block_sums_match_oracle(cuda_device, m_x, m_y, d, bandwidth):
+    """int8 tcgen05 Gram + LUT epilogue vs the float64 oracle; includes ragged sizes (tiles that
+    straddle the diagonal, the x/y boundary and the matrix edge) and the cfg1 shape."""
+    rng = np.random.default_rng(m_x + d)
+    z = rng.choice([-1, 1], size=(m_x + m_y, d)).astype(np.int8)
+    z[m_x:, : d // 5] = 1
+    kern = B.GaussianKernel(7, bandwidth=bandwidth).to(cuda_device)
+    sums = mmd_block_sums(torch.from_numpy(z).to(cuda_device), m_x, kern, path="i8").cpu().numpy()
+    k, bw, dist = O.gaussian_kernel_matrix(z.astype(np.float64), bandwidth=bandwidth)
+    want = [k[:m_x, :m_x].sum(), k[m_x:, m_x:].sum(), k[:m_x, m_x:].sum()]
+    np.testing.assert_allclose(sums[:3], want, rtol=2e-6)
+    if bandwidth is None:
+        assert sums[3] == pytest.approx(dist.sum(), rel=1e-6)
+
+
+def test_tensor_core_path_agrees_with_cuda_core_path_and_loss(cuda_device):
+    rng = np.random.default_rng(11)
+    x = _spins(rng, 512, 640, residue=1e-7)
+    y = _spins(rng, 384, 640)
+    y[:, :100] = 1.0
+    kern = B.GaussianKernel(7).to(cuda_device)
+    xt, yt = torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device)
+    a = float(B.maximum_mean_discrepancy_loss(xt, yt, kern, path="f32"))
+    b = float(B.maximum_mean_discrepancy_loss(xt, yt, kern, path="i8"))
+    want, scale = _terms(x, y)
+    assert abs(a - want) <= 1e-5 * scale and abs(b - want) <= 1e-5 * scale
+    # gradient still flows through the i8 forward (backward runs the fp32 kernels)
+    xg = xt.clone().requires_grad_(True)
+    B.maximum_mean_discrepancy_loss(xg, yt, kern, path="i8").backward()
+    assert torch.isfinite(xg.grad).all() and float(xg.grad.abs().max()) > 0
