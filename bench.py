@@ -96,8 +96,8 @@ def cpu_port_rate(g, h, J, beta, target_seconds, threads=None):
     """Oracle port (textbook double heat bath, all host threads) on a bounded sample of the workload."""
     from oracle import oracle as O
 
-    if threads:
-        O.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is specified as "all the host threads it can use"
+    O.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = O.num_threads()
     csr = O.PositionCSR(g.n, g.edge_i, g.edge_j, g.order)
     chains = 4 * cores
@@ -170,12 +170,17 @@ def run_b200(args):
     plan = (args.cpl, args.threads) if args.cpl and args.threads else None
     launches = {"n": 0}
 
+    # caller-owned output buffers: the steady state allocates nothing (a cudaMalloc between the
+    # start event and the launch would be charged to the kernel)
+    out_bufs = (torch.empty((chains, g.n), dtype=torch.int8, device=dev), torch.empty(chains, dtype=torch.float64, device=dev))
+    packed_buf = [None]
+
     def step_device():
-        ss = sampler._run(chains, sweeps, None, None, None, None, None, None, plan=plan)
+        ss = sampler._run(chains, sweeps, None, None, None, None, None, None, plan=plan, out=out_bufs)
         n_l = sampler.last_launches
-        packed = pack_spins(ss.samples_tensor, dg)
+        packed_buf[0] = pack_spins(ss.samples_tensor, dg)
         sum_s.zero_(); sum_ss.zero_()
-        edge_statistics(packed, chains, dg, out=(sum_s, sum_ss))
+        edge_statistics(packed_buf[0], chains, dg, out=(sum_s, sum_ss))
         n_l += 3                                    # pack + edge + node statistics kernels
         if world > 1:
             a, b = allreduce_statistics([sum_s, sum_ss])
@@ -189,28 +194,28 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    clocks = ClockSampler(local)
+    if not args.no_clocks:
+        clocks.start()                              # started before warm-up so the GPU never idles before step 0
     for _ in range(args.warmup):
         step_device()
     sync_all()
     launches["n"] = 0
-    clocks = ClockSampler(local)
-    clocks.start()
-    time.sleep(0.3)
     t_wall0 = time.time()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k in range(args.steps):
-        flush.fill_(k & 0xFF)                       # L2 flush between timed steps (256 MB write > 126 MB L2)
+        if not args.no_flush:
+            flush.fill_(k & 0xFF)                   # L2 flush between timed steps (256 MB write > 126 MB L2)
         sync_all()
         ev[k][0].record()
-        # the dominant kernel alone, on the stream it is launched on (torch's current stream)
-        kev[k][0].record()
-        ss = sampler._run(chains, sweeps, None, None, None, None, None, None, plan=plan, want_int8=True)
+        kev[k][0].record()                          # the dominant kernel alone, on the stream it is launched on
+        ss = sampler._run(chains, sweeps, None, None, None, None, None, None, plan=plan, out=out_bufs)
         kev[k][1].record()
         n_l = sampler.last_launches
-        packed = pack_spins(ss.samples_tensor, dg)
+        packed_buf[0] = pack_spins(ss.samples_tensor, dg)
         sum_s.zero_(); sum_ss.zero_()
-        edge_statistics(packed, chains, dg, out=(sum_s, sum_ss))
+        edge_statistics(packed_buf[0], chains, dg, out=(sum_s, sum_ss))
         if world > 1:
             a, b = allreduce_statistics([sum_s, sum_ss])
             sum_s.copy_(a); sum_ss.copy_(b)
@@ -227,6 +232,7 @@ def run_b200(args):
     total_s = float(total_ms) / 1e3
     updates_per_step = chains * sweeps * g.n * world
     value = updates_per_step * args.steps / total_s
+    timed_plan = sampler.last_plan
 
     # ---- end to end through the reference-facing call, host buffers in and out
     h_pin, J_pin = torch.from_numpy(h).pin_memory(), torch.from_numpy(J).pin_memory()
@@ -253,9 +259,12 @@ def run_b200(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = updates_per_step * e2e_steps / float(e2e_s)
 
+    # every rank leaves the process group here, together; the CPU baseline and the side metrics
+    # below are rank-0-only work with no collective in them
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     kernel_s = float(kern_ms.mean()) / 1e3            # gibbs_kernel + the small energy kernel behind it
@@ -291,20 +300,91 @@ def run_b200(args):
         "config": {"workload": f"GRBM block-Gibbs, Pegasus P16 ({g.n} spins, {g.n_edges} couplers), {chains} chains x "
                                f"{sweeps} sweeps per GPU, beta=1, prefactor 0.05 (BASELINE.json configs[1])",
                    "chains_per_gpu": chains, "sweeps": sweeps, "accept": args.accept,
-                   "chains_per_lane": sampler.last_plan[0], "threads": sampler.last_plan[1],
+                   "chains_per_lane": timed_plan[0], "threads": timed_plan[1],
                    "l2": "256 MB buffer written between timed steps", "parallelism": f"chains sharded x{world}",
                    "exchange": "int64 all-reduce of N+E counters per step" if world > 1 else "none"},
         "e2e": {"value": e2e_val, "unit": "spin-updates/s", "h2d_bytes_per_step": int(4 * (g.n + g.n_edges)),
                 "d2h_bytes_per_step": int(chains * g.n + 8 * chains), "steps": e2e_steps},
         "gpu_launches": launches["n"], "clocks": clk, "roofline": roofline,
+        "step_ms": [round(float(v), 3) for v in step_ms.tolist()],
         "cpu_baseline": {"value": cpu_rate, "unit": "spin-updates/s", "cores": cores, "kind": "port", "sample": sample},
     }
+    if not args.skip_extra:
+        line["mmd"] = bench_mmd(dev, peaks)
+        line["dvae_step"] = bench_dvae_step(dev)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def bench_mmd(dev, peaks, m_each=8192, d=5640, iters=5):
+    """BASELINE.json configs[2]: fused mixture-of-RBF MMD, 8192 encoder latents vs 8192 GRBM samples,
+    latent dim = P16 graph size, +-1 rows on the tcgen05 int8 path (auto bandwidth = two Gram passes)."""
+    import torch
+
+    import image_generation_b200 as B
+    from image_generation_b200.mmd import mmd_block_sums
+
+    gen = torch.Generator().manual_seed(1)
+    z = (torch.randint(0, 2, (2 * m_each, d), generator=gen, dtype=torch.int8) * 2 - 1).to(dev)
+    z[m_each:, : d // 8] = 1
+    out = {}
+    for label, bw in (("auto_bandwidth", None), ("fixed_bandwidth", 75.0)):
+        kern = B.GaussianKernel(7, bandwidth=bw).to(dev)
+        for _ in range(3):
+            mmd_block_sums(z, m_each, kern, path="i8")
+        torch.cuda.synchronize(dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for a, b in ev:
+            a.record()
+            mmd_block_sums(z, m_each, kern, path="i8")
+            b.record()
+        torch.cuda.synchronize(dev)
+        ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        passes = 2 if bw is None else 1
+        m = 2 * m_each
+        tiles = (m // 256) * (m // 256 + 1)                     # upper triangle of 128 x 256 tiles
+        executed = 2.0 * tiles * 128 * 256 * (-(-d // 128) * 128) * passes
+        i8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        out[label] = {
+            "ms": ms, "gram_passes": passes, "input_GBps": m * d / ms / 1e6,
+            "tflops_as_reference_computes_it": 2.0 * m * m * d * passes / ms / 1e9,
+            "roofline": {"bound": "tensor", "achieved": executed / ms / 1e9, "peak": i8_peak, "unit": "TOP/s",
+                         "frac": executed / ms / 1e9 / i8_peak, "traffic": None,
+                         "peak_source": "2 x measured bf16 burst (MEASURED_PEAKS.json has no int8 figure)",
+                         "executed_ops": executed, "note": "symmetric: only the upper triangle of tiles is contracted"}}
+    out["workload"] = f"MMD {m_each} x {m_each} rows, D = {d}, 7 kernels, int8 +-1 rows (BASELINE.json configs[2])"
+    return out
+
+
+def bench_dvae_step(dev, steps=20, warmup=5):
+    """BASELINE.json configs[0] on the GPU path: one DVAE+GRBM training step, B=128, R=8, n_latents=256 on the
+    Advantage2 checkpoint graph, 256 reads x 1000 sweeps, stock-PyTorch encoder / decoder."""
+    import torch
+
+    from image_generation_b200.dvae import HybridDVAE, synthetic_batch
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "grbm_checkpoints.npz"))
+    name = "Advantage2_system1_10_epochs"
+    edges = list(zip(z[name + "/edge_i"].tolist(), z[name + "/edge_j"].tolist()))
+    model = HybridDVAE(range(256), edges, device=dev)
+    model.setup()
+    model.train_init(n_epochs=1, n_batches=steps + warmup)
+    batches = [(synthetic_batch(128, seed=k, device=dev), None) for k in range(4)]
+    for k in range(warmup):
+        model.step(batches[k % 4], epoch=0, record_losses=False)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        model.step(batches[k % 4], epoch=0, record_losses=False)
+    torch.cuda.synchronize(dev)
+    ms = 1e3 * (time.perf_counter() - t0) / steps
+    return {"ms_per_step": ms, "steps": steps, "workload": "DVAE+GRBM step, B=128, R=8, n_latents=256, 256 reads x 1000 sweeps, "
+            "MMD on tcgen05 int8 path, NLL via packed statistics every 10th step (BASELINE.json configs[0], GPU path)"}
 
 
 def main():
+    if os.environ.get("B200_BENCH_FAULT_AFTER"):      # debugging aid: dump all stacks if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["B200_BENCH_FAULT_AFTER"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -316,6 +396,9 @@ def main():
     ap.add_argument("--cpl", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample nvidia-smi during the timed region")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostic: skip the L2 flush between timed steps")
+    ap.add_argument("--skip-extra", action="store_true", help="skip the MMD (configs[2]) and DVAE-step (configs[0]) side metrics")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -309,6 +309,8 @@ static gibbs_fn pick_mode(int mode)
 static gibbs_fn pick(int cpl, int mode)
 {
     switch (cpl) {
+        case 4: return pick_mode<4>(mode);
+        case 8: return pick_mode<8>(mode);
         case 16: return pick_mode<16>(mode);
         case 24: return pick_mode<24>(mode);
         case 28: return pick_mode<28>(mode);
@@ -361,7 +363,7 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
                      : (a->accept == B200GRBM_ACCEPT_FAST ? MODE_PHILOX_FAST : MODE_PHILOX_EXACT);
     gibbs_fn fn = pick(a->chains_per_lane, mode);
     if (fn == nullptr)
-        return fail(B200GRBM_EUNSUPPORTED, "gibbs_sweeps: chains_per_lane=%d not in {16,24,28,32}",
+        return fail(B200GRBM_EUNSUPPORTED, "gibbs_sweeps: chains_per_lane=%d not in {4,8,16,24,28,32}",
                     a->chains_per_lane);
     B200_TRY(require_device());
 

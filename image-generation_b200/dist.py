@@ -41,7 +41,7 @@ def allreduce_statistics(tensors: Sequence[torch.Tensor], group: Optional[dist.P
     if any(t.dtype != dtype for t in tensors):
         raise ValueError("allreduce_statistics needs tensors of one dtype")
     flat = torch.cat([t.reshape(-1) for t in tensors])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group if group not in (None, False) else None)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     out, k = [], 0
     for t in tensors:
         out.append(flat[k:k + t.numel()].reshape(t.shape))

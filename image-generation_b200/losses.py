@@ -67,8 +67,8 @@ def nll_loss(spins: torch.Tensor, grbm: GraphRestrictedBoltzmannMachine, sampler
     d_s, d_ss = edge_statistics(pack_spins(spins, dg), spins.shape[0], dg)
     m_s, m_ss = edge_statistics(pack_spins(model_rows, dg), model_rows.shape[0], dg)
     counts = torch.tensor([spins.shape[0], model_rows.shape[0]], dtype=torch.int64, device=spins.device)
-    if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                     and process_group is not False):
+    # process_group: None -> the default group when torch.distributed is initialised; False -> never reduce
+    if process_group is not False and torch.distributed.is_available() and torch.distributed.is_initialized():
         from .dist import allreduce_statistics
         d_s, d_ss, m_s, m_ss, counts = allreduce_statistics([d_s, d_ss, m_s, m_ss, counts], process_group)
     nd, nm = counts[0].double(), counts[1].double()

@@ -30,7 +30,7 @@ __all__ = ["BlockGibbsSampler", "SampleSet", "DeviceGraph", "plan_launch", "plan
            "beta_schedule"]
 
 _LOG2E = 1.4426950408889634
-SUPPORTED_CPL = (16, 24, 28, 32)
+SUPPORTED_CPL = (4, 8, 16, 24, 28, 32)
 #: QPU-only keyword arguments the reference passes (src/utils/common.py:130-138); accepted and ignored
 _IGNORED_QPU_KWARGS = {"answer_mode", "auto_scale", "annealing_time", "label", "anneal_schedule",
                        "programming_thermalization", "readout_thermalization", "reduce_intersample_correlation",
@@ -78,11 +78,12 @@ def plan_launch(chains: int, colour_sizes: Sequence[int], sm_count: int = 148, n
     One CTA owns ``chains_per_lane`` chains and an SM runs one CTA at a time, so the launch
     takes ``ceil(groups / sm_count)`` waves of work proportional to ``chains_per_lane``;
     minimise their product (4096 chains on 148 SMs: 28 -> 147 CTAs in one wave, 12.5 % less
-    work per SM than 32 -> 128 CTAs).  Ties go to 28, whose 7-bits-per-byte state layout
-    needs the fewest predicate moves per neighbour.
+    work per SM than 32 -> 128 CTAs; 256 chains: 4 -> 64 CTAs instead of 10, a 7x shorter
+    critical path).  Ties go to 28, whose 7-bits-per-byte state layout needs the fewest
+    predicate moves per neighbour, then to the larger group.
     """
     best = None
-    for cpl in (28, 32, 24, 16):
+    for cpl in (28, 32, 24, 16, 8, 4):
         groups = -(-chains // cpl)
         cost = -(-groups // max(sm_count, 1)) * cpl
         if best is None or cost < best[0]:
@@ -296,6 +297,7 @@ class BlockGibbsSampler:
         self._dg: Optional[DeviceGraph] = None
         self._edge_index: Optional[dict] = None
         self._coef_cache: dict = {}
+        self._staging = None
         self.last_launches = 0
         self.last_plan: tuple[int, int] = (0, 0)
 
@@ -377,9 +379,19 @@ class BlockGibbsSampler:
         if unknown:
             raise TypeError(f"sample_ising() got unexpected keyword arguments {sorted(unknown)}")
         hv, jv = self._arrays_from_problem(h, J)
-        dev = self.device
-        h_t = torch.from_numpy(hv).pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else torch.from_numpy(hv)
-        j_t = torch.from_numpy(jv).pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else torch.from_numpy(jv)
+        if self.device.type != "cuda":
+            raise RuntimeError("BlockGibbsSampler needs a CUDA device; there is no CPU fallback")
+        if self._staging is None:      # pinned host + device staging for (h, J), allocated once
+            g = self.graph
+            self._staging = (torch.empty(g.n, dtype=torch.float32).pin_memory(),
+                             torch.empty(g.n_edges, dtype=torch.float32).pin_memory(),
+                             torch.empty(g.n, dtype=torch.float32, device=self.device),
+                             torch.empty(g.n_edges, dtype=torch.float32, device=self.device))
+        h_pin, j_pin, h_t, j_t = self._staging
+        h_pin.copy_(torch.from_numpy(hv))
+        j_pin.copy_(torch.from_numpy(jv))
+        h_t.copy_(h_pin, non_blocking=True)
+        j_t.copy_(j_pin, non_blocking=True)
         self.device_graph.set_weights(h_t, j_t)
         return self._run(num_reads, num_sweeps, beta_range, beta_schedule_type, beta_schedule, seed, initial_states,
                          uniforms)
@@ -400,7 +412,8 @@ class BlockGibbsSampler:
 
     def _run(self, num_reads, num_sweeps, beta_range, beta_schedule_type, beta_sched, seed, initial_states,
              uniforms, packed_io: Optional[torch.Tensor] = None, want_int8: bool = True,
-             sweep_offset: int = 0, plan: Optional[tuple[int, int]] = None) -> SampleSet:
+             sweep_offset: int = 0, plan: Optional[tuple[int, int]] = None,
+             out: Optional[tuple[torch.Tensor, torch.Tensor]] = None) -> SampleSet:
         if num_reads <= 0:
             raise ValueError("num_reads must be positive")
         g, dg, dev = self.graph, self.device_graph, self.device
@@ -444,11 +457,19 @@ class BlockGibbsSampler:
                 raise ValueError("initial_states must have shape (num_reads, n)")
             a.state_in_dev = _lib.ptr(init)
             keep.append(init)
-        elif packed_io is not None:
-            a.packed_in_dev = _lib.ptr(packed_io)
+        if packed_io is not None:
+            # persistent chains: resume from / write back to a caller-owned packed state
+            if tuple(packed_io.shape) != (-(-num_reads // cpl), g.n_pad) or packed_io.dtype != torch.int32:
+                raise ValueError("packed_io must be int32 of shape (ceil(num_reads / chains_per_lane), n_pad)")
+            if initial_states is None and sweep_offset > 0:
+                a.packed_in_dev = _lib.ptr(packed_io)
+            a.packed_out_dev = _lib.ptr(packed_io)
         samples = None
         if want_int8:
-            samples = torch.empty((num_reads, g.n), dtype=torch.int8, device=dev)
+            # `out` = caller-owned (samples int8 (reads, n), energies float64 (reads,)) buffers: no allocation per call
+            samples = out[0] if out is not None else torch.empty((num_reads, g.n), dtype=torch.int8, device=dev)
+            if tuple(samples.shape) != (num_reads, g.n) or samples.dtype != torch.int8 or not samples.is_contiguous():
+                raise ValueError("out[0] must be a contiguous int8 tensor of shape (num_reads, n)")
             a.state_out_dev = _lib.ptr(samples)
         lib = _lib.load()
         with torch.cuda.device(dev):
@@ -456,7 +477,7 @@ class BlockGibbsSampler:
             self.last_launches = lib.b200grbm_last_launch_count()
             energies = None
             if samples is not None:
-                energies = torch.empty(num_reads, dtype=torch.float64, device=dev)
+                energies = out[1] if out is not None else torch.empty(num_reads, dtype=torch.float64, device=dev)
                 _lib.check(lib.b200grbm_energy_i8(_lib.ptr(samples), num_reads, g.n, g.n_edges,
                                                   _lib.ptr(dg.edge_i), _lib.ptr(dg.edge_j), _lib.ptr(dg.h_eff),
                                                   _lib.ptr(dg.j_eff), _lib.ptr(energies), _lib.current_stream(dev)))

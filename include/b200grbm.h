@@ -83,7 +83,7 @@ typedef struct b200grbm_sweep_args {
     const int32_t *tile_info_dev;        /* [n_tiles][2] */
     const int32_t *order_dev;  /* [n] node visited at position p (for int8 node-order I/O) */
     int32_t chains;            /* chains in this call */
-    int32_t chains_per_lane;   /* 16, 24, 28 or 32: chains bit-packed per state word */
+    int32_t chains_per_lane;   /* 4, 8, 16, 24, 28 or 32: chains bit-packed per state word */
     int32_t threads;           /* CTA size the tiles were built for, multiple of 32 in [64, 768] */
     int32_t accept;            /* B200GRBM_ACCEPT_* */
     uint64_t chain_offset;     /* global id of chain 0 of this call (multiple of 4) */

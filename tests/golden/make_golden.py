@@ -40,11 +40,13 @@ def main():
         }
         h64, J64 = h.astype(np.float64), J.astype(np.float64)
         energies = {p: float(h64 @ s + (J64 * s[ei] * s[ej]).sum()) for p, s in pats.items()}
+        dv = torch.load(os.path.join(REF, name, "dvae.pth"), map_location="cpu", weights_only=True)
+        dvae_keys = {k: list(v.shape) for k, v in dv.items()}
         with open(os.path.join(REF, name, "parameters.json")) as f:
             params = json.load(f)
         with open(os.path.join(REF, name, "losses.json")) as f:
             losses = json.load(f)
-        meta[name] = dict(keys=keys, energies=energies, sum_h=float(h64.sum()), sum_J=float(J64.sum()),
+        meta[name] = dict(keys=keys, dvae_keys=dvae_keys, energies=energies, sum_h=float(h64.sum()), sum_J=float(J64.sum()),
                           parameters=params, n_steps=len(losses["mse_losses"]),
                           mse_first=losses["mse_losses"][0], mse_last=losses["mse_losses"][-1],
                           dvae_first=losses["dvae_losses"][0])

@@ -1,0 +1,81 @@
+"""Harness around the hot path: checkpoint-layout compatibility (CPU) and one reference-shaped
+training step on the GPU (BASELINE.json configs[0])."""
+import numpy as np
+import pytest
+import torch
+
+import image_generation_b200 as B
+from image_generation_b200.dvae import (DEFAULT_PARAMETERS, Decoder, DiscreteVariationalAutoencoder, Encoder, HybridDVAE,
+                                       TrainingError, heaviside_spins, synthetic_batch, train_grbm)
+
+
+def test_state_dict_layout_matches_reference_checkpoints(golden):
+    z, meta = golden
+    m = meta["Advantage2_system1_10_epochs"]
+    dvae = DiscreteVariationalAutoencoder(Encoder(256), Decoder(256))
+    assert {k: list(v.shape) for k, v in dvae.state_dict().items()} == m["dvae_keys"]
+    grbm = B.GraphRestrictedBoltzmannMachine(range(256), list(zip(z["Advantage2_system1_10_epochs/edge_i"].tolist(),
+                                                                 z["Advantage2_system1_10_epochs/edge_j"].tolist())))
+    mine = {k: (str(v.dtype), list(v.shape)) for k, v in grbm.state_dict().items()}
+    assert mine == {k: tuple(v) for k, v in m["keys"].items()}
+
+
+def test_grbm_loads_checkpoints_with_other_edge_counts(golden):
+    z, meta = golden
+    grbm = B.GraphRestrictedBoltzmannMachine(range(256), [])
+    for name in meta:
+        ei, ej = z[name + "/edge_i"], z[name + "/edge_j"]
+        sd = {"_linear": torch.from_numpy(z[name + "/linear"]), "_quadratic": torch.from_numpy(z[name + "/quadratic"]),
+              "_edge_idx_i": torch.from_numpy(ei.astype(np.int64)), "_edge_idx_j": torch.from_numpy(ej.astype(np.int64)),
+              "_visible_idx": torch.arange(256)}
+        sd.update({k: torch.zeros(0, dtype=torch.int64) for k in ("_hidden_idx", "_flat_adj", "_flat_j_idx", "_bin_idx")})
+        grbm.load_state_dict(sd)
+        assert grbm.n_edges == ei.size and grbm.ising_graph().n_edges == ei.size
+        assert grbm.ising_graph().n_colours <= 6
+
+
+def test_forward_shapes_and_spin_values():
+    dvae = DiscreteVariationalAutoencoder(Encoder(64), Decoder(64)).eval()
+    x = synthetic_batch(5, seed=1)
+    assert x.shape == (5, 1, 32, 32) and set(x.unique().tolist()) <= {0.0, 1.0}
+    lat, spins, rec = dvae(x, 3)
+    assert lat.shape == (5, 64) and spins.shape == (5, 3, 64) and rec.shape == (5, 3, 1, 32, 32)
+    assert set(spins.detach().unique().tolist()) <= {-1.0, 1.0}
+    hs = heaviside_spins(lat, 1)
+    assert hs.shape == (5, 1, 64) and torch.allclose(hs.detach().abs(), torch.ones_like(hs), atol=1e-6)
+
+
+def test_schedules_and_errors():
+    assert train_grbm(0, 0) and train_grbm(10, 5) and not train_grbm(5, 0) and not train_grbm(0, 6)
+    assert DEFAULT_PARAMETERS["NUM_READS"] == 256 and DEFAULT_PARAMETERS["PREFACTOR"] == 0.05
+    model = HybridDVAE(range(8), [(0, 1)], device="cpu")
+    with pytest.raises(TrainingError):
+        model.step((torch.zeros(1, 1, 32, 32), None), 0)
+    with pytest.raises(ValueError):
+        HybridDVAE(range(8), [(0, 1)], device="cpu", parameters={"LATENT_TO_DISCRETE": "heaviside"}).setup()
+    with pytest.raises(ValueError):
+        HybridDVAE(range(8), [(0, 1)], n_latents=9, device="cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mmd_path,packed", [("i8", True), ("f32", False)])
+def test_reference_shaped_training_steps(cuda_device, golden, mmd_path, packed):
+    """cfg1: B=128, R=8, n_latents=256 on the Advantage2 checkpoint graph, 256 reads."""
+    z, _ = golden
+    name = "Advantage2_system1_10_epochs"
+    edges = list(zip(z[name + "/edge_i"].tolist(), z[name + "/edge_j"].tolist()))
+    model = HybridDVAE(range(256), edges, device=cuda_device, sampler_kwargs=dict(num_sweeps=100), mmd_path=mmd_path,
+                       packed_nll=packed)
+    model.setup()
+    model.train_init(n_epochs=1, n_batches=12)
+    h0 = model._grbm._linear.detach().clone()
+    for k in range(12):
+        mse = model.step((synthetic_batch(128, seed=k % 3), None), epoch=0)
+    assert torch.isfinite(mse) and len(model.losses["mse_losses"]) == 12
+    assert all(np.isfinite(v) for v in model.losses["dvae_losses"])
+    assert model.losses["mse_losses"][-1] < model.losses["mse_losses"][0]        # it learns the 3 repeated batches
+    assert not torch.equal(h0, model._grbm._linear.detach())                      # GRBM stepped at opt_step 0 and 10
+    imgs = model.generate()
+    assert imgs.shape == (256, 1, 32, 32) and float(imgs.min()) >= 0 and float(imgs.max()) <= 1
+    sd = model.state_dicts()
+    assert set(sd) == {"dvae.pth", "grbm.pth"} and "_encoder.conv.0.weight" in sd["dvae.pth"]

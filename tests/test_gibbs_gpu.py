@@ -28,7 +28,7 @@ def _oracle_csr(graph):
     return O.PositionCSR(graph.n, graph.edge_i, graph.edge_j, graph.order)
 
 
-@pytest.mark.parametrize("cpl,threads", [(16, 64), (24, 128), (28, 480), (32, 768)])
+@pytest.mark.parametrize("cpl,threads", [(4, 64), (8, 96), (16, 64), (24, 128), (28, 480), (32, 768)])
 def test_supplied_uniforms_bit_exact(cuda_device, cpl, threads):
     g = B.IsingGraph.pegasus(4)
     h, J = _problem(g, 1)
@@ -47,7 +47,7 @@ def test_supplied_uniforms_bit_exact(cuda_device, cpl, threads):
     np.testing.assert_allclose(ss.record.energy, O.energies(g.n, g.edge_i, g.edge_j, h, J, want), rtol=1e-12, atol=1e-9)
 
 
-@pytest.mark.parametrize("cpl,threads", [(16, 96), (28, 256), (32, 480)])
+@pytest.mark.parametrize("cpl,threads", [(4, 128), (8, 64), (16, 96), (28, 256), (32, 480)])
 def test_philox_exact_mode_bit_exact_and_geometry_independent(cuda_device, cpl, threads):
     g = B.IsingGraph.pegasus(5)
     h, J = _problem(g, 3)
