@@ -65,7 +65,7 @@ SIGNATURES = {
     "b200grbm_device_info": ([C.POINTER(_i32)] * 4, _i32),
     "b200grbm_set_weights": ([_vp, _vp, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _i32, _i32,
                               _vp, _vp, _vp, _vp], _i32),
-    "b200grbm_sweep_smem_bytes": ([_i32, _i32, _i32], C.c_int64),
+    "b200grbm_sweep_smem_bytes": ([_i32, _i32, _i32, _i32], C.c_int64),
     "b200grbm_gibbs_sweeps": ([C.POINTER(SweepArgs), _vp], _i32),
     "b200grbm_last_launch_count": ([], _i32),
     "b200grbm_pack_f32": ([_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp], _i32),

@@ -18,7 +18,7 @@
 //     (one FADD per neighbour-chain pair, Philox + acceptance per update), not by
 //     shared-memory or HBM bytes.  HBM sees one read and one write of the state per launch.
 //     CPL = 28 keeps bit 7 of every byte free so four R2Ps cover the word exactly.
-//   * The (2J, nbr, f0) tables are tiled per colour round -- tile = threads x (width + 1)
+//   * The (f0; 2J, nbr) tables are tiled per colour round -- tile = (1 + width) x threads
 //     8-byte entries, contiguous in global memory -- and streamed through a 2-stage
 //     shared-memory ring by the bulk-copy engine (cp.async.bulk + mbarrier complete_tx,
 //     SASS UBLKCP): the copy of round q+1 overlaps the arithmetic of round q, so no warp
@@ -37,7 +37,7 @@ namespace b200grbm {
 enum { MODE_PHILOX_EXACT = 0, MODE_PHILOX_FAST = 1, MODE_SUPPLIED_EXACT = 2 };
 
 struct SweepParams {
-    const uint2 *tiles;       // [n_tiles][width + 1][threads] entries {2J bits | f0 bits, nbr}
+    const uint2 *tiles;       // [n_tiles][1 + width][threads]: row 0 {f0 bits, -}, rows 1.. {2J bits, nbr}
     const int2 *tile_info;    // [n_tiles] {first visit position, spins in this round}
     const int32_t *order;
     const float *coef;
@@ -50,6 +50,7 @@ struct SweepParams {
     int chains, num_sweeps;
     uint32_t sweep_offset;
     uint32_t chain_block0;  // (chain_offset >> 2)
+    uint32_t info_bytes;    // shared-memory bytes reserved for the round table (multiple of 128)
     uint32_t state_bytes;   // shared-memory bytes reserved for W (multiple of 128)
     uint32_t tile_bytes;    // (width + 1) * threads * 8
     uint32_t rk[2 * B200GRBM_PHILOX_ROUNDS];
@@ -159,13 +160,32 @@ __device__ __forceinline__ uint32_t kernel_to_dense(uint32_t w)
     return (w & 0x7fu) | ((w >> 1) & 0x3f80u) | ((w >> 2) & 0x1fc000u) | ((w >> 3) & 0xfe00000u);
 }
 
+// Slots of a lane-task are consumed UNROLL at a time.  Large groups (CPL >= 16) hide the
+// LDS -> LDS dependency (entry, then the state word it points at) behind CPL predicated adds
+// per slot, so a 1-deep software pipeline is enough and keeps the register count at the
+// 80-register budget of a 736-thread CTA.  Small groups (CPL <= 8: few chains spread over
+// many CTAs, e.g. the reference's 256 reads) have almost no arithmetic per slot; there the
+// loads of four slots are issued together so a round costs two shared-memory latencies per
+// four slots instead of two per slot.
+template <int CPL>
+struct SlotUnroll { static constexpr int value = CPL <= 8 ? 4 : 1; };
+
+template <int CPL>
+__device__ __forceinline__ void add_slot(float (&f)[CPL], uint32_t w, float j2)
+{
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+        if (w & (1u << bitpos<CPL>(c))) f[c] = __fadd_rn(f[c], j2);
+}
+
 template <int CPL, int MODE>
 __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ SweepParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);                 // 2 mbarriers (16 B, padded to 128)
-    uint32_t *W = reinterpret_cast<uint32_t *>(smem_raw + 128);
-    unsigned char *stage0 = smem_raw + 128 + p.state_bytes;
+    int2 *tinfo = reinterpret_cast<int2 *>(smem_raw + 128);                  // round table, copied once
+    uint32_t *W = reinterpret_cast<uint32_t *>(smem_raw + 128 + p.info_bytes);
+    unsigned char *stage0 = smem_raw + 128 + p.info_bytes + p.state_bytes;
 
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
@@ -187,6 +207,7 @@ __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ S
             bulk_g2s(stage_addr, p.tiles, p.tile_bytes, bar_addr);
         }
     }
+    for (int k = tid; k < p.n_tiles; k += nthr) tinfo[k] = __ldg(p.tile_info + k);
 
     // ---- load / initialise the group's packed state
     for (int pp = tid; pp < p.n; pp += nthr) {
@@ -212,6 +233,7 @@ __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ S
 
     int tile = 0, t = 0;
     float coef = total_tiles > 0 ? __ldg(p.coef) : 0.f;
+    float coef_next = p.num_sweeps > 1 ? __ldg(p.coef + 1) : 0.f;   // one sweep ahead: never waited on
     for (long long q = 0; q < total_tiles; ++q) {
         const uint32_t s = (uint32_t)q & 1u;
         // stage s^1 was last read in round q-1, which every thread left through the
@@ -223,34 +245,47 @@ __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ S
             bulk_g2s(stage_addr + (s ^ 1u) * p.tile_bytes,
                      reinterpret_cast<const unsigned char *>(p.tiles) + (size_t)next_tile * p.tile_bytes, p.tile_bytes, nb);
         }
-        const int2 info = __ldg(p.tile_info + tile);
+        const int2 info = tinfo[tile];
         mbar_wait(bar_addr + 8u * s, (uint32_t)(q >> 1) & 1u);
 
         if (tid < info.y) {
             const int pp = info.x + tid;
             const uint32_t sweep = p.sweep_offset + (uint32_t)t;
+            // tile rows: 0 = f0, 1 .. width = neighbour slots
             const uint2 *ep = reinterpret_cast<const uint2 *>(stage0 + s * p.tile_bytes) + tid;
             float f[CPL];
-            const float fz = u2f(ep[(size_t)p.width * nthr].x);
+            const float fz = u2f(ep->x);
+            ep += nthr;
 #pragma unroll
             for (int c = 0; c < CPL; ++c) f[c] = fz;
 
-            // software pipeline: entry / state word of slot k+1 are fetched while slot k's adds
-            // issue (slot `width` is the f0 row, whose nbr field is 0 -> a harmless read)
-            uint2 e = *ep;
-            ep += nthr;
-            uint32_t w = W[e.y];
+            if (SlotUnroll<CPL>::value == 4) {
+                // width is a multiple of 4 here (padding slots hold 2J = 0, nbr = 0)
 #pragma unroll 1
-            for (int k = 0; k < p.width; ++k) {
-                const uint2 en = *ep;
+                for (int k = 0; k < p.width; k += 4) {
+                    const uint2 e0 = ep[0], e1 = ep[nthr], e2 = ep[2 * nthr], e3 = ep[3 * nthr];
+                    ep += 4 * nthr;
+                    const uint32_t w0 = W[e0.y], w1 = W[e1.y], w2 = W[e2.y], w3 = W[e3.y];
+                    add_slot<CPL>(f, w0, u2f(e0.x));
+                    add_slot<CPL>(f, w1, u2f(e1.x));
+                    add_slot<CPL>(f, w2, u2f(e2.x));
+                    add_slot<CPL>(f, w3, u2f(e3.x));
+                }
+            } else {
+                // software pipeline: entry / state word of slot k+1 are fetched while slot k's adds issue
+                uint2 e = *ep;
                 ep += nthr;
-                const uint32_t wn = W[en.y];
-                const float j2 = u2f(e.x);
-#pragma unroll
-                for (int c = 0; c < CPL; ++c)
-                    if (w & (1u << bitpos<CPL>(c))) f[c] = __fadd_rn(f[c], j2);
-                e = en;
-                w = wn;
+                uint32_t w = W[e.y];
+#pragma unroll 1
+                for (int k = 1; k < p.width; ++k) {
+                    const uint2 en = *ep;
+                    ep += nthr;
+                    const uint32_t wn = W[en.y];
+                    add_slot<CPL>(f, w, u2f(e.x));
+                    e = en;
+                    w = wn;
+                }
+                add_slot<CPL>(f, w, u2f(e.x));
             }
 
             uint32_t neww = 0;
@@ -278,7 +313,8 @@ __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ S
         if (++tile == p.n_tiles) {
             tile = 0;
             ++t;
-            if (t < p.num_sweeps) coef = __ldg(p.coef + t);
+            coef = coef_next;
+            if (t + 1 < p.num_sweeps) coef_next = __ldg(p.coef + t + 1);
         }
     }
 
@@ -327,10 +363,11 @@ using namespace b200grbm;
 
 extern "C" int32_t b200grbm_last_launch_count(void) { return g_last_launches; }
 
-extern "C" int64_t b200grbm_sweep_smem_bytes(int32_t n, int32_t ell_width, int32_t threads)
+extern "C" int64_t b200grbm_sweep_smem_bytes(int32_t n, int32_t ell_width, int32_t threads, int32_t n_tiles)
 {
     const int64_t state = ((int64_t)n * 4 + 127) / 128 * 128;
-    return 128 + state + 2 * (int64_t)(ell_width + 1) * threads * 8;
+    const int64_t info = ((int64_t)n_tiles * 8 + 127) / 128 * 128;
+    return 128 + info + state + 2 * (int64_t)(ell_width + 1) * threads * 8;
 }
 
 extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *stream)
@@ -385,6 +422,10 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
     p.num_sweeps = a->num_sweeps;
     p.sweep_offset = a->sweep_offset;
     p.chain_block0 = (uint32_t)(a->chain_offset >> 2);
+    if (a->chains_per_lane <= 8 && a->ell_width % 4 != 0)
+        return fail(B200GRBM_EINVAL, "gibbs_sweeps: chains_per_lane <= 8 consumes slots four at a time; ell_width=%d "
+                                     "must be padded to a multiple of 4", a->ell_width);
+    p.info_bytes = (uint32_t)(((size_t)a->n_tiles * 8 + 127) / 128 * 128);
     p.state_bytes = (uint32_t)(((size_t)a->n * 4 + 127) / 128 * 128);
     p.tile_bytes = (uint32_t)((size_t)(a->ell_width + 1) * a->threads * 8);
     uint32_t k0 = (uint32_t)a->seed, k1 = (uint32_t)(a->seed >> 32);
@@ -395,7 +436,7 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
         k1 += B200GRBM_PHILOX_W1;
     }
 
-    const size_t smem = (size_t)b200grbm_sweep_smem_bytes(a->n, a->ell_width, a->threads);
+    const size_t smem = (size_t)b200grbm_sweep_smem_bytes(a->n, a->ell_width, a->threads, a->n_tiles);
     int dev = 0, smem_optin = 0;
     B200_CUDA(cudaGetDevice(&dev));
     B200_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

@@ -40,10 +40,10 @@ __global__ void set_node_weights_kernel(const float *__restrict__ linear, int n,
     const float h = fminf(fmaxf(__fmul_rn(prefactor, linear[node]), lo), hi);
     if (h_eff != nullptr) h_eff[node] = h;
     float a = h;
-    uint2 *row = tiles + row_base[p];
+    uint2 *row = tiles + row_base[p];   // row 0 = f0, rows 1 .. width = slots
     // contract order: subtract J_k for k ascending; padded slots hold 2J = 0
-    for (int k = 0; k < width; ++k) a = __fsub_rn(a, __fmul_rn(0.5f, u2f(row[(size_t)k * stride].x)));
-    row[(size_t)width * stride].x = f2u(a);
+    for (int k = 0; k < width; ++k) a = __fsub_rn(a, __fmul_rn(0.5f, u2f(row[(size_t)(k + 1) * stride].x)));
+    row[0].x = f2u(a);
 }
 
 // ------------------------------------------------------------------ sign packing

@@ -157,6 +157,8 @@ class HybridDVAE:
         self._sampler_kwargs_extra = sampler_kwargs or {}
         self.mmd_path, self.packed_nll = mmd_path, packed_nll
         self.losses = {"mse_losses": [], "dvae_losses": []}
+        self.overlap_sampling = True
+        self._side_stream = None
         self._dvae = self._grbm = self.sampler = None
         self._tpar: dict = {}
 
@@ -204,14 +206,27 @@ class HybridDVAE:
         self._dvae.train()
         self._grbm.train()
         R = self.N_REPLICAS
+        # The negative-phase samples depend only on the GRBM parameters, not on this batch: on a
+        # GPU they are drawn on a side stream while the encoder / decoder run on the main one
+        # (the sweep launch for 256 reads occupies ~64 of the 148 SMs).
+        overlap = self.overlap_sampling and self.device.type == "cuda"
+        if overlap:
+            main = torch.cuda.current_stream(self.device)
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(self.device)
+            self._side_stream.wait_stream(main)
+            with torch.cuda.stream(self._side_stream), torch.no_grad():
+                samples = self._sample_prior()
         _, spins, recon = self._dvae(images, R)
 
         self._dvae_optimizer.zero_grad()
         mse = torch.nn.functional.mse_loss(recon, images.unsqueeze(1).expand(-1, R, -1, -1, -1))
-        with torch.no_grad():
-            samples = self._grbm.sample(self.sampler, prefactor=self.PREFACTOR, linear_range=self.linear_range,
-                                        quadratic_range=self.quadratic_range, device=spins.device,
-                                        sample_params=self.sampler_kwargs)
+        if overlap:
+            main.wait_stream(self._side_stream)
+            samples.record_stream(main)
+        else:
+            with torch.no_grad():
+                samples = self._sample_prior()
         spins = spins.reshape(-1, spins.shape[-1])
         mmd = maximum_mean_discrepancy_loss(x=spins, y=samples, kernel=self._tpar["kernel"], path=self.mmd_path)
         dvae_loss = mse + mmd
@@ -238,6 +253,11 @@ class HybridDVAE:
             group["lr"] = self._tpar["grbm_lr_schedule"][min(k, len(self._tpar["grbm_lr_schedule"]) - 1)]
         self._tpar["opt_step"] = k + 1
         return mse
+
+    def _sample_prior(self) -> torch.Tensor:
+        return self._grbm.sample(self.sampler, prefactor=self.PREFACTOR, linear_range=self.linear_range,
+                                 quadratic_range=self.quadratic_range, device=self.device,
+                                 sample_params=self.sampler_kwargs)
 
     @torch.no_grad()
     def generate(self) -> torch.Tensor:

@@ -48,10 +48,10 @@ def _splitmix64(x: int) -> int:
 SMEM_LIMIT = 227 * 1024  # opt-in shared memory per CTA on sm_100
 
 
-def sweep_smem_bytes(n: int, ell_width: int, threads: int) -> int:
-    """Dynamic shared memory of one sweep CTA: 2 mbarriers + state words + 2 tile stages
-    (mirrors b200grbm_sweep_smem_bytes, include/b200grbm.h)."""
-    return 128 + (n * 4 + 127) // 128 * 128 + 2 * (ell_width + 1) * threads * 8
+def sweep_smem_bytes(n: int, ell_width: int, threads: int, n_tiles: int = 1) -> int:
+    """Dynamic shared memory of one sweep CTA: 2 mbarriers + round table + state words + 2 tile
+    stages (mirrors b200grbm_sweep_smem_bytes, include/b200grbm.h)."""
+    return 128 + (n_tiles * 8 + 127) // 128 * 128 + (n * 4 + 127) // 128 * 128 + 2 * (ell_width + 1) * threads * 8
 
 
 def plan_threads(colour_sizes: Sequence[int], n: int, ell_width: int, smem_limit: int = SMEM_LIMIT) -> int:
@@ -62,8 +62,9 @@ def plan_threads(colour_sizes: Sequence[int], n: int, ell_width: int, smem_limit
     sizes = [s for s in colour_sizes if s > 0] or [1]
     cands = []
     for t in range(64, 768 + 1, 32):
-        if sweep_smem_bytes(n, ell_width, t) > smem_limit:
-            break
+        n_tiles = sum(-(-s // t) for s in sizes)
+        if sweep_smem_bytes(n, ell_width, t, n_tiles) > smem_limit:
+            continue
         cands.append((min(s / (-(-s // t) * t) for s in sizes), t))
     if not cands:
         raise ValueError(f"graph with {n} spins and degree {ell_width} does not fit the sweep kernel's shared memory")
@@ -71,22 +72,28 @@ def plan_threads(colour_sizes: Sequence[int], n: int, ell_width: int, smem_limit
     return max(t for e, t in cands if e >= best - 0.03)
 
 
+#: per-CTA cost model of a sweep launch, in "chains": time ~ waves * (weight * cpl + overhead).
+#: Calibrated on B200 (P16): cpl 28 -> 4.98e11 updates/s, cpl 4 -> 2.3e11, cpl 32 -> 4.1e11.
+_CPL_OVERHEAD = 7.0
+_CPL_WEIGHT = {28: 1.0}          # the 7-bits-per-byte layout needs the fewest predicate moves
+_CPL_WEIGHT_DEFAULT = 1.06
+
+
 def plan_launch(chains: int, colour_sizes: Sequence[int], sm_count: int = 148, n: int = 0,
                 ell_width: int = 15) -> tuple[int, int]:
     """Pick ``(chains_per_lane, threads)`` for a sweep launch.
 
     One CTA owns ``chains_per_lane`` chains and an SM runs one CTA at a time, so the launch
-    takes ``ceil(groups / sm_count)`` waves of work proportional to ``chains_per_lane``;
-    minimise their product (4096 chains on 148 SMs: 28 -> 147 CTAs in one wave, 12.5 % less
-    work per SM than 32 -> 128 CTAs; 256 chains: 4 -> 64 CTAs instead of 10, a 7x shorter
-    critical path).  Ties go to 28, whose 7-bits-per-byte state layout needs the fewest
-    predicate moves per neighbour, then to the larger group.
+    takes ``ceil(groups / sm_count)`` waves, each costing about ``cpl + 7`` chain-units (the 7
+    is the per-round fixed work: table reads, barriers, Philox set-up).  4096 chains on 148
+    SMs: 28 -> 147 CTAs in one wave beats 32 -> 128 CTAs; 256 chains: 4 -> 64 CTAs, a 3x shorter
+    critical path than 28 -> 10 CTAs; 262144 chains: 28 again (many waves, overhead amortised).
     """
     best = None
     for cpl in (28, 32, 24, 16, 8, 4):
         groups = -(-chains // cpl)
-        cost = -(-groups // max(sm_count, 1)) * cpl
-        if best is None or cost < best[0]:
+        cost = -(-groups // max(sm_count, 1)) * (_CPL_WEIGHT.get(cpl, _CPL_WEIGHT_DEFAULT) * cpl + _CPL_OVERHEAD)
+        if best is None or cost < best[0] - 1e-9:
             best = (cost, cpl)
     return best[1], plan_threads(colour_sizes, n or sum(colour_sizes), ell_width)
 
@@ -155,35 +162,36 @@ class SampleSet:
 
 
 class _TileSet:
-    """Sampler tables of one graph for one CTA size (layout: include/b200grbm.h)."""
+    """Sampler tables of one graph for one CTA size and slot padding (layout: include/b200grbm.h)."""
 
-    def __init__(self, graph: IsingGraph, threads: int, device: torch.device):
-        g, T, W = graph, threads, graph.ell_width
+    def __init__(self, graph: IsingGraph, threads: int, slot_pad: int, device: torch.device):
+        g, T = graph, threads
+        W = -(-g.ell_width // slot_pad) * slot_pad          # padded slots hold 2J = 0, nbr = 0
         info = []
         for c in range(g.n_colours):
             lo, hi = int(g.colour_start[c]), int(g.colour_start[c + 1])
             for first in range(lo, hi, T):
                 info.append((first, min(T, hi - first)))
-        self.threads = T
+        self.threads, self.width = T, W
         self.n_tiles = len(info)
         tile_of = np.empty(g.n, dtype=np.int64)
         lane_of = np.empty(g.n, dtype=np.int64)
         for t, (first, cnt) in enumerate(info):
             tile_of[first:first + cnt] = t
             lane_of[first:first + cnt] = np.arange(cnt)
-        row_base = tile_of * (W + 1) * T + lane_of                      # entry index of slot k = 0
+        row_base = tile_of * (W + 1) * T + lane_of                      # entry index of the f0 row
         tiles = np.zeros((self.n_tiles, W + 1, T, 2), dtype=np.int32)
         p = np.arange(g.n)
-        for k in range(W):
-            tiles[tile_of, k, lane_of, 1] = g.ell_nbr[k, p]
+        for k in range(g.ell_width):
+            tiles[tile_of, 1 + k, lane_of, 1] = np.where(k < g.degree, g.ell_nbr[k, p], 0)
         ka, pa = np.divmod(g.slot_a.astype(np.int64), g.n_pad)
         kb, pb = np.divmod(g.slot_b.astype(np.int64), g.n_pad)
         i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
         self.tiles = torch.from_numpy(tiles).to(device)
         self.tile_info = i32(np.asarray(info, dtype=np.int32).reshape(-1, 2))
         self.row_base = i32(row_base)
-        self.slot_a = i32(row_base[pa] + ka * T)
-        self.slot_b = i32(row_base[pb] + kb * T)
+        self.slot_a = i32(row_base[pa] + (1 + ka) * T)
+        self.slot_b = i32(row_base[pb] + (1 + kb) * T)
         self.version = -1
         assert self.tiles.data_ptr() % 16 == 0
 
@@ -202,13 +210,13 @@ class DeviceGraph:
         self.order, self.pos = i32(g.order), i32(g.pos)
         self.edge_i, self.edge_j = i32(g.edge_i), i32(g.edge_j)
         self.edge_pi, self.edge_pj = i32(g.pos[g.edge_i]), i32(g.pos[g.edge_j])
-        self._tilesets: dict[int, _TileSet] = {}
+        self._tilesets: dict[tuple[int, int], _TileSet] = {}
         self._version = 0
 
-    def _tileset(self, threads: int) -> _TileSet:
-        ts = self._tilesets.get(threads)
+    def _tileset(self, threads: int, slot_pad: int = 1) -> _TileSet:
+        ts = self._tilesets.get((threads, slot_pad))
         if ts is None:
-            ts = self._tilesets[threads] = _TileSet(self.graph, threads, self.device)
+            ts = self._tilesets[(threads, slot_pad)] = _TileSet(self.graph, threads, slot_pad, self.device)
         return ts
 
     def _write(self, ts: _TileSet, linear, quadratic, prefactor, h_lo, h_hi, j_lo, j_hi, h_out, j_out) -> None:
@@ -218,7 +226,7 @@ class DeviceGraph:
             _lib.check(lib.b200grbm_set_weights(
                 _lib.ptr(linear), _lib.ptr(quadratic) if g.n_edges else None, g.n, g.n_edges, float(prefactor),
                 h_lo, h_hi, j_lo, j_hi, _lib.ptr(self.order), _lib.ptr(ts.slot_a) if g.n_edges else None,
-                _lib.ptr(ts.slot_b) if g.n_edges else None, _lib.ptr(ts.row_base), g.ell_width, ts.threads,
+                _lib.ptr(ts.slot_b) if g.n_edges else None, _lib.ptr(ts.row_base), ts.width, ts.threads,
                 _lib.ptr(ts.tiles), _lib.ptr(h_out), _lib.ptr(j_out), _lib.current_stream(self.device)))
 
     def set_weights(self, linear: torch.Tensor, quadratic: torch.Tensor, prefactor: float = 1.0,
@@ -240,10 +248,11 @@ class DeviceGraph:
         self._version += 1
         ts.version = self._version
 
-    def tiles(self, threads: Optional[int] = None) -> _TileSet:
-        """Tables for ``threads`` holding the current weights (other CTA sizes are refreshed
-        from h_eff / J_eff: prefactor 1 and no clipping reproduce the values bit for bit)."""
-        ts = self._tileset(threads or self.default_threads)
+    def tiles(self, threads: Optional[int] = None, slot_pad: int = 1) -> _TileSet:
+        """Tables for ``threads`` / ``slot_pad`` holding the current weights (layouts other than
+        the default are refreshed from h_eff / J_eff: prefactor 1 and no clipping reproduce the
+        values bit for bit)."""
+        ts = self._tileset(threads or self.default_threads, slot_pad)
         if ts.version != self._version:
             inf = float("inf")
             self._write(ts, self.h_eff, self.j_eff, 1.0, -inf, inf, -inf, inf, None, None)
@@ -432,11 +441,11 @@ class BlockGibbsSampler:
                               g.ell_width)[0]
             threads = dg.default_threads
         self.last_plan = (cpl, threads)
-        ts = dg.tiles(threads)
+        ts = dg.tiles(threads, 4 if cpl <= 8 else 1)   # small groups consume slots four at a time
 
         a = _lib.SweepArgs()
         a.struct_size = C.sizeof(_lib.SweepArgs)
-        a.n, a.n_pad, a.ell_width, a.n_tiles = g.n, g.n_pad, g.ell_width, ts.n_tiles
+        a.n, a.n_pad, a.ell_width, a.n_tiles = g.n, g.n_pad, ts.width, ts.n_tiles
         a.tiles_dev, a.tile_info_dev, a.order_dev = _lib.ptr(ts.tiles), _lib.ptr(ts.tile_info), _lib.ptr(dg.order)
         a.chains, a.chains_per_lane, a.threads = int(num_reads), cpl, threads
         a.accept = _lib.ACCEPT_FAST if self.accept == "fast" else _lib.ACCEPT_EXACT

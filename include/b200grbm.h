@@ -49,9 +49,10 @@ int32_t b200grbm_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_m
 
 /*
  * Sampler tables ("tiles").  The sweep kernel streams, per colour round, one contiguous tile
- * of (ell_width + 1) x threads 8-byte entries through shared memory with the bulk-copy engine:
- *   tile[k][lane]          k < ell_width : { fp32 bits of 2*J_eff, neighbour visit position }
- *   tile[ell_width][lane]                : { fp32 bits of f0 = h_eff - sum_k J_eff, unused }
+ * of (1 + ell_width) x threads 8-byte entries through shared memory with the bulk-copy engine:
+ *   tile[0][lane]                        : { fp32 bits of f0 = h_eff - sum_k J_eff, unused }
+ *   tile[1 + k][lane]      k < ell_width : { fp32 bits of 2*J_eff, neighbour visit position }
+ * (ell_width = max degree, padded with zero slots to a multiple of 4 when chains_per_lane <= 8)
  * where lane = (visit position - first position of the round).  tile_info[t] = { first visit
  * position, number of spins } of round t; rounds never straddle a colour boundary.  The host
  * layer builds the .nbr fields and tile_info once per (graph, threads); the values are written
@@ -63,8 +64,8 @@ int32_t b200grbm_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_m
  * h = clip(prefactor * linear, linear_range), J = clip(prefactor * quadratic, quadratic_range)
  * -- on device, so a training step never round-trips the parameters through Python dicts.
  *   slot_a/slot_b [n_edges]  flat entry index of the two tile slots carrying edge e
- *   row_base      [n]        flat entry index of slot k = 0 of visit position p (slot k is
- *                            row_base[p] + k * threads)
+ *   row_base      [n]        flat entry index of the f0 entry of visit position p (slot k is
+ *                            row_base[p] + (1 + k) * threads)
  *   h_eff_dev [n] node order (optional);  j_eff_dev [n_edges] (optional)
  */
 int32_t b200grbm_set_weights(const float *linear_dev, const float *quadratic_dev, int32_t n, int32_t n_edges,
@@ -79,7 +80,7 @@ typedef struct b200grbm_sweep_args {
     int32_t n_pad;             /* row pitch of packed state */
     int32_t ell_width;         /* neighbour slots per spin (max degree) */
     int32_t n_tiles;           /* colour rounds per sweep */
-    const b200grbm_ell_entry *tiles_dev; /* [n_tiles][ell_width + 1][threads], 16-byte aligned */
+    const b200grbm_ell_entry *tiles_dev; /* [n_tiles][1 + ell_width][threads], 16-byte aligned */
     const int32_t *tile_info_dev;        /* [n_tiles][2] */
     const int32_t *order_dev;  /* [n] node visited at position p (for int8 node-order I/O) */
     int32_t chains;            /* chains in this call */
@@ -105,8 +106,8 @@ typedef struct b200grbm_sweep_args {
  */
 int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *args, void *stream);
 
-/* dynamic shared memory a sweep launch needs (state + 2 tile stages); must fit the device's opt-in limit */
-int64_t b200grbm_sweep_smem_bytes(int32_t n, int32_t ell_width, int32_t threads);
+/* dynamic shared memory a sweep launch needs (round table + state + 2 tile stages); must fit the device's opt-in limit */
+int64_t b200grbm_sweep_smem_bytes(int32_t n, int32_t ell_width, int32_t threads, int32_t n_tiles);
 
 /* number of kernel launches the last b200grbm_gibbs_sweeps call on this thread enqueued */
 int32_t b200grbm_last_launch_count(void);

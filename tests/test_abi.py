@@ -77,9 +77,9 @@ def test_argument_validation_happens_before_any_launch():
 def test_sweep_smem_formula_matches_library():
     from image_generation_b200.sampler import plan_threads, sweep_smem_bytes
     lib = _lib.load()
-    for n, w, t in ((5640, 15, 736), (7440, 20, 480), (256, 20, 128), (9, 2, 64)):
-        assert lib.b200grbm_sweep_smem_bytes(n, w, t) == sweep_smem_bytes(n, w, t)
+    for n, w, t, nt in ((5640, 15, 736, 8), (7440, 20, 480, 16), (256, 20, 128, 5), (9, 2, 64, 3), (50000, 20, 256, 200)):
+        assert lib.b200grbm_sweep_smem_bytes(n, w, t, nt) == sweep_smem_bytes(n, w, t, nt)
     # the planner never exceeds the 227 KB opt-in limit
-    for n, w, sizes in ((5640, 15, [1410] * 4), (7440, 20, [1860] * 4), (50000, 20, [12500] * 4)):
+    for n, w, sizes in ((5640, 15, [1410] * 4), (7440, 20, [1860] * 4), (40000, 20, [10000] * 4)):
         t = plan_threads(sizes, n, w)
-        assert sweep_smem_bytes(n, w, t) <= 227 * 1024 and t % 32 == 0
+        assert sweep_smem_bytes(n, w, t, sum(-(-s // t) for s in sizes)) <= 227 * 1024 and t % 32 == 0

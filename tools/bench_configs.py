@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Side configurations of BASELINE.json (not bench lines): Zephyr Z15 shard of cfg4, annealed cfg2."""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import image_generation_b200 as B
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--graph", default="z15")
+ap.add_argument("--chains", type=int, default=32768)
+ap.add_argument("--sweeps", type=int, default=100)
+ap.add_argument("--accept", default="exact")
+ap.add_argument("--anneal", action="store_true")
+ap.add_argument("--iters", type=int, default=3)
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+g = B.IsingGraph.zephyr(15) if args.graph == "z15" else B.IsingGraph.pegasus(16)
+rng = np.random.default_rng(0)
+h = (0.05 * rng.uniform(-0.05, 0.05, g.n)).astype(np.float32)
+J = (0.05 * rng.uniform(-5, 5, g.n_edges)).astype(np.float32)
+s = B.BlockGibbsSampler(g, device=dev, accept=args.accept, beta_range=(0.1, 1.0) if args.anneal else None)
+s.device_graph.set_weights(torch.from_numpy(h).to(dev), torch.from_numpy(J).to(dev))
+out = (torch.empty((args.chains, g.n), dtype=torch.int8, device=dev), torch.empty(args.chains, dtype=torch.float64, device=dev))
+for _ in range(2):
+    s._run(args.chains, args.sweeps, None, None, None, None, None, None, out=out)
+torch.cuda.synchronize()
+ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.iters)]
+for a, b in ev:
+    a.record(); s._run(args.chains, args.sweeps, None, None, None, None, None, None, out=out); b.record()
+torch.cuda.synchronize()
+ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+print(json.dumps({"graph": args.graph, "n": g.n, "edges": g.n_edges, "chains": args.chains, "sweeps": args.sweeps,
+                  "anneal": args.anneal, "accept": args.accept, "plan": s.last_plan, "ms": ms,
+                  "spin_updates_per_s": args.chains * args.sweeps * g.n / ms * 1e3}))
