@@ -21,9 +21,9 @@
 // Warp roles (320 threads, one persistent CTA per SM): warp 0 lane 0 = TMA producer,
 // warp 1 = TMEM allocator + (lane 0) MMA issuer, warps 2..9 = epilogue (two column halves x
 // four TMEM lane quarters).
-#include "common.cuh"
+#include "tc_common.cuh"
 
-#include <cuda.h>
+#include <cuda_bf16.h>
 
 namespace b200grbm {
 
@@ -38,7 +38,7 @@ constexpr int TC_THREADS = 320;
 constexpr int EPI_WARPS = 8;
 constexpr uint32_t TMEM_COLS = 512;
 
-enum { TC_PASS_DIST = 0, TC_PASS_KERNEL = 1 };
+enum { TC_PASS_DIST = 0, TC_PASS_KERNEL = 1, TC_PASS_COEF = 2 };
 
 struct TcParams {
     int m_x, m, d;
@@ -48,101 +48,21 @@ struct TcParams {
     int pass;
     const float *lut;   // [d + 1]
     double *sums;       // [4]
+    // TC_PASS_COEF: backward coefficients A[a][b] = w * c(h_ab), written as a bf16 (hi, lo) pair
+    int tiles_mx;       // row tiles covering the x rows
+    int m_pad;          // row pitch (elements) of coef_hi / coef_lo, multiple of 64
+    float w_xx, w_xy;
+    __nv_bfloat16 *coef_hi, *coef_lo;
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-
-__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void bar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (spin > (1u << 26)) __trap();   // a broken pipeline must fail the launch, never hang the GPU
-    }
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-        "l"(map), "r"(x), "r"(y), "r"(bar)
-        : "memory");
-}
-
-// K-major operand, 128-byte swizzle: rows are 128 B apart, 8-row groups 1024 B apart (SBO),
-// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.  (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(1024u >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-// cute::UMMA::InstrDescriptor for kind::i8: D = S32, A = B = signed int8, both K-major
-__device__ __forceinline__ constexpr uint32_t umma_idesc_i8(int m, int n)
-{
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // upper-triangle tile enumeration: column tile j ascending, row tiles i = 0 .. min(tiles_m, 2j+2) - 1
 __device__ __forceinline__ void tile_coords(const TcParams &p, int t, int &i, int &j)
 {
+    if (p.pass == TC_PASS_COEF) {          // full rectangle: x rows against every column
+        i = t % p.tiles_mx;
+        j = t / p.tiles_mx;
+        return;
+    }
     if (t < p.p0) {
         j = (int)((sqrtf(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
         while ((j + 1) * (j + 2) <= t) ++j;
@@ -266,7 +186,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
                 const int cbase = half * 128 + chunk * 32;
                 __syncwarp();                                   // tcgen05.ld is .sync.aligned
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + (uint32_t)cbase, v);
-                if (pure) {
+                if (p.pass == TC_PASS_COEF) {
+                    // 32 consecutive coefficients of this thread's row -> bf16 hi / lo halves, 64 B each
+                    if (row < p.m_x) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int c = 0; c < 32; c += 2) {
+                            float cf[2];
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const int col = col0 + cbase + c + q;
+                                const float raw = lut[(two_d - 2 * (int)v[c + q]) >> 2];
+                                cf[q] = (col < p.m && col != row) ? raw * (col < p.m_x ? p.w_xx : p.w_xy) : 0.f;
+                            }
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(cf[0], cf[1]);
+                            const __nv_bfloat162 l2 = __floats2bfloat162_rn(cf[0] - __low2float(h2), cf[1] - __high2float(h2));
+                            hi[c >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
+                            lo[c >> 1] = *reinterpret_cast<const uint32_t *>(&l2);
+                        }
+                        const size_t off = (size_t)row * p.m_pad + (size_t)(col0 + cbase);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (col0 + cbase + 8 * q < p.m_pad) {
+                                *reinterpret_cast<uint4 *>(p.coef_hi + off + 8 * q) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                                *reinterpret_cast<uint4 *>(p.coef_lo + off + 8 * q) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+                            }
+                        }
+                    }
+                } else if (pure) {
                     float part = 0.f;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) part += lut[(two_d - 2 * (int)v[c]) >> 2];
@@ -316,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
         double tot = 0.0;
         for (int w = 0; w < EPI_WARPS; ++w) tot += red[threadIdx.x][w];
         if (p.pass == TC_PASS_DIST) { if (threadIdx.x == 0) atomicAdd(p.sums + 3, tot); }
-        else if (tot != 0.0) atomicAdd(p.sums + threadIdx.x, tot);
+        else if (p.pass == TC_PASS_KERNEL && tot != 0.0) atomicAdd(p.sums + threadIdx.x, tot);
     }
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -334,9 +281,16 @@ __global__ void mmd_lut_kernel(int pass, int d, int m, int n_kernels, float mul_
     if (pass == TC_PASS_DIST) { lut[h] = (float)t; return; }
     const double mm = (double)m;
     const double bw = bandwidth > 0.f ? (double)bandwidth : sums[3] / (mm * mm - mm);
-    double k = 0.0;
-    for (int u = 0; u < n_kernels; ++u) k += exp(-t / (bw * pow((double)mul_factor, (double)(u - n_kernels / 2))));
-    lut[h] = (float)k;
+    double k = 0.0, dk = 0.0;                       // k(t) and dk/dt
+    for (int u = 0; u < n_kernels; ++u) {
+        const double b = bw * pow((double)mul_factor, (double)(u - n_kernels / 2));
+        const double e = exp(-t / b);
+        k += e;
+        dk -= e / b;
+    }
+    if (pass == TC_PASS_KERNEL) { lut[h] = (float)k; return; }
+    // TC_PASS_COEF: (dk/dt) (dt/d||.||) / ||.||  -> multiplies (x_a - z_b);  zero where the rows coincide
+    lut[h] = h == 0 ? 0.f : (float)(squared ? 2.0 * dk : dk / t);
 }
 
 // sign-pack fp32 rows into the zero-padded int8 matrix the TMA descriptor reads
@@ -349,11 +303,7 @@ __global__ void mmd_pack_i8_kernel(const float *__restrict__ z, int m, int d, in
     out[idx] = c < d ? (z[(size_t)r * d + c] > 0.f ? (int8_t)1 : (int8_t)-1) : (int8_t)0;
 }
 
-typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int32_t get_encode(encode_tiled_fn *out)
+int32_t get_tensor_map_encoder(encode_tiled_fn *out)
 {
     static encode_tiled_fn cached = nullptr;
     if (cached == nullptr) {
@@ -365,6 +315,25 @@ static int32_t get_encode(encode_tiled_fn *out)
         cached = reinterpret_cast<encode_tiled_fn>(fn);
     }
     *out = cached;
+    return 0;
+}
+
+int32_t make_tensor_map_2d(CUtensorMap *map, const void *base, CUtensorMapDataType dtype, uint64_t inner_elems,
+                           uint64_t rows, uint64_t row_pitch_bytes, uint32_t box_inner_elems, uint32_t box_rows)
+{
+    encode_tiled_fn encode = nullptr;
+    B200_TRY(get_tensor_map_encoder(&encode));
+    // cuTensorMapEncodeTiled is a driver-API call: make sure the runtime's primary context is
+    // current on THIS thread (autograd runs backward passes on its own threads)
+    B200_CUDA(cudaFree(nullptr));
+    const cuuint64_t gdim[2] = {(cuuint64_t)inner_elems, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)row_pitch_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)box_inner_elems, (cuuint32_t)box_rows};
+    const cuuint32_t estride[2] = {1u, 1u};
+    const CUresult cr = encode(map, dtype, 2, const_cast<void *>(base), gdim, gstride, box, estride,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(B200GRBM_EINVAL, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
     return 0;
 }
 
@@ -414,17 +383,8 @@ extern "C" int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int
         return fail(B200GRBM_EUNSUPPORTED, "mmd_forward_i8: d=%d needs a %zu B look-up table, too large for shared memory", d,
                     lut_bytes);
 
-    encode_tiled_fn encode = nullptr;
-    B200_TRY(get_encode(&encode));
     CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)d_pad, (cuuint64_t)m};
-    const cuuint64_t gstride[1] = {(cuuint64_t)d_pad};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, 128u};
-    const cuuint32_t estride[2] = {1u, 1u};
-    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(z_dev), gdim, gstride, box,
-                               estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) return fail(B200GRBM_EINVAL, "mmd_forward_i8: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    B200_TRY(make_tensor_map_2d(&tmap, z_dev, CU_TENSOR_MAP_DATA_TYPE_UINT8, (uint64_t)d_pad, (uint64_t)m, (uint64_t)d_pad, BK, 128));
 
     TcParams p = {};
     p.m_x = m_x; p.m = m; p.d = d;
@@ -455,6 +415,61 @@ extern "C" int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int
                                                lut_dev);
     B200_CUDA(cudaGetLastError());
     p.pass = TC_PASS_KERNEL;
+    mmd_gram_i8_kernel<<<grid, TC_THREADS, smem + 1024, st>>>(tmap, p);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int32_t b200grbm_mmd_coef_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,
+                                        int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth,
+                                        const double *sums_dev, float w_xx, float w_xy, float *lut_dev,
+                                        void *coef_hi_dev, void *coef_lo_dev, int32_t m_pad, void *stream)
+{
+    if (m_x <= 0 || m_y <= 0 || d <= 0 || d_pad < d || d_pad % 16 != 0)
+        return fail(B200GRBM_EINVAL, "mmd_coef_i8: m_x=%d m_y=%d d=%d d_pad=%d", m_x, m_y, d, d_pad);
+    const int m = m_x + m_y;
+    if (m_pad < m || m_pad % 64 != 0) return fail(B200GRBM_EINVAL, "mmd_coef_i8: m_pad=%d must be a multiple of 64 >= m=%d", m_pad, m);
+    if (n_kernels < 1 || n_kernels > 16 || !(mul_factor > 0.f))
+        return fail(B200GRBM_EINVAL, "mmd_coef_i8: n_kernels=%d mul_factor=%g", n_kernels, mul_factor);
+    if (!z_dev || !lut_dev || !sums_dev || !coef_hi_dev || !coef_lo_dev)
+        return fail(B200GRBM_EINVAL, "mmd_coef_i8: NULL pointer argument");
+    if (((reinterpret_cast<uintptr_t>(z_dev) | reinterpret_cast<uintptr_t>(coef_hi_dev) | reinterpret_cast<uintptr_t>(coef_lo_dev)) & 15u) != 0)
+        return fail(B200GRBM_EINVAL, "mmd_coef_i8: z_dev / coef buffers must be 16-byte aligned");
+    B200_TRY(require_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, smem_optin = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t lut_bytes = ((size_t)(d + 1) * 4 + 15) / 16 * 16;
+    int stages = 4;
+    size_t smem = 0;
+    for (; stages >= 2; --stages) {
+        smem = (size_t)stages * STAGE_BYTES + lut_bytes + (2 * stages + 4) * 8 + 16;
+        if (smem + 1024 <= (size_t)smem_optin) break;
+    }
+    if (stages < 2) return fail(B200GRBM_EUNSUPPORTED, "mmd_coef_i8: d=%d look-up table does not fit shared memory", d);
+    CUtensorMap tmap;
+    B200_TRY(make_tensor_map_2d(&tmap, z_dev, CU_TENSOR_MAP_DATA_TYPE_UINT8, (uint64_t)d_pad, (uint64_t)m, (uint64_t)d_pad, BK, 128));
+    TcParams p = {};
+    p.m_x = m_x; p.m = m; p.d = d;
+    p.n_kblocks = (d_pad + BK - 1) / BK;
+    p.tiles_m = (m + BM - 1) / BM;
+    p.tiles_n = (m_pad + BN - 1) / BN;        // cover the zero padding columns as well
+    p.tiles_mx = (m_x + BM - 1) / BM;
+    p.total_tiles = p.tiles_mx * p.tiles_n;
+    p.stages = stages;
+    p.pass = TC_PASS_COEF;
+    p.lut = lut_dev;
+    p.sums = const_cast<double *>(sums_dev);
+    p.m_pad = m_pad; p.w_xx = w_xx; p.w_xy = w_xy;
+    p.coef_hi = reinterpret_cast<__nv_bfloat16 *>(coef_hi_dev);
+    p.coef_lo = reinterpret_cast<__nv_bfloat16 *>(coef_lo_dev);
+    B200_CUDA(cudaFuncSetAttribute(mmd_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + 1024)));
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    mmd_lut_kernel<<<(d + 1 + 255) / 256, 256, 0, st>>>(TC_PASS_COEF, d, m, n_kernels, mul_factor, squared, bandwidth, sums_dev,
+                                                        lut_dev);
+    B200_CUDA(cudaGetLastError());
     mmd_gram_i8_kernel<<<grid, TC_THREADS, smem + 1024, st>>>(tmap, p);
     B200_CUDA(cudaGetLastError());
     return 0;

@@ -102,8 +102,11 @@ class _MMDFunction(torch.autograd.Function):
     def forward(ctx, x, y, kernel: GaussianKernel, estimator: str, path: str):
         m_x, m_y = x.shape[0], y.shape[0]
         z = torch.cat([x.detach().to(torch.float32), y.detach().to(torch.float32)], 0).contiguous()
+        zi = None
         if path == "i8":
-            sums = mmd_block_sums(torch.sign(z).to(torch.int8), m_x, kernel, "i8")
+            from .mmd_tc import mmd_block_sums_i8, pack_rows_i8
+            zi, _ = pack_rows_i8(z)                       # sign-packed, zero-padded int8 rows (kept for backward)
+            sums = mmd_block_sums_i8(zi, m_x, kernel, d=z.shape[1])
         else:
             sums = mmd_block_sums(z, m_x, kernel, "f32")
         scale = 1.0 / kernel.n_kernels if kernel.reduce == "mean" else 1.0
@@ -120,15 +123,20 @@ class _MMDFunction(torch.autograd.Function):
             w_xx = 2.0 / (m_x * m_x)
         xy = sums[2] / (m_x * m_y)
         val = scale * (xx + yy - 2.0 * xy)
-        ctx.save_for_backward(z, sums)
-        ctx.meta = (m_x, m_y, kernel, scale * w_xx, -2.0 * scale / (m_x * m_y))
+        if zi is not None:
+            ctx.save_for_backward(zi, sums)
+        else:
+            ctx.save_for_backward(z, sums)
+        ctx.meta = (m_x, m_y, kernel, scale * w_xx, -2.0 * scale / (m_x * m_y), path, z.shape[1])
         return val.to(x.dtype if x.dtype.is_floating_point else torch.float32)
 
     @staticmethod
     def backward(ctx, grad_out):
         z, sums = ctx.saved_tensors
-        m_x, m_y, kernel, w_xx, w_xy = ctx.meta
-        d = z.shape[1]
+        m_x, m_y, kernel, w_xx, w_xy, path, d = ctx.meta
+        if path == "i8":
+            from .mmd_tc import mmd_backward_i8
+            return mmd_backward_i8(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out.detach().reshape(())), None, None, None, None
         coef = torch.empty((m_x, m_x + m_y), dtype=torch.float32, device=z.device)
         grad_x = torch.empty((m_x, d), dtype=torch.float32, device=z.device)
         g = grad_out.detach().reshape(1).to(torch.float32).contiguous()
@@ -149,7 +157,9 @@ def maximum_mean_discrepancy_loss(x: torch.Tensor, y: torch.Tensor, kernel: Gaus
     ``path="i8"`` sign-packs both inputs and runs the Gram contraction on the tcgen05 int8
     tensor-core kernel (exact for +-1 rows; encoder spins carry only straight-through residue
     ~1e-7, src/utils/common.py:162-173); ``"f32"`` is the precise CUDA-core path for arbitrary
-    real inputs.  The backward pass uses the fp32 kernels in either case.
+    real inputs.  The backward pass of the ``"i8"`` path also runs on tensor cores (coefficient
+    matrix from the int8 Gram as a bf16 hi/lo pair, then one bf16 GEMM); the gradient is
+    evaluated at the sign-packed points.
     """
     if estimator not in ("unbiased", "biased"):
         raise ValueError("estimator must be 'unbiased' or 'biased'")

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["pack_rows_i8", "mmd_block_sums_i8"]
+__all__ = ["pack_rows_i8", "mmd_block_sums_i8", "mmd_backward_i8", "gemm_bf16_tn"]
 
 
 def pack_rows_i8(z: torch.Tensor) -> tuple[torch.Tensor, int]:
@@ -34,10 +34,15 @@ def pack_rows_i8(z: torch.Tensor) -> tuple[torch.Tensor, int]:
     return out, d_pad
 
 
-def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = None) -> torch.Tensor:
-    """``[S_xx, S_yy, S_xy, sum_ab t_ab]`` (float64) for +-1 rows ``z = [x; y]`` on tensor cores."""
-    m, d = z.shape
-    zi, d_pad = pack_rows_i8(z)
+def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = None, d: int = None) -> torch.Tensor:
+    """``[S_xx, S_yy, S_xy, sum_ab t_ab]`` (float64) for +-1 rows ``z = [x; y]`` on tensor cores.
+    ``d``: true feature count when ``z`` is already the zero-padded int8 matrix of :func:`pack_rows_i8`."""
+    m = z.shape[0]
+    if d is None:
+        d = z.shape[1]
+        zi, d_pad = pack_rows_i8(z)
+    else:
+        zi, d_pad = z, z.shape[1]
     if sums is None:
         sums = torch.empty(4, dtype=torch.float64, device=z.device)
     lut = torch.empty(d + 1, dtype=torch.float32, device=z.device)
@@ -48,3 +53,47 @@ def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = No
                                                kernel.mul_factor, int(kernel.squared), bw, _lib.ptr(lut),
                                                _lib.ptr(sums), _lib.current_stream(z.device)))
     return sums
+
+
+def gemm_bf16_tn(a_hi: torch.Tensor, a_lo, b: torch.Tensor, m_rows: int) -> torch.Tensor:
+    """``C[m_rows, N] = (a_hi + a_lo)[:m_rows] @ b.T`` on the tcgen05 bf16 kernel (fp32 out).
+    ``a_hi`` / ``a_lo``: bf16 ``(rows_alloc, K)``, ``b``: bf16 ``(N, K)``, ``K`` a multiple of 64."""
+    rows_alloc, k = a_hi.shape
+    n = b.shape[0]
+    ldc = (n + 3) // 4 * 4
+    c = torch.empty((m_rows, ldc), dtype=torch.float32, device=a_hi.device)
+    lib = _lib.load()
+    with torch.cuda.device(a_hi.device):
+        _lib.check(lib.b200grbm_gemm_bf16_tn(_lib.ptr(a_hi), _lib.ptr(a_lo), m_rows, k, rows_alloc, _lib.ptr(b), n,
+                                             _lib.ptr(c), ldc, _lib.current_stream(a_hi.device)))
+    return c[:, :n]
+
+
+def mmd_backward_i8(zi: torch.Tensor, d: int, m_x: int, kernel, sums: torch.Tensor, w_xx: float, w_xy: float,
+                    grad_out: torch.Tensor) -> torch.Tensor:
+    """d(MMD)/dx for +-1 rows on tensor cores: coefficient matrix from the int8 Gram (bf16 hi/lo
+    pair), then one bf16 GEMM against ``[Z^T; 1]`` -- the extra column is the row sum:
+    ``grad_x[a] = rowsum_a x_a - (A Z)_a``.  ``zi``: the packed int8 ``(m, d_pad)`` rows of the forward."""
+    m, d_pad = zi.shape
+    dev = zi.device
+    m_pad = (m + 63) // 64 * 64
+    rows_alloc = (m_x + 127) // 128 * 128
+    a_hi = torch.empty((rows_alloc, m_pad), dtype=torch.bfloat16, device=dev)
+    a_lo = torch.empty((rows_alloc, m_pad), dtype=torch.bfloat16, device=dev)
+    if rows_alloc > m_x:           # rows the kernel never writes are still read by TMA: keep them finite
+        a_hi[m_x:].zero_()
+        a_lo[m_x:].zero_()
+    lut = torch.empty(d + 1, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    bw = -1.0 if kernel.bandwidth is None else kernel.bandwidth
+    with torch.cuda.device(dev):
+        _lib.check(lib.b200grbm_mmd_coef_i8(_lib.ptr(zi), m_x, m - m_x, d, d_pad, kernel.n_kernels, kernel.mul_factor,
+                                            int(kernel.squared), bw, _lib.ptr(sums), w_xx, w_xy, _lib.ptr(lut),
+                                            _lib.ptr(a_hi), _lib.ptr(a_lo), m_pad, _lib.current_stream(dev)))
+    # B = [Z^T; 1] as bf16 (N = d + 1 rows, K = m_pad): layout preparation only
+    b = torch.zeros((d + 1, m_pad), dtype=torch.bfloat16, device=dev)
+    b[:d, :m] = zi[:, :d].t()
+    b[d, :m] = 1
+    c = gemm_bf16_tn(a_hi, a_lo, b, m_x)                       # (m_x, d + 1)
+    x = zi[:m_x, :d].to(torch.float32)
+    return grad_out.to(torch.float32) * (c[:, d:d + 1] * x - c[:, :d])

@@ -188,6 +188,23 @@ int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, i
                                 int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth, float *lut_dev,
                                 double *sums_dev, void *stream);
 
+/*
+ * Backward of the +-1 MMD on tensor cores (dvae_loss.backward() through the MMD term,
+ * src/model_wrapper.py:320-326):  grad_x[a] = rowsum_a(A) x_a - (A Z)_a.
+ * b200grbm_mmd_coef_i8 re-runs the int8 Gram over (x rows) x (all rows) and writes
+ * A_ab = w * (dk/dt)(dt/d||.||)/||.|| (w = w_xx for x-x pairs, w_xy for x-y pairs, 0 on the
+ * diagonal and on padding) as a bf16 (hi, lo) pair, row pitch m_pad (multiple of 64, >= m);
+ * both buffers hold at least ceil(m_x / 128) * 128 rows.  sums_dev[3] is the forward's distance sum.
+ * b200grbm_gemm_bf16_tn: C[M][ldc] (fp32) = (A_hi + A_lo)[M][K] * B[N][K]^T with bf16 operands
+ * (tcgen05.mma.kind::f16); a_lo_dev may be NULL; a_rows_alloc = rows allocated in the A buffers.
+ */
+int32_t b200grbm_mmd_coef_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad, int32_t n_kernels,
+                             float mul_factor, int32_t squared, float bandwidth, const double *sums_dev, float w_xx,
+                             float w_xy, float *lut_dev, void *coef_hi_dev, void *coef_lo_dev, int32_t m_pad,
+                             void *stream);
+int32_t b200grbm_gemm_bf16_tn(const void *a_hi_dev, const void *a_lo_dev, int32_t M, int32_t K, int32_t a_rows_alloc,
+                              const void *b_dev, int32_t N, float *c_dev, int32_t ldc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,7 +140,50 @@ def test_tensor_core_path_agrees_with_cuda_core_path_and_loss(cuda_device):
     b = float(B.maximum_mean_discrepancy_loss(xt, yt, kern, path="i8"))
     want, scale = _terms(x, y)
     assert abs(a - want) <= 1e-5 * scale and abs(b - want) <= 1e-5 * scale
-    # gradient still flows through the i8 forward (backward runs the fp32 kernels)
+    # gradients: tensor-core backward (int8 Gram -> bf16 hi/lo coefficients -> bf16 GEMM) vs CUDA-core backward
     xg = xt.clone().requires_grad_(True)
     B.maximum_mean_discrepancy_loss(xg, yt, kern, path="i8").backward()
-    assert torch.isfinite(xg.grad).all() and float(xg.grad.abs().max()) > 0
+    xf = xt.clone().requires_grad_(True)
+    B.maximum_mean_discrepancy_loss(xf, yt, kern, path="f32").backward()
+    ref = xf.grad.cpu().numpy()
+    np.testing.assert_allclose(xg.grad.cpu().numpy(), ref, rtol=1e-3, atol=3e-5 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("m_x,m_y,d,squared,estimator", [(128, 128, 64, False, "unbiased"), (200, 77, 100, False, "biased"),
+                                                           (70, 45, 333, True, "unbiased"), (1024, 256, 256, False, "unbiased")])
+def test_tensor_core_backward_matches_oracle(cuda_device, m_x, m_y, d, squared, estimator):
+    """d(MMD)/dx on tensor cores vs the float64 oracle at +-1 points (bandwidth frozen = .detach())."""
+    rng = np.random.default_rng(m_x * 7 + d)
+    x = _spins(rng, m_x, d)
+    y = _spins(rng, m_y, d)
+    y[:, : d // 4] = 1.0
+    kern = B.GaussianKernel(7, squared=squared).to(cuda_device)
+    xt = torch.from_numpy(x).to(cuda_device).requires_grad_(True)
+    val = B.maximum_mean_discrepancy_loss(xt, torch.from_numpy(y).to(cuda_device), kern, estimator=estimator, path="i8")
+    (2.0 * val).backward()
+    bw = O.gaussian_kernel_matrix(np.concatenate([x, y]).astype(np.float64), squared=squared)[1]
+    want_val, grad = O.mmd(x, y, squared=squared, estimator=estimator, bandwidth=bw, return_grad=True)
+    got = xt.grad.cpu().numpy() / 2.0
+    assert got.shape == grad.shape
+    # bf16 (hi, lo) coefficients carry 2^-16 relative error each; sums of ~m terms
+    np.testing.assert_allclose(got, grad, rtol=2e-3, atol=5e-5 * np.abs(grad).max())
+    rel = np.linalg.norm(got - grad) / np.linalg.norm(grad)
+    assert rel < 2e-4, rel
+
+
+def test_bf16_gemm_kernel_matches_torch(cuda_device):
+    from image_generation_b200.mmd_tc import gemm_bf16_tn
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for (M, N, K) in ((128, 256, 64), (200, 300, 192), (1000, 257, 1280), (64, 5, 64)):
+        rows_alloc = (M + 127) // 128 * 128
+        a = torch.zeros((rows_alloc, K), dtype=torch.float32)
+        a[:M] = torch.randn((M, K), generator=g)
+        b = torch.randn((N, K), generator=g)
+        a_hi = a.to(torch.bfloat16)
+        a_lo = (a - a_hi.float()).to(torch.bfloat16)
+        bb = b.to(torch.bfloat16)
+        got = gemm_bf16_tn(a_hi.to(cuda_device), a_lo.to(cuda_device), bb.to(cuda_device), M).cpu()
+        want = (a_hi.double() + a_lo.double())[:M] @ bb.double().t()
+        torch.testing.assert_close(got.double(), want, rtol=1e-5, atol=1e-4)
+        got1 = gemm_bf16_tn(a_hi.to(cuda_device), None, bb.to(cuda_device), M).cpu()
+        torch.testing.assert_close(got1.double(), a_hi.double()[:M] @ bb.double().t(), rtol=1e-5, atol=1e-4)
