@@ -283,7 +283,10 @@ def run_b200(args):
     hbm_bytes = 2.0 * chains * g.n                      # int8 state written once (+ read when resuming chains)
     roofline = {
         "bound": "smem", "kernel": "b200grbm::gibbs_kernel", "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
-        "frac": achieved / smem_peak, "traffic": None,
+        "frac": achieved / smem_peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one gibbs_kernel launch in the committed ncu --set full capture
+        # (profiles/r1_gibbs_v4_ncu_summary.txt; 20-sweep launch, the final state write mostly still sits in L2)
+        "traffic": 968704 + 153856, "traffic_note": "ncu capture of a 20-sweep launch; algorithmic HBM bytes per launch = state write 23.1 MB",
         "algorithmic_bytes_per_update": P16_MEAN_DEGREE + 1.0, "updates_per_launch": upd_per_launch,
         "kernel_ms": kernel_s * 1e3,
         "peak_source": f"SURVEY.md 8(d): n_SM({sms}) x 128 B/clk x SM clock sampled under load ({f_sm / 1e6:.0f} MHz)",
@@ -351,6 +354,25 @@ def bench_mmd(dev, peaks, m_each=8192, d=5640, iters=5):
                          "frac": executed / ms / 1e9 / i8_peak, "traffic": None,
                          "peak_source": "2 x measured bf16 burst (MEASURED_PEAKS.json has no int8 figure)",
                          "executed_ops": executed, "note": "symmetric: only the upper triangle of tiles is contracted"}}
+    # value + gradient wrt x through the public call (what ModelWrapper.step does at src/model_wrapper.py:320-326)
+    x = z[:m_each].float().requires_grad_(True)
+    y = z[m_each:].float()
+    kern = B.GaussianKernel(7).to(dev)
+    for _ in range(2):
+        x.grad = None
+        B.maximum_mean_discrepancy_loss(x, y, kern, path="i8").backward()
+    torch.cuda.synchronize(dev)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    x.grad = None
+    e0.record()
+    val = B.maximum_mean_discrepancy_loss(x, y, kern, path="i8")
+    e1.record()
+    val.backward()
+    e2.record()
+    torch.cuda.synchronize(dev)
+    out["loss_call"] = {"forward_ms": e0.elapsed_time(e1), "backward_ms": e1.elapsed_time(e2),
+                        "note": "maximum_mean_discrepancy_loss(x, y, GaussianKernel(7), path='i8') from fp32 inputs: cat + sign-pack + "
+                                "2 Gram passes; backward = int8 Gram coefficient pass (bf16 hi/lo) + tcgen05 bf16 GEMM"}
     out["workload"] = f"MMD {m_each} x {m_each} rows, D = {d}, 7 kernels, int8 +-1 rows (BASELINE.json configs[2])"
     return out
 

@@ -16,14 +16,14 @@ The directory name contains a hyphen; ``import image_generation_b200`` (repo-roo
 ``importlib.import_module("image-generation_b200")`` both resolve to this package.
 """
 from .topology import IsingGraph, pegasus_graph, zephyr_graph, greedy_get_subgraph, get_graph_mapping
-from .sampler import BlockGibbsSampler, SampleSet, plan_launch, beta_schedule
+from .sampler import BlockGibbsSampler, PersistentChains, SampleSet, plan_launch, beta_schedule
 from .grbm import GraphRestrictedBoltzmannMachine
 from .mmd import GaussianKernel, maximum_mean_discrepancy_loss
 from .losses import nll_loss, PersistentQPUSampleHelper
 
 __all__ = [
     "IsingGraph", "pegasus_graph", "zephyr_graph", "greedy_get_subgraph", "get_graph_mapping",
-    "BlockGibbsSampler", "SampleSet", "plan_launch", "beta_schedule",
+    "BlockGibbsSampler", "PersistentChains", "SampleSet", "plan_launch", "beta_schedule",
     "GraphRestrictedBoltzmannMachine", "GaussianKernel", "maximum_mean_discrepancy_loss",
     "nll_loss", "PersistentQPUSampleHelper",
 ]

@@ -269,6 +269,22 @@ class HybridDVAE:
                                     sample_params=self.sampler_kwargs)
         return self._dvae.decoder(samples.unsqueeze(1)).squeeze(1).clip(0.0, 1.0)
 
+    def save(self, file_path) -> None:
+        """``dvae.pth`` + ``grbm.pth`` state dicts in ``file_path`` (src/model_wrapper.py:148-162)."""
+        import os
+        os.makedirs(file_path, exist_ok=True)
+        torch.save(self._dvae.state_dict(), os.path.join(file_path, "dvae.pth"))
+        torch.save(self._grbm.state_dict(), os.path.join(file_path, "grbm.pth"))
+
+    def load(self, file_path) -> None:
+        """Rebuild via ``setup()`` then load both state dicts (src/model_wrapper.py:164-175); works for the
+        reference's shipped ``models/<QPU>_<k>_epochs`` folders.  The sampler is rebuilt on the loaded graph."""
+        import os
+        self.setup()
+        self._dvae.load_state_dict(torch.load(os.path.join(file_path, "dvae.pth"), map_location=self.device, weights_only=True))
+        self._grbm.load_state_dict(torch.load(os.path.join(file_path, "grbm.pth"), map_location=self.device, weights_only=True))
+        self.sampler = self._grbm.make_sampler(self.device, seed=self.RANDOM_SEED, **self._sampler_kwargs_extra)
+
     def state_dicts(self) -> dict:
         """``{"dvae.pth": ..., "grbm.pth": ...}`` with the reference's key layout (src/model_wrapper.py:148-162)."""
         return {"dvae.pth": self._dvae.state_dict(), "grbm.pth": self._grbm.state_dict()}

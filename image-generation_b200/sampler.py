@@ -26,8 +26,8 @@ import torch
 from . import _lib
 from .topology import IsingGraph
 
-__all__ = ["BlockGibbsSampler", "SampleSet", "DeviceGraph", "plan_launch", "plan_threads", "sweep_smem_bytes",
-           "beta_schedule"]
+__all__ = ["BlockGibbsSampler", "PersistentChains", "SampleSet", "DeviceGraph", "plan_launch", "plan_threads",
+           "sweep_smem_bytes", "beta_schedule"]
 
 _LOG2E = 1.4426950408889634
 SUPPORTED_CPL = (4, 8, 16, 24, 28, 32)
@@ -422,7 +422,7 @@ class BlockGibbsSampler:
     def _run(self, num_reads, num_sweeps, beta_range, beta_schedule_type, beta_sched, seed, initial_states,
              uniforms, packed_io: Optional[torch.Tensor] = None, want_int8: bool = True,
              sweep_offset: int = 0, plan: Optional[tuple[int, int]] = None,
-             out: Optional[tuple[torch.Tensor, torch.Tensor]] = None) -> SampleSet:
+             out: Optional[tuple[torch.Tensor, torch.Tensor]] = None, resume: bool = False) -> SampleSet:
         if num_reads <= 0:
             raise ValueError("num_reads must be positive")
         g, dg, dev = self.graph, self.device_graph, self.device
@@ -470,7 +470,7 @@ class BlockGibbsSampler:
             # persistent chains: resume from / write back to a caller-owned packed state
             if tuple(packed_io.shape) != (-(-num_reads // cpl), g.n_pad) or packed_io.dtype != torch.int32:
                 raise ValueError("packed_io must be int32 of shape (ceil(num_reads / chains_per_lane), n_pad)")
-            if initial_states is None and sweep_offset > 0:
+            if initial_states is None and resume:
                 a.packed_in_dev = _lib.ptr(packed_io)
             a.packed_out_dev = _lib.ptr(packed_io)
         samples = None
@@ -494,3 +494,39 @@ class BlockGibbsSampler:
         return SampleSet(self.variables, samples, energies,
                          info={"seed": int(seed), "chains_per_lane": cpl, "threads": threads,
                                "num_sweeps": num_sweeps, "accept": self.accept})
+
+
+class PersistentChains:
+    """Chains that stay resident on the device between calls (persistent contrastive divergence).
+
+    This is the intent behind the reference's ``PersistentQPUSampleHelper`` deque
+    (src/utils/persistent_qpu_sampler.py:41-49, :79-103 -- dead code there because the helper
+    resets itself on every call, SURVEY.md finding 10 / section 8f-4): instead of restarting from
+    random spins at every training step, the bit-packed chain state is kept in HBM and advanced
+    by a few sweeps under the *current* (h, J).  The Philox sweep counter keeps running, so
+    ``advance(a); advance(b)`` is bit-identical to ``advance(a + b)`` under fixed weights.
+    """
+
+    def __init__(self, sampler: BlockGibbsSampler, num_chains: int, seed: Optional[int] = None):
+        if num_chains <= 0:
+            raise ValueError("num_chains must be positive")
+        self.sampler = sampler
+        self.num_chains = int(num_chains)
+        g = sampler.graph
+        self.seed = _splitmix64(sampler.seed) if seed is None else int(seed)
+        dg = sampler.device_graph
+        cpl = plan_launch(num_chains, np.diff(g.colour_start).tolist(), _lib.device_info()["sm_count"], g.n, g.ell_width)[0]
+        self.plan = (cpl, dg.default_threads)
+        self.packed = torch.zeros((-(-num_chains // cpl), g.n_pad), dtype=torch.int32, device=sampler.device)
+        self.sweeps_done = 0
+        self._started = False
+
+    def advance(self, num_sweeps: int, beta_schedule: Optional[Sequence[float]] = None, want_samples: bool = True) -> SampleSet:
+        """Run ``num_sweeps`` more sweeps under the sampler's current weights (set them with
+        ``sampler.device_graph.set_weights`` or through ``grbm.sample``); returns the current states."""
+        s = self.sampler
+        ss = s._run(self.num_chains, num_sweeps, None, None, beta_schedule, self.seed, None, None, packed_io=self.packed,
+                    want_int8=want_samples, sweep_offset=self.sweeps_done, plan=self.plan, resume=self._started)
+        self._started = True
+        self.sweeps_done += int(ss.info["num_sweeps"])
+        return ss

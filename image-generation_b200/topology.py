@@ -28,6 +28,7 @@ __all__ = [
     "greedy_colouring",
     "IsingGraph",
     "greedy_get_subgraph",
+    "greedy_get_subgraph_nx",
     "get_graph_mapping",
 ]
 
@@ -320,6 +321,16 @@ def greedy_get_subgraph(n_nodes: int, random_seed: Optional[int], nodes: Sequenc
         chosen.append(best)
         chosen_set.add(best)
     return chosen
+
+
+def greedy_get_subgraph_nx(n_nodes: int, random_seed: Optional[int], graph):
+    """networkx front end with the reference's signature minus the QPU lookup
+    (src/utils/common.py:22-84): returns ``graph.subgraph(selected)``, so iterating its nodes --
+    and therefore :func:`get_graph_mapping` -- follows networkx's own view order exactly as in
+    the reference."""
+    adjacency = {v: list(graph.neighbors(v)) for v in graph.nodes()}
+    chosen = greedy_get_subgraph(n_nodes, random_seed, list(graph.nodes()), adjacency)
+    return graph.subgraph(chosen)
 
 
 def get_graph_mapping(sub_nodes: Iterable[int]) -> dict:

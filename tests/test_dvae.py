@@ -79,3 +79,26 @@ def test_reference_shaped_training_steps(cuda_device, golden, mmd_path, packed):
     assert imgs.shape == (256, 1, 32, 32) and float(imgs.min()) >= 0 and float(imgs.max()) <= 1
     sd = model.state_dicts()
     assert set(sd) == {"dvae.pth", "grbm.pth"} and "_encoder.conv.0.weight" in sd["dvae.pth"]
+
+
+def test_save_load_round_trip(tmp_path):
+    model = HybridDVAE(range(16), [(a, a + 1) for a in range(15)], device="cpu", parameters={"N_REPLICAS": 2})
+    model.setup()
+    model.save(str(tmp_path / "ckpt"))
+    other = HybridDVAE(range(16), [(0, 5)], device="cpu")       # different edge list: the checkpoint's wins
+    other.load(str(tmp_path / "ckpt"))
+    for k, v in model.state_dicts()["grbm.pth"].items():
+        assert torch.equal(v, other.state_dicts()["grbm.pth"][k]), k
+    for k, v in model.state_dicts()["dvae.pth"].items():
+        assert torch.equal(v, other.state_dicts()["dvae.pth"][k]), k
+    assert other.sampler.graph.n_edges == 15
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/models"), reason="reference tree not present")
+def test_shipped_reference_checkpoints_load():
+    import os
+    for name in sorted(os.listdir("/root/reference/models")):
+        model = HybridDVAE(range(256), [], device="cpu")
+        model.load(os.path.join("/root/reference/models", name))
+        assert model._grbm.n_edges in (2059, 1636, 1635)
+        assert model.sampler.graph.n == 256

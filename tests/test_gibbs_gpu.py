@@ -218,3 +218,30 @@ def test_fast_acceptance_matches_oracle_statistics_on_pegasus(cuda_device):
     m_fast = fast.record.sample.astype(np.float64).mean()
     m_ref = ref.astype(np.float64).mean()
     assert abs(m_fast - m_ref) < 4 * np.sqrt(1.0 / (chains * g.n) + 1.0 / (1024 * g.n)) * 3  # spins are correlated
+
+
+def test_persistent_chains_continue_bit_exactly(cuda_device):
+    """chains kept on the device between calls.  advance(a); advance(b) equals one
+    oracle run of a + b sweeps (the Philox sweep counter keeps running), and weights may change in between."""
+    g = B.IsingGraph.pegasus(3)
+    h, J = _problem(g, 21)
+    csr = _oracle_csr(g)
+    chains, seed = 90, 4242
+    s = B.BlockGibbsSampler(g, device=cuda_device)
+    s.device_graph.set_weights(torch.from_numpy(h), torch.from_numpy(J))
+    pc = B.PersistentChains(s, chains, seed=seed)
+    pc.advance(3)
+    got = pc.advance(4).record.sample
+    want = O.gibbs(csr, h, J, O.init_state(csr, chains, seed), [1.0] * 7, seed=seed)
+    assert np.array_equal(got, want) and pc.sweeps_done == 7
+    # new weights (a training step happened): continue from the stored state
+    h2, J2 = _problem(g, 22)
+    s.device_graph.set_weights(torch.from_numpy(h2), torch.from_numpy(J2))
+    got2 = pc.advance(2, beta_schedule=[0.5, 0.9]).record.sample
+    want2 = O.gibbs(csr, h2, J2, want, [0.5, 0.9], seed=seed, sweep_offset=7)
+    assert np.array_equal(got2, want2)
+    # packed state round trip: statistics straight from the packed words
+    from image_generation_b200.stats import edge_statistics
+    s1, s2 = edge_statistics(pc.packed, chains, s.device_graph, pc.plan[0])
+    o1, o2 = O.edge_stats(g.n, g.edge_i, g.edge_j, want2)
+    assert np.array_equal(s1.cpu().numpy(), o1) and np.array_equal(s2.cpu().numpy()[: g.n_edges], o2)
