@@ -14,12 +14,14 @@ __all__ = ["pack_rows_i8", "mmd_block_sums_i8", "mmd_backward_i8", "gemm_bf16_tn
 
 
 def pack_rows_i8(z: torch.Tensor) -> tuple[torch.Tensor, int]:
-    """Rows -> contiguous int8 ``(m, d_pad)`` with ``d_pad`` a multiple of 16 and zero padding
+    """Rows -> contiguous int8 ``(m, d_pad)`` with ``d_pad`` a multiple of 128 and zero padding
     (the layout the TMA descriptor reads).  Real-valued rows are packed by sign."""
     if not z.is_cuda:
         raise RuntimeError("the tcgen05 MMD path runs on CUDA only (no CPU fallback)")
     m, d = z.shape
-    d_pad = (d + 15) // 16 * 16
+    # row pitch = a whole number of 128-byte lines: every 128 B TMA box row is then one aligned L2 line
+    # (a 16-byte-granular pitch makes each box row straddle two lines)
+    d_pad = (d + 127) // 128 * 128
     if z.dtype == torch.int8:
         if d_pad == d and z.is_contiguous() and z.data_ptr() % 16 == 0:
             return z, d_pad

@@ -245,3 +245,21 @@ def test_persistent_chains_continue_bit_exactly(cuda_device):
     s1, s2 = edge_statistics(pc.packed, chains, s.device_graph, pc.plan[0])
     o1, o2 = O.edge_stats(g.n, g.edge_i, g.edge_j, want2)
     assert np.array_equal(s1.cpu().numpy(), o1) and np.array_equal(s2.cpu().numpy()[: g.n_edges], o2)
+
+
+def test_edgeless_graph_gives_independent_spins(cuda_device):
+    """Degenerate structure: no couplers at all (a GRBM built with an empty edge list)."""
+    n = 40
+    g = B.IsingGraph.build(n, [], [])
+    assert g.n_edges == 0 and g.n_colours == 1
+    h = np.linspace(-1.5, 1.5, n).astype(np.float32)
+    J = np.zeros(0, dtype=np.float32)
+    csr = _oracle_csr(g)
+    s = B.BlockGibbsSampler(g, device=cuda_device)
+    ss = s.sample_ising(h, J, num_reads=50, num_sweeps=3, seed=8)
+    want = O.gibbs(csr, h, J, O.init_state(csr, 50, 8), [1.0] * 3, seed=8)
+    assert np.array_equal(ss.record.sample, want)
+    np.testing.assert_allclose(ss.record.energy, want.astype(np.float64) @ h.astype(np.float64), rtol=1e-12, atol=1e-9)
+    big = s.sample_ising(h, J, num_reads=40000, num_sweeps=2, seed=9).samples_tensor.float().mean(0).cpu().numpy()
+    p_plus = 1.0 / (1.0 + np.exp(2.0 * h.astype(np.float64)))
+    assert np.abs(big - (2 * p_plus - 1)).max() < 4.5 / np.sqrt(40000)
