@@ -32,8 +32,6 @@
 //     parameter block (uniform-register operands).
 #include "common.cuh"
 
-#include <stdlib.h>
-
 namespace b200grbm {
 
 enum { MODE_PHILOX_EXACT = 0, MODE_PHILOX_FAST = 1, MODE_SUPPLIED_EXACT = 2 };
@@ -55,7 +53,6 @@ struct SweepParams {
     uint32_t info_bytes;    // shared-memory bytes reserved for the round table (multiple of 128)
     uint32_t state_bytes;   // shared-memory bytes reserved for W (multiple of 128)
     uint32_t tile_bytes;    // (width + 1) * threads * 8
-    int debug_skip_copies;  // timing experiment only (B200GRBM_DEBUG_SKIP_COPIES=1): wrong results, no table traffic
     uint32_t rk[2 * B200GRBM_PHILOX_ROUNDS];
 };
 
@@ -241,7 +238,7 @@ __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ S
         const uint32_t s = (uint32_t)q & 1u;
         // stage s^1 was last read in round q-1, which every thread left through the
         // __syncthreads() below -> safe to refill it now while round q computes
-        if (tid == 0 && q + 1 < total_tiles && !(p.debug_skip_copies && q >= 1)) {
+        if (tid == 0 && q + 1 < total_tiles) {
             const int next_tile = tile + 1 == p.n_tiles ? 0 : tile + 1;
             const uint32_t nb = bar_addr + 8u * (s ^ 1u);
             mbar_expect_tx(nb, p.tile_bytes);
@@ -249,7 +246,7 @@ __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ S
                      reinterpret_cast<const unsigned char *>(p.tiles) + (size_t)next_tile * p.tile_bytes, p.tile_bytes, nb);
         }
         const int2 info = tinfo[tile];
-        if (!(p.debug_skip_copies && q >= 2)) mbar_wait(bar_addr + 8u * s, (uint32_t)(q >> 1) & 1u);
+        mbar_wait(bar_addr + 8u * s, (uint32_t)(q >> 1) & 1u);
 
         if (tid < info.y) {
             const int pp = info.x + tid;
@@ -431,8 +428,6 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
     p.info_bytes = (uint32_t)(((size_t)a->n_tiles * 8 + 127) / 128 * 128);
     p.state_bytes = (uint32_t)(((size_t)a->n * 4 + 127) / 128 * 128);
     p.tile_bytes = (uint32_t)((size_t)(a->ell_width + 1) * a->threads * 8);
-    const char *dbg = getenv("B200GRBM_DEBUG_SKIP_COPIES");
-    p.debug_skip_copies = (dbg != nullptr && dbg[0] == '1') ? 1 : 0;
     uint32_t k0 = (uint32_t)a->seed, k1 = (uint32_t)(a->seed >> 32);
     for (int r = 0; r < B200GRBM_PHILOX_ROUNDS; ++r) {
         p.rk[2 * r] = k0;
