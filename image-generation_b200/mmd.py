@@ -75,6 +75,7 @@ def mmd_block_sums(z: torch.Tensor, m_x: int, kernel: GaussianKernel, path: str 
     """``[S_xx, S_yy, S_xy, sum_ab t_ab]`` (float64, device) for the stacked rows ``z = [x; y]``.
 
     ``path``: ``"f32"`` CUDA-core fp32 kernels, ``"i8"`` tcgen05 int8 Gram (rows must be +-1),
+    ``"bf16"`` / ``"bf16x3"`` tcgen05 bf16 Gram for real-valued rows (single rounding / split hi+lo),
     ``"auto"`` picks ``"i8"`` for int8 input and ``"f32"`` otherwise.
     """
     if not z.is_cuda:
@@ -91,6 +92,9 @@ def mmd_block_sums(z: torch.Tensor, m_x: int, kernel: GaussianKernel, path: str 
         if path == "i8":
             from .mmd_tc import mmd_block_sums_i8
             return mmd_block_sums_i8(z, m_x, kernel, sums)
+        if path in ("bf16", "bf16x3"):
+            from .mmd_tc import mmd_block_sums_bf16
+            return mmd_block_sums_bf16(z, m_x, kernel, split=(path == "bf16x3"), sums=sums)
         z32 = z.detach().to(torch.float32).contiguous()
         _lib.check(lib.b200grbm_mmd_forward_f32(_lib.ptr(z32), m_x, m_y, d, kernel.n_kernels, kernel.mul_factor,
                                                 int(kernel.squared), bw, _lib.ptr(sums), st))
@@ -108,7 +112,7 @@ class _MMDFunction(torch.autograd.Function):
             zi, _ = pack_rows_i8(z)                       # sign-packed, zero-padded int8 rows (kept for backward)
             sums = mmd_block_sums_i8(zi, m_x, kernel, d=z.shape[1])
         else:
-            sums = mmd_block_sums(z, m_x, kernel, "f32")
+            sums = mmd_block_sums(z, m_x, kernel, path)
         scale = 1.0 / kernel.n_kernels if kernel.reduce == "mean" else 1.0
         diag = float(kernel.n_kernels)            # k(a, a) = n_kernels * exp(0)
         if estimator == "unbiased":
@@ -157,14 +161,15 @@ def maximum_mean_discrepancy_loss(x: torch.Tensor, y: torch.Tensor, kernel: Gaus
     ``path="i8"`` sign-packs both inputs and runs the Gram contraction on the tcgen05 int8
     tensor-core kernel (exact for +-1 rows; encoder spins carry only straight-through residue
     ~1e-7, src/utils/common.py:162-173); ``"f32"`` is the precise CUDA-core path for arbitrary
-    real inputs.  The backward pass of the ``"i8"`` path also runs on tensor cores (coefficient
+    real inputs; ``"bf16"`` / ``"bf16x3"`` run the Gram of real-valued rows on the tcgen05 bf16
+    kernel (forward; their backward uses the fp32 kernels).  The backward pass of the ``"i8"`` path also runs on tensor cores (coefficient
     matrix from the int8 Gram as a bf16 hi/lo pair, then one bf16 GEMM); the gradient is
     evaluated at the sign-packed points.
     """
     if estimator not in ("unbiased", "biased"):
         raise ValueError("estimator must be 'unbiased' or 'biased'")
-    if path not in ("f32", "i8"):
-        raise ValueError("path must be 'f32' or 'i8'")
+    if path not in ("f32", "i8", "bf16", "bf16x3"):
+        raise ValueError("path must be 'f32', 'i8', 'bf16' or 'bf16x3'")
     if x.dim() != 2 or y.dim() != 2 or x.shape[1] != y.shape[1]:
         raise ValueError(f"x and y must be (rows, features) with equal features, got {tuple(x.shape)} and {tuple(y.shape)}")
     if not isinstance(kernel, GaussianKernel):

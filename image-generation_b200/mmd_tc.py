@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["pack_rows_i8", "mmd_block_sums_i8", "mmd_backward_i8", "gemm_bf16_tn"]
+__all__ = ["pack_rows_i8", "mmd_block_sums_i8", "mmd_block_sums_bf16", "mmd_backward_i8", "gemm_bf16_tn"]
 
 
 def pack_rows_i8(z: torch.Tensor) -> tuple[torch.Tensor, int]:
@@ -99,3 +99,33 @@ def mmd_backward_i8(zi: torch.Tensor, d: int, m_x: int, kernel, sums: torch.Tens
     c = gemm_bf16_tn(a_hi, a_lo, b, m_x)                       # (m_x, d + 1)
     x = zi[:m_x, :d].to(torch.float32)
     return grad_out.to(torch.float32) * (c[:, d:d + 1] * x - c[:, :d])
+
+
+def mmd_block_sums_bf16(z: torch.Tensor, m_x: int, kernel, split: bool = True, sums: torch.Tensor = None) -> torch.Tensor:
+    """``[S_xx, S_yy, S_xy, sum_ab t_ab]`` for real-valued rows on the tcgen05 bf16 kernel.
+    ``split=True`` feeds the rows as a bf16 (hi, lo) pair and contracts hi.hi + hi.lo + lo.hi
+    (fp32-class accuracy, three times the tensor work); ``split=False`` rounds the rows to bf16 once
+    (the distances are then exactly those of the rounded points)."""
+    if not z.is_cuda:
+        raise RuntimeError("the tcgen05 MMD path runs on CUDA only (no CPU fallback)")
+    m, d = z.shape
+    k_pad = (d + 63) // 64 * 64
+    z32 = z.detach().to(torch.float32)
+    hi = torch.zeros((m, k_pad), dtype=torch.bfloat16, device=z.device)
+    hi[:, :d] = z32.to(torch.bfloat16)
+    lo = None
+    rounded = hi[:, :d].to(torch.float32)
+    if split:
+        lo = torch.zeros((m, k_pad), dtype=torch.bfloat16, device=z.device)
+        lo[:, :d] = (z32 - rounded).to(torch.bfloat16)
+        rounded = rounded + lo[:, :d].to(torch.float32)
+    norms = (rounded * rounded).sum(1).contiguous()
+    if sums is None:
+        sums = torch.empty(4, dtype=torch.float64, device=z.device)
+    lib = _lib.load()
+    bw = -1.0 if kernel.bandwidth is None else kernel.bandwidth
+    with torch.cuda.device(z.device):
+        _lib.check(lib.b200grbm_mmd_forward_bf16(_lib.ptr(hi), _lib.ptr(lo), _lib.ptr(norms), m_x, m - m_x, k_pad,
+                                                 kernel.n_kernels, kernel.mul_factor, int(kernel.squared), bw,
+                                                 _lib.ptr(sums), _lib.current_stream(z.device)))
+    return sums

@@ -205,6 +205,17 @@ int32_t b200grbm_mmd_coef_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int3
 int32_t b200grbm_gemm_bf16_tn(const void *a_hi_dev, const void *a_lo_dev, int32_t M, int32_t K, int32_t a_rows_alloc,
                               const void *b_dev, int32_t N, float *c_dev, int32_t ldc, void *stream);
 
+/*
+ * Continuous (real-valued) rows on tensor cores: bf16 Gram with fp32 accumulation (north star:
+ * "bf16/fp32-accumulate for continuous encoder latents").  z_hi_dev: bf16 [m][k_pad] (k_pad a
+ * multiple of 64, zero padded); z_lo_dev: optional bf16 residual z - hi for the split-bf16 form
+ * (hi.hi + hi.lo + lo.hi, ~2^-16 relative error per product) or NULL; norms_dev: fp32 squared norms
+ * of the rounded rows.  Same sums_dev contract as b200grbm_mmd_forward_f32.
+ */
+int32_t b200grbm_mmd_forward_bf16(const void *z_hi_dev, const void *z_lo_dev, const float *norms_dev, int32_t m_x,
+                                  int32_t m_y, int32_t k_pad, int32_t n_kernels, float mul_factor, int32_t squared,
+                                  float bandwidth, double *sums_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

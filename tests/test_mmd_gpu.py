@@ -187,3 +187,37 @@ def test_bf16_gemm_kernel_matches_torch(cuda_device):
         torch.testing.assert_close(got.double(), want, rtol=1e-5, atol=1e-4)
         got1 = gemm_bf16_tn(a_hi.to(cuda_device), None, bb.to(cuda_device), M).cpu()
         torch.testing.assert_close(got1.double(), a_hi.double()[:M] @ bb.double().t(), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("m_x,m_y,d", [(256, 256, 128), (300, 215, 333), (1024, 256, 256)])
+@pytest.mark.parametrize("bandwidth", [None, 12.0])
+def test_bf16_tensor_core_path_for_continuous_rows(cuda_device, m_x, m_y, d, bandwidth):
+    """Real-valued latents on the tcgen05 bf16 Gram.  Split-bf16 (hi.hi + hi.lo + lo.hi) meets the 1e-5 bar
+    against the float64 oracle on the original rows; the single-rounding form is exact for the rounded rows."""
+    rng = np.random.default_rng(m_x + 3 * d)
+    z = rng.normal(size=(m_x + m_y, d)).astype(np.float32)
+    z[m_x:] += 0.3
+    kern = B.GaussianKernel(7, bandwidth=bandwidth).to(cuda_device)
+    zt = torch.from_numpy(z).to(cuda_device)
+
+    def want(rows):
+        k, bw, dist = O.gaussian_kernel_matrix(rows.astype(np.float64), bandwidth=bandwidth)
+        return np.array([k[:m_x, :m_x].sum(), k[m_x:, m_x:].sum(), k[:m_x, m_x:].sum(), dist.sum()])
+
+    got3 = mmd_block_sums(zt, m_x, kern, path="bf16x3").cpu().numpy()
+    w = want(z)
+    np.testing.assert_allclose(got3[:3], w[:3], rtol=1e-5)
+    if bandwidth is None:
+        assert got3[3] == pytest.approx(w[3], rel=1e-5)
+    got1 = mmd_block_sums(zt, m_x, kern, path="bf16").cpu().numpy()
+    z_rounded = torch.from_numpy(z).to(torch.bfloat16).to(torch.float32).numpy()
+    np.testing.assert_allclose(got1[:3], want(z_rounded)[:3], rtol=2e-5)
+    np.testing.assert_allclose(got1[:3], w[:3], rtol=2e-3)          # and close to the unrounded answer
+    # the loss call accepts the path; gradient comes from the fp32 kernels
+    xg = zt[:m_x].clone().requires_grad_(True)
+    val = B.maximum_mean_discrepancy_loss(xg, zt[m_x:], kern, path="bf16x3")
+    val.backward()
+    ref = O.mmd(z[:m_x], z[m_x:], bandwidth=bandwidth)
+    k, _, _ = O.gaussian_kernel_matrix(z.astype(np.float64), bandwidth=bandwidth)
+    scale = abs(k[:m_x, :m_x].mean()) + abs(k[m_x:, m_x:].mean()) + 2 * abs(k[:m_x, m_x:].mean())
+    assert abs(float(val) - ref) <= 1e-5 * scale and torch.isfinite(xg.grad).all()
