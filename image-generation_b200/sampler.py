@@ -99,12 +99,20 @@ def plan_launch(chains: int, colour_sizes: Sequence[int], sm_count: int = 148, n
 
 
 def beta_schedule(num_sweeps: int, beta_range: Optional[Sequence[float]] = None,
-                  beta_schedule_type: str = "geometric") -> np.ndarray:
+                  beta_schedule_type: str = "geometric", num_sweeps_per_beta: int = 1) -> np.ndarray:
     """One inverse temperature per sweep.  ``beta_range=None`` is plain Gibbs at beta = 1
     (the Boltzmann law of static/eq5.png at the GRBM's own temperature); otherwise a
-    geometric / linear ramp like the reference-style annealer."""
+    geometric / linear ramp like the reference-style annealer, with
+    ``num_sweeps_per_beta`` sweeps at each of ``num_sweeps // num_sweeps_per_beta`` temperatures."""
     if num_sweeps < 0:
         raise ValueError("num_sweeps must be non-negative")
+    if num_sweeps_per_beta < 1:
+        raise ValueError("num_sweeps_per_beta must be at least 1")
+    if num_sweeps_per_beta > 1:
+        if num_sweeps % num_sweeps_per_beta:
+            raise ValueError("num_sweeps must be a multiple of num_sweeps_per_beta")
+        return np.repeat(beta_schedule(num_sweeps // num_sweeps_per_beta, beta_range, beta_schedule_type),
+                         num_sweeps_per_beta)
     if beta_range is None:
         return np.ones(num_sweeps, dtype=np.float64)
     b0, b1 = float(beta_range[0]), float(beta_range[1])
@@ -281,7 +289,7 @@ class BlockGibbsSampler:
     def __init__(self, graph: Union[IsingGraph, tuple], device: Union[str, torch.device, None] = None,
                  num_sweeps: int = 1000, beta_range: Optional[Sequence[float]] = None,
                  beta_schedule_type: str = "geometric", seed: int = 0, accept: str = "exact",
-                 variables: Optional[Sequence] = None, chain_offset: int = 0):
+                 variables: Optional[Sequence] = None, chain_offset: int = 0, num_sweeps_per_beta: int = 1):
         if not isinstance(graph, IsingGraph):
             nodes, edges = graph
             nodes = list(nodes)
@@ -299,6 +307,7 @@ class BlockGibbsSampler:
         self.num_sweeps = num_sweeps
         self.beta_range = beta_range
         self.beta_schedule_type = beta_schedule_type
+        self.num_sweeps_per_beta = int(num_sweeps_per_beta)
         self.seed = int(seed)
         self.accept = accept
         self.chain_offset = int(chain_offset)
@@ -331,12 +340,15 @@ class BlockGibbsSampler:
     def _coef(self, num_sweeps, beta_range, beta_schedule_type, beta_sched) -> torch.Tensor:
         if beta_sched is not None:
             betas = np.asarray(beta_sched, dtype=np.float64).reshape(-1)
+            if betas.size and betas.min() < 0:
+                raise ValueError("beta_schedule must be non-negative")
             key = None
         else:
-            key = (num_sweeps, None if beta_range is None else tuple(map(float, beta_range)), beta_schedule_type)
+            key = (num_sweeps, None if beta_range is None else tuple(map(float, beta_range)), beta_schedule_type,
+                   self.num_sweeps_per_beta)
             if key in self._coef_cache:
                 return self._coef_cache[key]
-            betas = beta_schedule(num_sweeps, beta_range, beta_schedule_type)
+            betas = beta_schedule(num_sweeps, beta_range, beta_schedule_type, self.num_sweeps_per_beta)
         coef = torch.from_numpy((2.0 * betas * _LOG2E).astype(np.float32)).to(self.device)
         if key is not None:
             self._coef_cache[key] = coef

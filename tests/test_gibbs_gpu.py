@@ -263,3 +263,28 @@ def test_edgeless_graph_gives_independent_spins(cuda_device):
     big = s.sample_ising(h, J, num_reads=40000, num_sweeps=2, seed=9).samples_tensor.float().mean(0).cpu().numpy()
     p_plus = 1.0 / (1.0 + np.exp(2.0 * h.astype(np.float64)))
     assert np.abs(big - (2 * p_plus - 1)).max() < 4.5 / np.sqrt(40000)
+
+
+@pytest.mark.parametrize("accept", ["exact", "fast"])
+def test_energy_histogram_matches_oracle_chains(cuda_device, accept):
+    """north_star check (b), energy histograms: GPU chains (native Philox, either acceptance rule) against an
+    independent set of CPU-oracle chains -- two-sample Kolmogorov-Smirnov on the energies plus a binned
+    comparison within 3 standard errors per bin."""
+    from scipy import stats
+    g = B.IsingGraph.pegasus(2)
+    h, J = _problem(g, 33, 0.2, 0.35)
+    sweeps, n_gpu, n_cpu = 60, 20000, 6000
+    e_gpu = B.BlockGibbsSampler(g, device=cuda_device, accept=accept, seed=77).sample_ising(
+        h, J, num_reads=n_gpu, num_sweeps=sweeps).record.energy
+    csr = _oracle_csr(g)
+    ref = O.gibbs(csr, h, J, O.init_state(csr, n_cpu, 901), [1.0] * sweeps, seed=901)
+    e_cpu = O.energies(g.n, g.edge_i, g.edge_j, h, J, ref)
+    ks = stats.ks_2samp(e_gpu, e_cpu)
+    assert ks.pvalue > 1e-3, ks
+    edges = np.quantile(np.concatenate([e_gpu, e_cpu]), np.linspace(0, 1, 13))
+    edges[0], edges[-1] = -np.inf, np.inf
+    p_gpu = np.histogram(e_gpu, edges)[0] / n_gpu
+    p_cpu = np.histogram(e_cpu, edges)[0] / n_cpu
+    se = np.sqrt(p_gpu * (1 - p_gpu) / n_gpu + p_cpu * (1 - p_cpu) / n_cpu)
+    z = np.abs(p_gpu - p_cpu) / se
+    assert z.max() < 4.0 and np.mean(z < 3.0) >= 0.9, z

@@ -82,6 +82,10 @@ def test_beta_schedule():
         B.beta_schedule(4, (0.0, 1.0), "geometric")
     with pytest.raises(ValueError):
         B.beta_schedule(4, (0.1, 1.0), "cubic")
+    r = B.beta_schedule(6, (0.5, 2.0), "linear", num_sweeps_per_beta=2)
+    assert r.tolist() == [0.5, 0.5, 1.25, 1.25, 2.0, 2.0]
+    with pytest.raises(ValueError):
+        B.beta_schedule(5, (0.5, 2.0), "linear", num_sweeps_per_beta=2)
 
 
 def test_greedy_get_subgraph_is_deterministic_and_connected():
