@@ -56,6 +56,13 @@ struct TcParams {
 };
 
 // upper-triangle tile enumeration: column tile j ascending, row tiles i = 0 .. min(tiles_m, 2j+2) - 1
+// LUT index = Hamming distance (D - a.b) / 2; clamped so that rows that are not +-1 (caller error)
+// can never read outside the table
+__device__ __forceinline__ int lut_index(int two_d, int gram, int d)
+{
+    return min(max((two_d - 2 * gram) >> 2, 0), d);
+}
+
 __device__ __forceinline__ void tile_coords(const TcParams &p, int t, int &i, int &j)
 {
     if (p.pass == TC_PASS_COEF) {          // full rectangle: x rows against every column
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
 #pragma unroll
                             for (int q = 0; q < 2; ++q) {
                                 const int col = col0 + cbase + c + q;
-                                const float raw = lut[(two_d - 2 * (int)v[c + q]) >> 2];
+                                const float raw = lut[lut_index(two_d, (int)v[c + q], p.d)];
                                 cf[q] = (col < p.m && col != row) ? raw * (col < p.m_x ? p.w_xx : p.w_xy) : 0.f;
                             }
                             const __nv_bfloat162 h2 = __floats2bfloat162_rn(cf[0], cf[1]);
@@ -216,14 +223,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
                 } else if (pure) {
                     float part = 0.f;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) part += lut[(two_d - 2 * (int)v[c]) >> 2];
+                    for (int c = 0; c < 32; ++c) part += lut[lut_index(two_d, (int)v[c], p.d)];
                     a_xx += part;            // sorted into its block after the loop
                 } else {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const int col = col0 + cbase + c;
                         if (row < p.m && col < p.m && col >= row) {
-                            const float kv = lut[(two_d - 2 * (int)v[c]) >> 2];
+                            const float kv = lut[lut_index(two_d, (int)v[c], p.d)];
                             const bool rx = row < p.m_x, cx = col < p.m_x;
                             const float w = col == row ? 1.f : 2.f;
                             if (p.pass == TC_PASS_DIST) a_xx += w * kv;

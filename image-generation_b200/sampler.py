@@ -190,8 +190,10 @@ class _TileSet:
         row_base = tile_of * (W + 1) * T + lane_of                      # entry index of the f0 row
         tiles = np.zeros((self.n_tiles, W + 1, T, 2), dtype=np.int32)
         p = np.arange(g.n)
-        for k in range(g.ell_width):
-            tiles[tile_of, 1 + k, lane_of, 1] = np.where(k < g.degree, g.ell_nbr[k, p], 0)
+        # padding slots (k >= degree, and the slot_pad filler) carry 2J = 0 and point at the lane's OWN
+        # position: the word read there is never written by another thread in the same round
+        for k in range(W):
+            tiles[tile_of, 1 + k, lane_of, 1] = np.where(k < g.degree, g.ell_nbr[min(k, g.ell_width - 1), p], p)
         ka, pa = np.divmod(g.slot_a.astype(np.int64), g.n_pad)
         kb, pb = np.divmod(g.slot_b.astype(np.int64), g.n_pad)
         i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
