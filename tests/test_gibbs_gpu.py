@@ -288,3 +288,21 @@ def test_energy_histogram_matches_oracle_chains(cuda_device, accept):
     se = np.sqrt(p_gpu * (1 - p_gpu) / n_gpu + p_cpu * (1 - p_cpu) / n_cpu)
     z = np.abs(p_gpu - p_cpu) / se
     assert z.max() < 4.0 and np.mean(z < 3.0) >= 0.9, z
+
+
+def test_cold_schedule_exercises_the_clamp_bit_exactly(cuda_device):
+    """Large beta * |f| (deep anneal / quench): the exp2 argument saturates at +-120 on both sides the same way."""
+    g = B.IsingGraph.pegasus(2)
+    h, J = _problem(g, 41, 2.0, 1.0)                       # |f| up to ~17
+    csr = _oracle_csr(g)
+    beta = [0.01, 1.0, 20.0, 200.0, 5000.0]
+    s = B.BlockGibbsSampler(g, device=cuda_device)
+    got = s.sample_ising(h, J, num_reads=64, beta_schedule=beta, seed=3).record.sample
+    want = O.gibbs(csr, h, J, O.init_state(csr, 64, 3), beta, seed=3)
+    assert np.array_equal(got, want)
+    # at beta = 5000 the last sweep is a zero-temperature descent: no spin opposes its local field
+    fields = np.zeros_like(got, dtype=np.float64) + h
+    np.add.at(fields, (slice(None), g.edge_i), got[:, g.edge_j] * J)
+    np.add.at(fields, (slice(None), g.edge_j), got[:, g.edge_i] * J)
+    last_colour = g.colour == g.colour.max()               # spins updated last saw the final configuration
+    assert np.all((got * fields)[:, last_colour] <= 1e-6)
