@@ -293,7 +293,12 @@ def run_b200(args):
         "hbm": {"achieved": hbm_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": hbm_bytes / kernel_s / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
-        "note": "state is bit-packed (32 chains per word) so the kernel is issue-bound, not byte-bound; see DESIGN.md",
+        # the binding resource: warp-instruction issue.  56.6 warp instructions per 32 spin-updates is the count ncu
+        # reports for this kernel (smsp__inst_executed.sum / updates, profiles/r1_gibbs_v4_ncu_summary.txt)
+        "issue": {"warp_instr_per_32_updates": 56.6, "peak_updates_per_s": sms * 4 * 32 / 56.6 * f_sm,
+                  "frac": (upd_per_launch / kernel_s) / (sms * 4 * 32 / 56.6 * f_sm),
+                  "ncu_issue_active_frac": 0.77},
+        "note": "state is bit-packed (28 chains per word) so the kernel is issue-bound, not byte-bound; see DESIGN.md 5.1",
     }
     cpu_rate, cores, sample = cpu_port_rate(g, h, J, CFG["beta"], args.cpu_seconds)
     line = {
