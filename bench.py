@@ -404,8 +404,54 @@ def bench_dvae_step(dev, steps=20, warmup=5):
         model.step(batches[k % 4], epoch=0, record_losses=False)
     torch.cuda.synchronize(dev)
     ms = 1e3 * (time.perf_counter() - t0) / steps
-    return {"ms_per_step": ms, "steps": steps, "workload": "DVAE+GRBM step, B=128, R=8, n_latents=256, 256 reads x 1000 sweeps, "
-            "MMD on tcgen05 int8 path, NLL via packed statistics every 10th step (BASELINE.json configs[0], GPU path)"}
+    out = {"ms_per_step": ms, "steps": steps, "workload": "DVAE+GRBM step, B=128, R=8, n_latents=256, 256 reads x 1000 sweeps, "
+           "MMD on tcgen05 int8 path, NLL via packed statistics every 10th step (BASELINE.json configs[0], GPU path)"}
+    try:
+        out["cpu_baseline"] = cpu_dvae_step(z, name, edges)
+    except Exception as exc:  # the side metric must never take the bench line down
+        out["cpu_baseline"] = {"error": repr(exc)}
+    return out
+
+
+def cpu_dvae_step(z, name, edges):
+    """BASELINE.json configs[0] as the reference runs it without a QPU: the same step on the host -- stock PyTorch
+    encoder / decoder on CPU, the oracle port as the classical sampler (256 reads x 1000 sweeps, all host threads),
+    the stock torch form of the MMD (cat -> cdist -> 7 x exp -> block means) with autograd."""
+    import torch
+
+    from image_generation_b200.dvae import Decoder, DiscreteVariationalAutoencoder, Encoder, synthetic_batch
+    from oracle import oracle as O
+
+    O.set_num_threads(len(os.sched_getaffinity(0)))
+    torch.manual_seed(0)
+    dvae = DiscreteVariationalAutoencoder(Encoder(256), Decoder(256))
+    opt = torch.optim.Adam(dvae.parameters(), lr=1e-4, weight_decay=0.01)
+    ei, ej = z[name + "/edge_i"], z[name + "/edge_j"]
+    h = np.clip(np.float32(0.05) * z[name + "/linear"], -4, 4).astype(np.float32)
+    J = np.clip(np.float32(0.05) * z[name + "/quadratic"], -1, 1).astype(np.float32)
+    csr = O.PositionCSR(256, ei, ej, np.arange(256))
+    images = synthetic_batch(128, seed=0)
+    mult = 2.0 ** (torch.arange(7) - 3).float()
+    times = []
+    for it in range(2):
+        t0 = time.perf_counter()
+        _, spins, recon = dvae(images, 8)
+        opt.zero_grad()
+        mse = torch.nn.functional.mse_loss(recon, images.unsqueeze(1).expand(-1, 8, -1, -1, -1))
+        samples = torch.from_numpy(O.gibbs(csr, h, J, O.init_state(csr, 256, it), [1.0] * 1000, seed=it, f64=True)).float()
+        x = spins.reshape(-1, 256)
+        zz = torch.cat([x, samples], 0)
+        dmat = torch.cdist(zz, zz, p=2)
+        bw = dmat.detach().sum() / (zz.shape[0] ** 2 - zz.shape[0])
+        k = torch.exp(-dmat.unsqueeze(0) / (bw * mult).reshape(-1, 1, 1)).sum(0)
+        mx, my = x.shape[0], samples.shape[0]
+        kxx, kyy, kxy = k[:mx, :mx], k[mx:, mx:], k[:mx, mx:]
+        mmd = ((kxx.sum() - kxx.trace()) / (mx * (mx - 1)) + (kyy.sum() - kyy.trace()) / (my * (my - 1)) - 2 * kxy.mean())
+        (mse + mmd).backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    return {"ms_per_step": 1e3 * times[-1], "cores": O.num_threads(), "kind": "port",
+            "sample": "one full step (second of two), oracle_gibbs_f64 sampler, stock-torch CPU nets and MMD; NLL update not included"}
 
 
 def main():
