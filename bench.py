@@ -331,6 +331,11 @@ def bench_mmd(dev, peaks, m_each=8192, d=5640, iters=5):
     import image_generation_b200 as B
     from image_generation_b200.mmd import mmd_block_sums
 
+    from image_generation_b200 import _lib as L
+
+    # int8 tcgen05 peak of THIS device (MEASURED_PEAKS.json has none): back-to-back kind::i8 MMAs from resident
+    # zero operands -- an upper bound real data cannot reach under the power cap; 2 x the cuBLAS bf16 burst beside it
+    i8_probe = L.tensor_peak("i8", 10000, dev) / 1e12
     gen = torch.Generator().manual_seed(1)
     z = (torch.randint(0, 2, (2 * m_each, d), generator=gen, dtype=torch.int8) * 2 - 1).to(dev)
     z[m_each:, : d // 8] = 1
@@ -351,13 +356,14 @@ def bench_mmd(dev, peaks, m_each=8192, d=5640, iters=5):
         m = 2 * m_each
         tiles = (m // 256) * (m // 256 + 1)                     # upper triangle of 128 x 256 tiles
         executed = 2.0 * tiles * 128 * 256 * (-(-d // 128) * 128) * passes
-        i8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        i8_2x = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
         out[label] = {
             "ms": ms, "gram_passes": passes, "input_GBps": m * d / ms / 1e6,
             "tflops_as_reference_computes_it": 2.0 * m * m * d * passes / ms / 1e9,
-            "roofline": {"bound": "tensor", "achieved": executed / ms / 1e9, "peak": i8_peak, "unit": "TOP/s",
-                         "frac": executed / ms / 1e9 / i8_peak, "traffic": None,
-                         "peak_source": "2 x measured bf16 burst (MEASURED_PEAKS.json has no int8 figure)",
+            "roofline": {"bound": "tensor", "achieved": executed / ms / 1e9, "peak": i8_probe, "unit": "TOP/s",
+                         "frac": executed / ms / 1e9 / i8_probe, "traffic": None,
+                         "peak_source": "int8 tcgen05 probe on this device (b200grbm_tensor_peak, resident zero operands)",
+                         "frac_of_2x_bf16_burst": executed / ms / 1e9 / i8_2x, "peak_2x_bf16_burst": i8_2x,
                          "executed_ops": executed, "note": "symmetric: only the upper triangle of tiles is contracted"}}
     # value + gradient wrt x through the public call (what ModelWrapper.step does at src/model_wrapper.py:320-326)
     x = z[:m_each].float().requires_grad_(True)

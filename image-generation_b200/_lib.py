@@ -81,6 +81,7 @@ SIGNATURES = {
                               _vp], _i32),
     "b200grbm_gemm_bf16_tn": ([_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp], _i32),
     "b200grbm_mmd_forward_bf16": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _vp], _i32),
+    "b200grbm_tensor_peak": ([_i32, _i32, C.POINTER(C.c_double), _vp], _i32),
     "b200grbm_mmd_backward_f32": ([_vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _f32, _f32, _vp, _vp, _vp,
                                    _vp], _i32),
 }
@@ -131,3 +132,15 @@ def device_info() -> dict:
     vals = [C.c_int32() for _ in range(4)]
     check(lib.b200grbm_device_info(*[C.byref(v) for v in vals]))
     return dict(sm_count=vals[0].value, cc=(vals[1].value, vals[2].value), smem_optin=vals[3].value)
+
+
+def tensor_peak(kind: str = "i8", iters: int = 20000, device=None) -> float:
+    """Measured tcgen05 peak of the current device in op/s (2 x MAC): ``kind`` "i8" or "bf16"."""
+    import torch
+
+    lib = load()
+    out = C.c_double()
+    dev = torch.device("cuda" if device is None else device)
+    with torch.cuda.device(dev):
+        check(lib.b200grbm_tensor_peak(0 if kind == "i8" else 1, int(iters), C.byref(out), current_stream(dev)))
+    return out.value

@@ -216,6 +216,13 @@ int32_t b200grbm_mmd_forward_bf16(const void *z_hi_dev, const void *z_lo_dev, co
                                   int32_t m_y, int32_t k_pad, int32_t n_kernels, float mul_factor, int32_t squared,
                                   float bandwidth, double *sums_dev, void *stream);
 
+/*
+ * Tensor-core peak probe (measurement aid, not on the product path): back-to-back tcgen05.mma
+ * (kind 0 = int8, 1 = bf16; M128 x N256) from resident shared-memory operands on every SM.
+ * Writes 2 * MAC / s to the HOST pointer ops_per_s_out and synchronises the stream.
+ */
+int32_t b200grbm_tensor_peak(int32_t kind, int32_t iters, double *ops_per_s_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
