@@ -11,7 +11,7 @@ $NVCC $COMMON --fmad=false -c gibbs.cu -o build/gibbs.o &
 $NVCC $COMMON -c common.cu -o build/common.o &
 $NVCC $COMMON -c stats.cu -o build/stats.o &
 wait
-for f in mmd_simt.cu mmd_tc.cu gemm_tc.cu mmd_bf16.cu tc_peak.cu; do
+for f in mmd_simt.cu mmd_tc.cu mmd_tc2.cu gemm_tc.cu mmd_bf16.cu tc_peak.cu; do
   if [ -f "$f" ]; then $NVCC $COMMON -c "$f" -o "build/${f%.cu}.o"; fi
 done
 $NVCC -shared $ARCH -o libb200grbm.so build/*.o -lcudart

@@ -24,6 +24,7 @@
 #include "tc_common.cuh"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace b200grbm {
 
@@ -344,6 +345,23 @@ int32_t make_tensor_map_2d(CUtensorMap *map, const void *base, CUtensorMapDataTy
     return 0;
 }
 
+// CTA-pair version of the forward passes (mmd_tc2.cu)
+int32_t launch_gram_i8_2cta(const CUtensorMap &tmap, int m_x, int m, int d, int d_pad, int pass, const float *lut,
+                            double *sums, cudaStream_t st);
+
+// Forward tile shape.  Measured on B200 (8192 + 8192 rows): while the sample matrix fits in L2 the single-CTA
+// kernel and the CTA-pair kernel run at the same k-block rate (742 vs 750 clk per 128-byte k-block at
+// D = 5632); once it does not (D = 11264, 185 MB) the pair kernel's 33 % smaller operand traffic wins
+// (1.04 vs 1.16 ms).  B200GRBM_MMD_TILE=1|2 forces one of them (A/B measurements, parity tests of both).
+static bool use_pair_kernel(int m, int d_pad)
+{
+    const char *env = getenv("B200GRBM_MMD_TILE");
+    if (env != nullptr && env[0] == '1') return false;
+    if (env != nullptr && env[0] == '2') return true;
+    const int tiles = (m + 255) / 256;
+    return tiles * (tiles + 1) / 2 >= 74 && (size_t)m * (size_t)d_pad > (size_t)100 << 20;
+}
+
 }  // namespace b200grbm
 
 using namespace b200grbm;
@@ -410,20 +428,29 @@ extern "C" int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     B200_CUDA(cudaMemsetAsync(sums_dev, 0, 4 * sizeof(double), st));
     const int lut_blocks = (d + 1 + 255) / 256;
+    const bool pair = use_pair_kernel(m, d_pad);
     if (!(bandwidth > 0.f)) {
         mmd_lut_kernel<<<lut_blocks, 256, 0, st>>>(TC_PASS_DIST, d, m, n_kernels, mul_factor, squared, bandwidth, sums_dev,
                                                    lut_dev);
         B200_CUDA(cudaGetLastError());
-        p.pass = TC_PASS_DIST;
-        mmd_gram_i8_kernel<<<grid, TC_THREADS, smem + 1024, st>>>(tmap, p);
-        B200_CUDA(cudaGetLastError());
+        if (pair) {
+            B200_TRY(launch_gram_i8_2cta(tmap, m_x, m, d, d_pad, TC_PASS_DIST, lut_dev, sums_dev, st));
+        } else {
+            p.pass = TC_PASS_DIST;
+            mmd_gram_i8_kernel<<<grid, TC_THREADS, smem + 1024, st>>>(tmap, p);
+            B200_CUDA(cudaGetLastError());
+        }
     }
     mmd_lut_kernel<<<lut_blocks, 256, 0, st>>>(TC_PASS_KERNEL, d, m, n_kernels, mul_factor, squared, bandwidth, sums_dev,
                                                lut_dev);
     B200_CUDA(cudaGetLastError());
-    p.pass = TC_PASS_KERNEL;
-    mmd_gram_i8_kernel<<<grid, TC_THREADS, smem + 1024, st>>>(tmap, p);
-    B200_CUDA(cudaGetLastError());
+    if (pair) {
+        B200_TRY(launch_gram_i8_2cta(tmap, m_x, m, d, d_pad, TC_PASS_KERNEL, lut_dev, sums_dev, st));
+    } else {
+        p.pass = TC_PASS_KERNEL;
+        mmd_gram_i8_kernel<<<grid, TC_THREADS, smem + 1024, st>>>(tmap, p);
+        B200_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -126,6 +126,76 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
 }
 
+// ---------------------------------------------------------------- CTA-pair (cta_group::2) helpers
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// shared::cluster address of `local_smem_addr` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_smem_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+
+__device__ __forceinline__ void bar_arrive_cluster(uint32_t cluster_bar_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+
+// TMA load issued by either CTA of a pair; the transaction bytes are credited to `cluster_bar_addr`,
+// which may live in the peer CTA (cute::SM100_TMA_2SM_LOAD_2D)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t cluster_bar_addr)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            dst),
+        "l"(map), "r"(x), "r"(y), "r"(cluster_bar_addr)
+        : "memory");
+}
+
+// M = 256 across the pair: each CTA supplies 128 rows of A and half of B's N rows at the same
+// shared-memory offsets; issued by the leader (even) CTA only
+__device__ __forceinline__ void umma_i8_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// arrive (when the preceding MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t slot_smem_addr, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem_addr), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t base, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

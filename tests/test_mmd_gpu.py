@@ -221,3 +221,21 @@ def test_bf16_tensor_core_path_for_continuous_rows(cuda_device, m_x, m_y, d, ban
     k, _, _ = O.gaussian_kernel_matrix(z.astype(np.float64), bandwidth=bandwidth)
     scale = abs(k[:m_x, :m_x].mean()) + abs(k[m_x:, m_x:].mean()) + 2 * abs(k[:m_x, m_x:].mean())
     assert abs(float(val) - ref) <= 1e-5 * scale and torch.isfinite(xg.grad).all()
+
+
+def test_cta_pair_kernel_matches_single_cta_kernel(cuda_device, monkeypatch):
+    """The tcgen05 cta_group::2 (256 x 256 pair-tile) forward and the single-CTA forward give the same block sums
+    (B200GRBM_MMD_TILE forces either; the dispatcher picks the pair kernel once the sample matrix outgrows L2)."""
+    rng = np.random.default_rng(5)
+    m_x, m_y, d = 700, 900, 520
+    z = rng.choice([-1, 1], size=(m_x + m_y, d)).astype(np.int8)
+    z[m_x:, :90] = 1
+    zt = torch.from_numpy(z).to(cuda_device)
+    k, bw, dist = O.gaussian_kernel_matrix(z.astype(np.float64))
+    want = [k[:m_x, :m_x].sum(), k[m_x:, m_x:].sum(), k[:m_x, m_x:].sum(), dist.sum()]
+    got = {}
+    for tile in ("1", "2"):
+        monkeypatch.setenv("B200GRBM_MMD_TILE", tile)
+        got[tile] = mmd_block_sums(zt, m_x, B.GaussianKernel(7).to(cuda_device), path="i8").cpu().numpy()
+        np.testing.assert_allclose(got[tile], want, rtol=2e-6)
+    np.testing.assert_allclose(got["1"], got["2"], rtol=1e-9)

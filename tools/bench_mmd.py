@@ -12,12 +12,21 @@ ap.add_argument("--d", type=int, default=5640)
 ap.add_argument("--path", default="i8")
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--bandwidth", type=float, default=0.0)
+ap.add_argument("--zeros", action="store_true", help="all-zero operands: same work, minimal switching power (is the kernel power-limited?)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 g = torch.Generator(device="cpu").manual_seed(0)
 z = (torch.randint(0, 2, (2 * args.m, args.d), generator=g, dtype=torch.int8) * 2 - 1).to(dev)
+if args.zeros:
+    z.zero_()
 kern = B.GaussianKernel(7, bandwidth=args.bandwidth if args.bandwidth > 0 else None).to(dev)
-zz = z if args.path == "i8" else z.float()
+if args.path == "i8":
+    from image_generation_b200.mmd_tc import mmd_block_sums_i8, pack_rows_i8
+    zi, _ = pack_rows_i8(z)                       # resident kernel layout: row pitch padded to whole 128-byte lines
+    mmd_block_sums = lambda zz, m_x, kern, path: mmd_block_sums_i8(zz, m_x, kern, d=args.d)
+    zz = zi
+else:
+    zz = z.float()
 for _ in range(2):
     s = mmd_block_sums(zz, args.m, kern, path=args.path)
 torch.cuda.synchronize()
