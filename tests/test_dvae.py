@@ -102,3 +102,46 @@ def test_shipped_reference_checkpoints_load():
         model.load(os.path.join("/root/reference/models", name))
         assert model._grbm.n_edges in (2059, 1636, 1635)
         assert model.sampler.graph.n == 256
+
+
+@pytest.mark.gpu
+def test_integration_recipe_of_the_reference_setup(cuda_device):
+    """the reference's setup() path with the QPU replaced -- Zephyr working graph ->
+    greedy_get_subgraph(n_latents, seed) -> get_graph_mapping -> GRBM(graph.nodes, graph.edges) -> sampler with the
+    reference's sampler kwargs -> the three hot calls of ModelWrapper.step (src/model_wrapper.py:309-344)."""
+    nx = pytest.importorskip("networkx")
+    from image_generation_b200.topology import greedy_get_subgraph_nx
+    n, ei, ej, _ = B.zephyr_graph(4)
+    qpu_graph = nx.Graph()
+    qpu_graph.add_nodes_from(range(n))
+    qpu_graph.add_edges_from(zip(ei.tolist(), ej.tolist()))
+    n_latents, seed = 64, 775321899904
+    sub = greedy_get_subgraph_nx(n_latents, seed, qpu_graph)
+    mapping = B.get_graph_mapping(sub.nodes())
+    graph = nx.relabel_nodes(sub, mapping)
+    grbm = B.GraphRestrictedBoltzmannMachine(graph.nodes, graph.edges).to(cuda_device)
+    sampler = B.BlockGibbsSampler((list(graph.nodes), list(graph.edges)), device=cuda_device, num_sweeps=200, seed=seed)
+    sampler_kwargs = dict(num_reads=256, answer_mode="raw", auto_scale=False, annealing_time=1, label="Examples - ML MNIST Image Gen")
+    linear_range, quadratic_range = (-4.0, 4.0), (-1.0, 1.0)
+
+    spins = (torch.randint(0, 2, (128, 8, n_latents), device=cuda_device).float() * 2 - 1).requires_grad_(True)
+    with torch.no_grad():
+        samples = grbm.sample(sampler=sampler, prefactor=0.05, linear_range=linear_range, quadratic_range=quadratic_range,
+                              device=spins.device, sample_params=sampler_kwargs)
+    assert samples.shape == (256, n_latents) and samples.dtype == torch.float32 and samples.device.type == "cuda"
+    assert set(samples.unique().tolist()) <= {-1.0, 1.0}
+    flat = spins.reshape(-1, n_latents)
+    mmd = B.maximum_mean_discrepancy_loss(x=flat, y=samples, kernel=B.GaussianKernel(n_kernels=7).to(cuda_device))
+    mmd.backward()
+    assert torch.isfinite(mmd) and spins.grad is not None and torch.isfinite(spins.grad).all()
+    helper = B.PersistentQPUSampleHelper(max_deque_size=4096, iterations_before_resampling=100)
+    nll, sample_set = B.nll_loss(spins=flat.detach(), grbm=grbm, sampler=sampler, sampler_kwargs=sampler_kwargs,
+                                 linear_range=linear_range, quadratic_range=quadratic_range, prefactor=0.05,
+                                 persistent_qpu_sample_helper=helper, sample_set=None)
+    nll.backward()
+    assert grbm._linear.grad.shape == (n_latents,) and grbm._quadratic.grad.shape == (graph.number_of_edges(),)
+    assert sample_set.record.sample.shape == (256, n_latents) and sample_set.vartype == "SPIN"
+    # the gradient is <s>_data - <s>_model / <ss>_data - <ss>_model (src/losses.py:61)
+    model = torch.from_numpy(sample_set.record.sample).float().to(cuda_device)
+    want = flat.detach().mean(0) - model.mean(0)
+    torch.testing.assert_close(grbm._linear.grad, want, rtol=1e-5, atol=1e-6)
