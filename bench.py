@@ -329,8 +329,6 @@ def bench_mmd(dev, peaks, m_each=8192, d=5640, iters=5):
     import torch
 
     import image_generation_b200 as B
-    from image_generation_b200.mmd import mmd_block_sums
-
     from image_generation_b200 import _lib as L
 
     # int8 tcgen05 peak of THIS device (MEASURED_PEAKS.json has none): back-to-back kind::i8 MMAs from resident

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .sampler import BlockGibbsSampler, SampleSet
+from .sampler import BlockGibbsSampler
 from .topology import IsingGraph
 
 __all__ = ["GraphRestrictedBoltzmannMachine"]

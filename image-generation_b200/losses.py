@@ -7,7 +7,7 @@ reproduced -- SURVEY.md finding 10).
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence
+from typing import Sequence
 
 import torch
 

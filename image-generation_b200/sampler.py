@@ -17,7 +17,6 @@ src/utils/persistent_qpu_sampler.py:84-88).  All arithmetic runs in the sm_100a 
 from __future__ import annotations
 
 import ctypes as C
-import math
 from typing import Mapping, Optional, Sequence, Union
 
 import numpy as np
