@@ -284,6 +284,9 @@ class HybridDVAE:
         self._dvae.load_state_dict(torch.load(os.path.join(file_path, "dvae.pth"), map_location=self.device, weights_only=True))
         self._grbm.load_state_dict(torch.load(os.path.join(file_path, "grbm.pth"), map_location=self.device, weights_only=True))
         self.sampler = self._grbm.make_sampler(self.device, seed=self.RANDOM_SEED, **self._sampler_kwargs_extra)
+        # a checkpoint with another edge count replaces the parameter objects: rebind the optimizer to them
+        self._grbm_optimizer = torch.optim.Adam(self._grbm.parameters(), lr=self.BM_INITIAL_LR,
+                                                weight_decay=self.BM_WEIGHT_DECAY)
 
     def state_dicts(self) -> dict:
         """``{"dvae.pth": ..., "grbm.pth": ...}`` with the reference's key layout (src/model_wrapper.py:148-162)."""
