@@ -306,3 +306,39 @@ def test_cold_schedule_exercises_the_clamp_bit_exactly(cuda_device):
     np.add.at(fields, (slice(None), g.edge_j), got[:, g.edge_i] * J)
     last_colour = g.colour == g.colour.max()               # spins updated last saw the final configuration
     assert np.all((got * fields)[:, last_colour] <= 1e-6)
+
+
+def test_full_size_cfg4_shard_properties(cuda_device):
+    """BASELINE.json cfg4, one GPU's shard: Zephyr Z15 (7440 spins, 71736 couplers), 32768 chains.
+    Bit-exact replay of sampled chain blocks by the oracle, and size-independent properties of the statistics:
+    popcount statistics == an independent int64 reduction of the int8 samples; statistics of two chain shards
+    (chain_offset) add up to the statistics of the single launch (the multi-GPU all-reduce identity)."""
+    from image_generation_b200.stats import edge_statistics, pack_spins
+    g = B.IsingGraph.zephyr(15)
+    assert (g.n, g.n_edges) == (7440, 71736)
+    rng = np.random.default_rng(15)
+    h = (0.05 * rng.uniform(-0.05, 0.05, g.n)).astype(np.float32)
+    J = (0.05 * rng.uniform(-5, 5, g.n_edges)).astype(np.float32)
+    chains, sweeps, seed = 32768, 3, 99
+    s = B.BlockGibbsSampler(g, device=cuda_device)
+    ss = s.sample_ising(h, J, num_reads=chains, num_sweeps=sweeps, seed=seed)
+    x = ss.samples_tensor
+    csr = _oracle_csr(g)
+    for block in (0, 28 * 500, 32764):
+        want = O.gibbs(csr, h, J, O.init_state(csr, 4, seed, chain_offset=block), [1.0] * sweeps, seed=seed, chain_offset=block)
+        assert np.array_equal(x[block:block + 4].cpu().numpy(), want), block
+    s1, s2 = edge_statistics(pack_spins(x, s.device_graph), chains, s.device_graph)
+    assert torch.equal(s1, x.to(torch.int64).sum(0))
+    ei = torch.as_tensor(g.edge_i[:4096].astype(np.int64), device=cuda_device)
+    ej = torch.as_tensor(g.edge_j[:4096].astype(np.int64), device=cuda_device)
+    ref = torch.zeros(4096, dtype=torch.int64, device=cuda_device)
+    for k in range(0, chains, 4096):                       # chunked: (4096 x 4096) int16 products at a time
+        blk = x[k:k + 4096].to(torch.int16)
+        ref += (blk[:, ei] * blk[:, ej]).to(torch.int64).sum(0)
+    assert torch.equal(s2[:4096], ref)
+    parts = []
+    for off, cnt in ((0, 16384), (16384, 16384)):
+        sh = B.BlockGibbsSampler(g, device=cuda_device, chain_offset=off)
+        xs = sh.sample_ising(h, J, num_reads=cnt, num_sweeps=sweeps, seed=seed).samples_tensor
+        parts.append(edge_statistics(pack_spins(xs, sh.device_graph), cnt, sh.device_graph))
+    assert torch.equal(parts[0][0] + parts[1][0], s1) and torch.equal(parts[0][1] + parts[1][1], s2)
