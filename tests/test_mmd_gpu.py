@@ -239,3 +239,27 @@ def test_cta_pair_kernel_matches_single_cta_kernel(cuda_device, monkeypatch):
         got[tile] = mmd_block_sums(zt, m_x, B.GaussianKernel(7).to(cuda_device), path="i8").cpu().numpy()
         np.testing.assert_allclose(got[tile], want, rtol=2e-6)
     np.testing.assert_allclose(got["1"], got["2"], rtol=1e-9)
+
+
+def test_full_size_cfg3_tensor_core_vs_cuda_core(cuda_device):
+    """BASELINE.json cfg3 at full size (8192 + 8192 rows, D = 5640): the tcgen05 int8 path against the independent
+    CUDA-core fp32 path (directly accumulated differences), plus size-independent properties."""
+    g = torch.Generator().manual_seed(3)
+    m, d = 8192, 5640
+    z = torch.randint(0, 2, (2 * m, d), generator=g, dtype=torch.int8) * 2 - 1
+    z[m:, :700] = 1
+    z = z.to(cuda_device)
+    kern = B.GaussianKernel(7).to(cuda_device)
+    s_tc = mmd_block_sums(z, m, kern, path="i8").cpu().numpy()
+    s_cc = mmd_block_sums(z.float(), m, kern, path="f32").cpu().numpy()
+    np.testing.assert_allclose(s_tc, s_cc, rtol=3e-6)
+    # diagonal blocks contain m entries equal to n_kernels, and every entry lies in (0, n_kernels]
+    assert s_tc[0] > 7 * m and s_tc[0] <= 7.0 * m * m and s_tc[2] <= 7.0 * m * m
+    # swapping the roles of x and y swaps S_xx and S_yy and keeps S_xy and the distance sum
+    zs = torch.cat([z[m:], z[:m]], 0).contiguous()
+    s_sw = mmd_block_sums(zs, m, kern, path="i8").cpu().numpy()
+    np.testing.assert_allclose(s_sw[[1, 0, 2, 3]], s_tc, rtol=1e-9)
+    # identical clouds: the biased estimate vanishes
+    x = z[:m].float()
+    val = B.maximum_mean_discrepancy_loss(x, x.clone(), kern, estimator="biased", path="i8")
+    assert abs(float(val)) < 1e-6          # block sums agree to fp32 partial-sum rounding (~1e-8 relative)
