@@ -105,13 +105,14 @@ class _MMDFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, kernel: GaussianKernel, estimator: str, path: str):
         m_x, m_y = x.shape[0], y.shape[0]
-        z = torch.cat([x.detach().to(torch.float32), y.detach().to(torch.float32)], 0).contiguous()
-        zi = None
+        d = x.shape[1]
+        zi = z = None
         if path == "i8":
-            from .mmd_tc import mmd_block_sums_i8, pack_rows_i8
-            zi, _ = pack_rows_i8(z)                       # sign-packed, zero-padded int8 rows (kept for backward)
-            sums = mmd_block_sums_i8(zi, m_x, kernel, d=z.shape[1])
+            from .mmd_tc import mmd_block_sums_i8, pack_pair_i8
+            zi = pack_pair_i8(x, y)                       # sign-packed, zero-padded int8 rows (kept for backward)
+            sums = mmd_block_sums_i8(zi, m_x, kernel, d=d)
         else:
+            z = torch.cat([x.detach().to(torch.float32), y.detach().to(torch.float32)], 0).contiguous()
             sums = mmd_block_sums(z, m_x, kernel, path)
         scale = 1.0 / kernel.n_kernels if kernel.reduce == "mean" else 1.0
         diag = float(kernel.n_kernels)            # k(a, a) = n_kernels * exp(0)
@@ -131,7 +132,7 @@ class _MMDFunction(torch.autograd.Function):
             ctx.save_for_backward(zi, sums)
         else:
             ctx.save_for_backward(z, sums)
-        ctx.meta = (m_x, m_y, kernel, scale * w_xx, -2.0 * scale / (m_x * m_y), path, z.shape[1])
+        ctx.meta = (m_x, m_y, kernel, scale * w_xx, -2.0 * scale / (m_x * m_y), path, d)
         return val.to(x.dtype if x.dtype.is_floating_point else torch.float32)
 
     @staticmethod

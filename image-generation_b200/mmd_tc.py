@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["pack_rows_i8", "mmd_block_sums_i8", "mmd_block_sums_bf16", "mmd_backward_i8", "gemm_bf16_tn"]
+__all__ = ["pack_rows_i8", "pack_pair_i8", "mmd_block_sums_i8", "mmd_block_sums_bf16", "mmd_backward_i8", "gemm_bf16_tn"]
 
 
 def pack_rows_i8(z: torch.Tensor) -> tuple[torch.Tensor, int]:
@@ -34,6 +34,30 @@ def pack_rows_i8(z: torch.Tensor) -> tuple[torch.Tensor, int]:
     with torch.cuda.device(z.device):
         _lib.check(lib.b200grbm_mmd_pack_i8(_lib.ptr(z32), m, d, d_pad, _lib.ptr(out), _lib.current_stream(z.device)))
     return out, d_pad
+
+
+def pack_pair_i8(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Sign-pack ``x`` and ``y`` straight into one zero-padded int8 matrix ``[x; y]`` (no fp32 concatenation):
+    the spin extraction of the encoder output (src/model_wrapper.py:318) fused with the MMD input layout."""
+    if not (x.is_cuda and y.is_cuda):
+        raise RuntimeError("the tcgen05 MMD path runs on CUDA only (no CPU fallback)")
+    (m_x, d), m_y = x.shape, y.shape[0]
+    d_pad = (d + 127) // 128 * 128
+    out = torch.empty((m_x + m_y, d_pad), dtype=torch.int8, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        st = _lib.current_stream(x.device)
+        for src, row0 in ((x, 0), (y, m_x)):
+            rows = src.shape[0]
+            dst = out[row0:row0 + rows]
+            if src.dtype == torch.int8:
+                dst[:, :d] = src
+                if d_pad > d:
+                    dst[:, d:] = 0
+            else:
+                s32 = src.detach().to(torch.float32).contiguous()
+                _lib.check(lib.b200grbm_mmd_pack_i8(_lib.ptr(s32), rows, d, d_pad, dst.data_ptr(), st))
+    return out
 
 
 def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = None, d: int = None) -> torch.Tensor:
