@@ -26,6 +26,8 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 namespace b200grbm {
 
 constexpr int BM = 128;             // accumulator rows   (UMMA M)
@@ -40,6 +42,8 @@ constexpr int EPI_WARPS = 8;
 constexpr uint32_t TMEM_COLS = 512;
 
 enum { TC_PASS_DIST = 0, TC_PASS_KERNEL = 1, TC_PASS_COEF = 2 };
+constexpr int TC_MAX_SB = 136;          // up to 16 super-blocks per side (m <= 65536)
+constexpr int TC_SB_ROWS = 32, TC_SB_COLS = 16;   // tiles per super-block: 32 x 128 rows, 16 x 256 columns
 
 struct TcParams {
     int m_x, m, d;
@@ -54,6 +58,11 @@ struct TcParams {
     int m_pad;          // row pitch (elements) of coef_hi / coef_lo, multiple of 64
     float w_xx, w_xy;
     __nv_bfloat16 *coef_hi, *coef_lo;
+    // L2-sized super-blocks of the tile triangle (forward passes): 4096 x 4096 entries = 32 x 16 tiles per
+    // block pair, so the rows a wave of CTAs touches (2 x 23 MB at D = 5640) stay resident in one L2 partition
+    int sb_count;                       // 0 -> plain column-major triangle
+    int sb_start[TC_MAX_SB + 1];
+    unsigned char sb_bi[TC_MAX_SB], sb_bj[TC_MAX_SB];
 };
 
 // upper-triangle tile enumeration: column tile j ascending, row tiles i = 0 .. min(tiles_m, 2j+2) - 1
@@ -71,16 +80,36 @@ __device__ __forceinline__ void tile_coords(const TcParams &p, int t, int &i, in
         j = t / p.tiles_mx;
         return;
     }
-    if (t < p.p0) {
+    int tm = p.tiles_m, j0 = p.j0, p0 = p.p0, ibase = 0, jbase = 0;
+    if (p.sb_count > 0) {
+        int k = 0;
+        while (k + 1 < p.sb_count && p.sb_start[k + 1] <= t) ++k;
+        t -= p.sb_start[k];
+        const int bi = p.sb_bi[k], bj = p.sb_bj[k];
+        ibase = bi * TC_SB_ROWS;
+        jbase = bj * TC_SB_COLS;
+        const int nr = min(TC_SB_ROWS, p.tiles_m - ibase), nc = min(TC_SB_COLS, p.tiles_n - jbase);
+        if (bi != bj) {                     // whole block lies right of the diagonal
+            i = ibase + t % nr;
+            j = jbase + t / nr;
+            return;
+        }
+        tm = nr;                            // diagonal block: the same triangle rule in local coordinates
+        j0 = nr / 2 < nc ? nr / 2 : nc;
+        p0 = j0 * (j0 + 1);
+    }
+    if (t < p0) {
         j = (int)((sqrtf(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
         while ((j + 1) * (j + 2) <= t) ++j;
         while (j * (j + 1) > t) --j;
         i = t - j * (j + 1);
     } else {
-        const int r = t - p.p0;
-        j = p.j0 + r / p.tiles_m;
-        i = r % p.tiles_m;
+        const int r = t - p0;
+        j = j0 + r / tm;
+        i = r % tm;
     }
+    i += ibase;
+    j += jbase;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap,
@@ -422,6 +451,32 @@ extern "C" int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int
     p.stages = stages;
     p.lut = lut_dev;
     p.sums = sums_dev;
+    {   // super-block order (column block outer, row block inner); same tile set, L2-friendly order
+        const int nb = (p.tiles_n + TC_SB_COLS - 1) / TC_SB_COLS;
+        const char *env = getenv("B200GRBM_MMD_ORDER");
+        if (nb >= 2 && nb * (nb + 1) / 2 <= TC_MAX_SB && !(env != nullptr && env[0] == '0')) {
+            int k = 0, start = 0;
+            for (int bj = 0; bj < nb; ++bj)
+                for (int bi = 0; bi <= bj; ++bi) {
+                    const int nr = std::min(TC_SB_ROWS, p.tiles_m - bi * TC_SB_ROWS), nc = std::min(TC_SB_COLS, p.tiles_n - bj * TC_SB_COLS);
+                    if (nr <= 0 || nc <= 0) continue;
+                    int cnt = nr * nc;
+                    if (bi == bj) {
+                        const int j0 = nr / 2 < nc ? nr / 2 : nc;
+                        cnt = j0 * (j0 + 1) + (nc - j0) * nr;
+                    }
+                    p.sb_bi[k] = (unsigned char)bi;
+                    p.sb_bj[k] = (unsigned char)bj;
+                    p.sb_start[k] = start;
+                    start += cnt;
+                    ++k;
+                }
+            p.sb_start[k] = start;
+            p.sb_count = k;
+            if (start != p.total_tiles)
+                return fail(B200GRBM_EINVAL, "mmd_forward_i8: internal tile enumeration mismatch (%d vs %d)", start, p.total_tiles);
+        }
+    }
 
     B200_CUDA(cudaFuncSetAttribute(mmd_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + 1024)));
     const int sms = sm_count() > 0 ? sm_count() : 148;

@@ -263,3 +263,17 @@ def test_full_size_cfg3_tensor_core_vs_cuda_core(cuda_device):
     x = z[:m].float()
     val = B.maximum_mean_discrepancy_loss(x, x.clone(), kern, estimator="biased", path="i8")
     assert abs(float(val)) < 1e-6          # block sums agree to fp32 partial-sum rounding (~1e-8 relative)
+
+
+def test_tensor_core_super_block_tile_order_ragged(cuda_device):
+    """m > 4096 switches the forward to L2-sized super-blocks of the tile triangle; ragged sizes make the last
+    super-blocks partial.  Every tile must still be visited exactly once: block sums against the float64 oracle."""
+    rng = np.random.default_rng(77)
+    m_x, m_y, d = 3000, 2531, 48
+    z = rng.choice([-1, 1], size=(m_x + m_y, d)).astype(np.int8)
+    z[m_x:, :10] = 1
+    kern = B.GaussianKernel(7).to(cuda_device)
+    got = mmd_block_sums(torch.from_numpy(z).to(cuda_device), m_x, kern, path="i8").cpu().numpy()
+    k, bw, dist = O.gaussian_kernel_matrix(z.astype(np.float64))
+    want = [k[:m_x, :m_x].sum(), k[m_x:, m_x:].sum(), k[:m_x, m_x:].sum(), dist.sum()]
+    np.testing.assert_allclose(got, want, rtol=2e-6)
