@@ -81,6 +81,8 @@ SIGNATURES = {
                               _vp], _i32),
     "b200grbm_gemm_bf16_tn": ([_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp], _i32),
     "b200grbm_mmd_forward_bf16": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _vp], _i32),
+    "b200grbm_mmd_coef_bf16": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _f32, _f32, _vp, _vp, _i32,
+                                _vp], _i32),
     "b200grbm_tensor_peak": ([_i32, _i32, C.POINTER(C.c_double), _vp], _i32),
     "b200grbm_mmd_backward_f32": ([_vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _f32, _f32, _vp, _vp, _vp,
                                    _vp], _i32),

@@ -11,6 +11,8 @@
 // Skeleton shared with mmd_tc.cu / gemm_tc.cu (TMA ring -> tcgen05.mma.kind::f16 -> 2 TMEM stages).
 #include "tc_common.cuh"
 
+#include <cuda_bf16.h>
+
 namespace b200grbm {
 
 constexpr int F_BM = 128, F_BN = 256, F_BK = 64;
@@ -18,7 +20,7 @@ constexpr int F_UMMA_K = 16;
 constexpr int F_A_BYTES = F_BM * F_BK * 2, F_B_BYTES = F_BN * F_BK * 2, F_STAGE_BYTES = F_A_BYTES + F_B_BYTES;
 constexpr int F_STAGES = 4, F_THREADS = 320, F_EPI_WARPS = 8, F_MAX_KERNELS = 16;
 
-enum { F_PASS_DIST = 0, F_PASS_KERNEL = 1 };
+enum { F_PASS_DIST = 0, F_PASS_KERNEL = 1, F_PASS_COEF = 2 };
 
 struct BfParams {
     int m_x, m, k_pad;
@@ -28,10 +30,19 @@ struct BfParams {
     float mul_factor, bandwidth;
     const float *norms;                    // [m] squared norms of the rounded rows
     double *sums;                          // [4]
+    // F_PASS_COEF (backward): A[a][b] = w * (dk/dt) (dt/d||.||) / ||.|| as a bf16 (hi, lo) pair, x rows only
+    int tiles_mx, m_pad;
+    float w_xx, w_xy;
+    __nv_bfloat16 *coef_hi, *coef_lo;
 };
 
 __device__ __forceinline__ void bf_tile_coords(const BfParams &p, int t, int &i, int &j)
 {
+    if (p.pass == F_PASS_COEF) {           // full rectangle: x rows against every column
+        i = t % p.tiles_mx;
+        j = t / p.tiles_mx;
+        return;
+    }
     if (t < p.p0) {
         j = (int)((sqrtf(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
         while ((j + 1) * (j + 2) <= t) ++j;
@@ -158,6 +169,49 @@ __global__ void __launch_bounds__(F_THREADS, 1) mmd_gram_bf16_kernel(const __gri
                 const int cbase = half * 128 + chunk * 32;
                 __syncwarp();
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * F_BN + (uint32_t)cbase, v);
+                if (p.pass == F_PASS_COEF) {
+                    if (row < p.m_x) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int q = 0; q < 32; q += 2) {
+                            float cf[2];
+#pragma unroll
+                            for (int h2 = 0; h2 < 2; ++h2) {
+                                const int col = col0 + cbase + q + h2;
+                                const float d2 = fmaxf(fmaf(-2.f, u2f(v[q + h2]), n_row + cn[cbase + q + h2]), 0.f);
+                                float tt;
+                                if (p.squared) tt = d2;
+                                else asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(tt) : "f"(d2));
+                                float dk = 0.f;                       // dk/dt = ln2 * sum_u c_u exp2(t c_u)
+#pragma unroll
+                                for (int u = 0; u < F_MAX_KERNELS; ++u) {
+                                    if (u < p.n_kernels) {
+                                        float e;
+                                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(tt * c[u]));
+                                        dk = fmaf(c[u], e, dk);
+                                    }
+                                }
+                                dk *= 0.6931471805599453f;
+                                float val = p.squared ? 2.f * dk : (tt > 0.f ? __fdividef(dk, tt) : 0.f);
+                                if (col >= p.m || col == row || d2 <= 0.f) val = 0.f;
+                                cf[h2] = val * (col < p.m_x ? p.w_xx : p.w_xy);
+                            }
+                            const __nv_bfloat162 hh = __floats2bfloat162_rn(cf[0], cf[1]);
+                            const __nv_bfloat162 ll = __floats2bfloat162_rn(cf[0] - __low2float(hh), cf[1] - __high2float(hh));
+                            hi[q >> 1] = *reinterpret_cast<const uint32_t *>(&hh);
+                            lo[q >> 1] = *reinterpret_cast<const uint32_t *>(&ll);
+                        }
+                        const size_t off = (size_t)row * p.m_pad + (size_t)(col0 + cbase);
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; ++g4) {
+                            if (col0 + cbase + 8 * g4 < p.m_pad) {
+                                *reinterpret_cast<uint4 *>(p.coef_hi + off + 8 * g4) = make_uint4(hi[4 * g4], hi[4 * g4 + 1], hi[4 * g4 + 2], hi[4 * g4 + 3]);
+                                *reinterpret_cast<uint4 *>(p.coef_lo + off + 8 * g4) = make_uint4(lo[4 * g4], lo[4 * g4 + 1], lo[4 * g4 + 2], lo[4 * g4 + 3]);
+                            }
+                        }
+                    }
+                    continue;
+                }
 #pragma unroll 4
                 for (int q = 0; q < 32; ++q) {
                     const int col = col0 + cbase + q;
@@ -220,7 +274,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mmd_gram_bf16_kernel(const __gri
         double tot = 0.0;
         for (int w = 0; w < F_EPI_WARPS; ++w) tot += red[threadIdx.x][w];
         if (p.pass == F_PASS_DIST) { if (threadIdx.x == 0) atomicAdd(p.sums + 3, tot); }
-        else if (tot != 0.0) atomicAdd(p.sums + threadIdx.x, tot);
+        else if (p.pass == F_PASS_KERNEL && tot != 0.0) atomicAdd(p.sums + threadIdx.x, tot);
     }
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -274,6 +328,50 @@ extern "C" int32_t b200grbm_mmd_forward_bf16(const void *z_hi_dev, const void *z
         B200_CUDA(cudaGetLastError());
     }
     p.pass = F_PASS_KERNEL;
+    mmd_gram_bf16_kernel<<<grid, F_THREADS, smem, st>>>(map_hi, map_lo, p);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int32_t b200grbm_mmd_coef_bf16(const void *z_hi_dev, const void *z_lo_dev, const float *norms_dev, int32_t m_x,
+                                          int32_t m_y, int32_t k_pad, int32_t n_kernels, float mul_factor, int32_t squared,
+                                          float bandwidth, const double *sums_dev, float w_xx, float w_xy, void *coef_hi_dev,
+                                          void *coef_lo_dev, int32_t m_pad, void *stream)
+{
+    if (m_x <= 0 || m_y <= 0 || k_pad <= 0 || k_pad % 64 != 0)
+        return fail(B200GRBM_EINVAL, "mmd_coef_bf16: m_x=%d m_y=%d k_pad=%d (must be a multiple of 64)", m_x, m_y, k_pad);
+    const int m = m_x + m_y;
+    if (m_pad < m || m_pad % 64 != 0) return fail(B200GRBM_EINVAL, "mmd_coef_bf16: m_pad=%d must be a multiple of 64 >= m=%d", m_pad, m);
+    if (n_kernels < 1 || n_kernels > F_MAX_KERNELS || !(mul_factor > 0.f))
+        return fail(B200GRBM_EINVAL, "mmd_coef_bf16: n_kernels=%d mul_factor=%g", n_kernels, mul_factor);
+    if (!z_hi_dev || !norms_dev || !sums_dev || !coef_hi_dev || !coef_lo_dev)
+        return fail(B200GRBM_EINVAL, "mmd_coef_bf16: NULL pointer argument");
+    B200_TRY(require_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap map_hi, map_lo;
+    B200_TRY(make_tensor_map_2d(&map_hi, z_hi_dev, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)k_pad, (uint64_t)m,
+                                (uint64_t)k_pad * 2, F_BK, 128));
+    B200_TRY(make_tensor_map_2d(&map_lo, z_lo_dev ? z_lo_dev : z_hi_dev, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)k_pad,
+                                (uint64_t)m, (uint64_t)k_pad * 2, F_BK, 128));
+    BfParams p = {};
+    p.m_x = m_x; p.m = m; p.k_pad = k_pad;
+    p.kblocks_per_product = k_pad / F_BK;
+    p.products = z_lo_dev ? 3 : 1;
+    p.tiles_m = (m + F_BM - 1) / F_BM;
+    p.tiles_n = (m_pad + F_BN - 1) / F_BN;
+    p.tiles_mx = (m_x + F_BM - 1) / F_BM;
+    p.total_tiles = p.tiles_mx * p.tiles_n;
+    p.pass = F_PASS_COEF;
+    p.n_kernels = n_kernels; p.squared = squared; p.mul_factor = mul_factor; p.bandwidth = bandwidth;
+    p.norms = norms_dev;
+    p.sums = const_cast<double *>(sums_dev);
+    p.m_pad = m_pad; p.w_xx = w_xx; p.w_xy = w_xy;
+    p.coef_hi = reinterpret_cast<__nv_bfloat16 *>(coef_hi_dev);
+    p.coef_lo = reinterpret_cast<__nv_bfloat16 *>(coef_lo_dev);
+    const size_t smem = (size_t)F_STAGES * F_STAGE_BYTES + 2 * F_BN * sizeof(float) + (2 * F_STAGES + 4) * 8 + 16 + 1024;
+    B200_CUDA(cudaFuncSetAttribute(mmd_gram_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     mmd_gram_bf16_kernel<<<grid, F_THREADS, smem, st>>>(map_hi, map_lo, p);
     B200_CUDA(cudaGetLastError());
     return 0;

@@ -111,6 +111,11 @@ class _MMDFunction(torch.autograd.Function):
             from .mmd_tc import mmd_block_sums_i8, pack_pair_i8
             zi = pack_pair_i8(x, y)                       # sign-packed, zero-padded int8 rows (kept for backward)
             sums = mmd_block_sums_i8(zi, m_x, kernel, d=d)
+        elif path in ("bf16", "bf16x3"):
+            from .mmd_tc import mmd_block_sums_bf16
+            z = torch.cat([x.detach().to(torch.float32), y.detach().to(torch.float32)], 0).contiguous()
+            sums, ops = mmd_block_sums_bf16(z, m_x, kernel, split=(path == "bf16x3"), return_operands=True)
+            ctx.bf16_operands = ops
         else:
             z = torch.cat([x.detach().to(torch.float32), y.detach().to(torch.float32)], 0).contiguous()
             sums = mmd_block_sums(z, m_x, kernel, path)
@@ -142,6 +147,10 @@ class _MMDFunction(torch.autograd.Function):
         if path == "i8":
             from .mmd_tc import mmd_backward_i8
             return mmd_backward_i8(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out.detach().reshape(())), None, None, None, None
+        if path in ("bf16", "bf16x3"):
+            from .mmd_tc import mmd_backward_bf16
+            return (mmd_backward_bf16(ctx.bf16_operands, m_x, kernel, sums, w_xx, w_xy, grad_out.detach().reshape(())),
+                    None, None, None, None)
         coef = torch.empty((m_x, m_x + m_y), dtype=torch.float32, device=z.device)
         grad_x = torch.empty((m_x, d), dtype=torch.float32, device=z.device)
         g = grad_out.detach().reshape(1).to(torch.float32).contiguous()
@@ -163,7 +172,7 @@ def maximum_mean_discrepancy_loss(x: torch.Tensor, y: torch.Tensor, kernel: Gaus
     tensor-core kernel (exact for +-1 rows; encoder spins carry only straight-through residue
     ~1e-7, src/utils/common.py:162-173); ``"f32"`` is the precise CUDA-core path for arbitrary
     real inputs; ``"bf16"`` / ``"bf16x3"`` run the Gram of real-valued rows on the tcgen05 bf16
-    kernel (forward; their backward uses the fp32 kernels).  The backward pass of the ``"i8"`` path also runs on tensor cores (coefficient
+    kernel, forward and backward.  The backward pass of the ``"i8"`` path also runs on tensor cores (coefficient
     matrix from the int8 Gram as a bf16 hi/lo pair, then one bf16 GEMM); the gradient is
     evaluated at the sign-packed points.
     """

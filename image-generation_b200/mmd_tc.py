@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["pack_rows_i8", "pack_pair_i8", "mmd_block_sums_i8", "mmd_block_sums_bf16", "mmd_backward_i8", "gemm_bf16_tn"]
+__all__ = ["pack_rows_i8", "pack_pair_i8", "mmd_block_sums_i8", "mmd_block_sums_bf16", "mmd_backward_bf16", "mmd_backward_i8", "gemm_bf16_tn"]
 
 
 def pack_rows_i8(z: torch.Tensor) -> tuple[torch.Tensor, int]:
@@ -125,13 +125,9 @@ def mmd_backward_i8(zi: torch.Tensor, d: int, m_x: int, kernel, sums: torch.Tens
     return grad_out.to(torch.float32) * (c[:, d:d + 1] * x - c[:, :d])
 
 
-def mmd_block_sums_bf16(z: torch.Tensor, m_x: int, kernel, split: bool = True, sums: torch.Tensor = None) -> torch.Tensor:
-    """``[S_xx, S_yy, S_xy, sum_ab t_ab]`` for real-valued rows on the tcgen05 bf16 kernel.
-    ``split=True`` feeds the rows as a bf16 (hi, lo) pair and contracts hi.hi + hi.lo + lo.hi
-    (fp32-class accuracy, three times the tensor work); ``split=False`` rounds the rows to bf16 once
-    (the distances are then exactly those of the rounded points)."""
-    if not z.is_cuda:
-        raise RuntimeError("the tcgen05 MMD path runs on CUDA only (no CPU fallback)")
+def _split_bf16(z: torch.Tensor, split: bool):
+    """fp32 rows -> zero-padded bf16 ``hi`` (and residual ``lo``) with K padded to 64, plus the fp32 squared
+    norms of the rounded rows."""
     m, d = z.shape
     k_pad = (d + 63) // 64 * 64
     z32 = z.detach().to(torch.float32)
@@ -144,6 +140,19 @@ def mmd_block_sums_bf16(z: torch.Tensor, m_x: int, kernel, split: bool = True, s
         lo[:, :d] = (z32 - rounded).to(torch.bfloat16)
         rounded = rounded + lo[:, :d].to(torch.float32)
     norms = (rounded * rounded).sum(1).contiguous()
+    return hi, lo, norms, rounded, k_pad
+
+
+def mmd_block_sums_bf16(z: torch.Tensor, m_x: int, kernel, split: bool = True, sums: torch.Tensor = None,
+                        return_operands: bool = False):
+    """``[S_xx, S_yy, S_xy, sum_ab t_ab]`` for real-valued rows on the tcgen05 bf16 kernel.
+    ``split=True`` feeds the rows as a bf16 (hi, lo) pair and contracts hi.hi + hi.lo + lo.hi
+    (fp32-class accuracy, three times the tensor work); ``split=False`` rounds the rows to bf16 once
+    (the distances are then exactly those of the rounded points)."""
+    if not z.is_cuda:
+        raise RuntimeError("the tcgen05 MMD path runs on CUDA only (no CPU fallback)")
+    m = z.shape[0]
+    hi, lo, norms, rounded, k_pad = _split_bf16(z, split)
     if sums is None:
         sums = torch.empty(4, dtype=torch.float64, device=z.device)
     lib = _lib.load()
@@ -152,4 +161,39 @@ def mmd_block_sums_bf16(z: torch.Tensor, m_x: int, kernel, split: bool = True, s
         _lib.check(lib.b200grbm_mmd_forward_bf16(_lib.ptr(hi), _lib.ptr(lo), _lib.ptr(norms), m_x, m - m_x, k_pad,
                                                  kernel.n_kernels, kernel.mul_factor, int(kernel.squared), bw,
                                                  _lib.ptr(sums), _lib.current_stream(z.device)))
+    if return_operands:
+        return sums, (hi, lo, norms, rounded)
     return sums
+
+
+def mmd_backward_bf16(operands, m_x: int, kernel, sums: torch.Tensor, w_xx: float, w_xy: float,
+                      grad_out: torch.Tensor) -> torch.Tensor:
+    """d(MMD)/dx for real-valued rows on tensor cores: coefficient matrix from the bf16 Gram (bf16 hi/lo pair),
+    then bf16 GEMMs against ``[Z^T; 1]`` (Z itself as a hi/lo pair): ``grad_x[a] = rowsum_a x_a - (A Z)_a``."""
+    hi, lo, norms, rounded = operands
+    m, k_pad = hi.shape
+    d = rounded.shape[1]
+    dev = hi.device
+    m_pad = (m + 63) // 64 * 64
+    rows_alloc = (m_x + 127) // 128 * 128
+    a_hi = torch.empty((rows_alloc, m_pad), dtype=torch.bfloat16, device=dev)
+    a_lo = torch.empty((rows_alloc, m_pad), dtype=torch.bfloat16, device=dev)
+    if rows_alloc > m_x:
+        a_hi[m_x:].zero_()
+        a_lo[m_x:].zero_()
+    lib = _lib.load()
+    bw = -1.0 if kernel.bandwidth is None else kernel.bandwidth
+    with torch.cuda.device(dev):
+        _lib.check(lib.b200grbm_mmd_coef_bf16(_lib.ptr(hi), _lib.ptr(lo), _lib.ptr(norms), m_x, m - m_x, k_pad,
+                                              kernel.n_kernels, kernel.mul_factor, int(kernel.squared), bw,
+                                              _lib.ptr(sums), w_xx, w_xy, _lib.ptr(a_hi), _lib.ptr(a_lo), m_pad,
+                                              _lib.current_stream(dev)))
+    b_hi = torch.zeros((d + 1, m_pad), dtype=torch.bfloat16, device=dev)       # [Z^T; 1], K = m_pad
+    b_hi[:d, :m] = hi[:, :d].t()
+    b_hi[d, :m] = 1
+    c = gemm_bf16_tn(a_hi, a_lo, b_hi, m_x)
+    if lo is not None:                                                          # + A_hi . Z_lo
+        b_lo = torch.zeros((d + 1, m_pad), dtype=torch.bfloat16, device=dev)
+        b_lo[:d, :m] = lo[:, :d].t()
+        c = c + gemm_bf16_tn(a_hi, None, b_lo, m_x)
+    return grad_out.to(torch.float32) * (c[:, d:d + 1] * rounded[:m_x] - c[:, :d])

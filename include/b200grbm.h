@@ -223,6 +223,16 @@ int32_t b200grbm_mmd_forward_bf16(const void *z_hi_dev, const void *z_lo_dev, co
  */
 int32_t b200grbm_tensor_peak(int32_t kind, int32_t iters, double *ops_per_s_out, void *stream);
 
+/*
+ * Backward coefficients for real-valued rows on the tcgen05 bf16 kernel (counterpart of
+ * b200grbm_mmd_coef_i8): A_ab = w * (dk/dt)(dt/d||.||)/||.|| as a bf16 (hi, lo) pair for the x rows,
+ * then grad_x = rowsum(A) x - A Z through b200grbm_gemm_bf16_tn.  sums_dev[3] = the forward's distance sum.
+ */
+int32_t b200grbm_mmd_coef_bf16(const void *z_hi_dev, const void *z_lo_dev, const float *norms_dev, int32_t m_x,
+                               int32_t m_y, int32_t k_pad, int32_t n_kernels, float mul_factor, int32_t squared,
+                               float bandwidth, const double *sums_dev, float w_xx, float w_xy, void *coef_hi_dev,
+                               void *coef_lo_dev, int32_t m_pad, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

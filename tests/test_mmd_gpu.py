@@ -213,14 +213,23 @@ def test_bf16_tensor_core_path_for_continuous_rows(cuda_device, m_x, m_y, d, ban
     z_rounded = torch.from_numpy(z).to(torch.bfloat16).to(torch.float32).numpy()
     np.testing.assert_allclose(got1[:3], want(z_rounded)[:3], rtol=2e-5)
     np.testing.assert_allclose(got1[:3], w[:3], rtol=2e-3)          # and close to the unrounded answer
-    # the loss call accepts the path; gradient comes from the fp32 kernels
+    # the loss call: value and gradient (tensor-core backward: bf16 coefficient pass + bf16 GEMMs) vs the oracle
     xg = zt[:m_x].clone().requires_grad_(True)
     val = B.maximum_mean_discrepancy_loss(xg, zt[m_x:], kern, path="bf16x3")
     val.backward()
-    ref = O.mmd(z[:m_x], z[m_x:], bandwidth=bandwidth)
+    bw = O.gaussian_kernel_matrix(z.astype(np.float64), bandwidth=bandwidth)[1]
+    ref, ref_grad = O.mmd(z[:m_x], z[m_x:], bandwidth=bw, return_grad=True)
     k, _, _ = O.gaussian_kernel_matrix(z.astype(np.float64), bandwidth=bandwidth)
     scale = abs(k[:m_x, :m_x].mean()) + abs(k[m_x:, m_x:].mean()) + 2 * abs(k[:m_x, m_x:].mean())
-    assert abs(float(val) - ref) <= 1e-5 * scale and torch.isfinite(xg.grad).all()
+    assert abs(float(val.detach()) - ref) <= 1e-5 * scale
+    got_grad = xg.grad.cpu().numpy()
+    rel = np.linalg.norm(got_grad - ref_grad) / np.linalg.norm(ref_grad)
+    assert rel < 5e-4, rel
+    # and the CUDA-core backward agrees
+    xf = zt[:m_x].clone().requires_grad_(True)
+    B.maximum_mean_discrepancy_loss(xf, zt[m_x:], kern, path="f32").backward()
+    rel2 = np.linalg.norm(got_grad - xf.grad.cpu().numpy()) / np.linalg.norm(ref_grad)
+    assert rel2 < 5e-4, rel2
 
 
 def test_cta_pair_kernel_matches_single_cta_kernel(cuda_device, monkeypatch):
