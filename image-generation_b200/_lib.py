@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libb200grbm.so")
 
 ACCEPT_EXACT = 0
 ACCEPT_FAST = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class B200Error(RuntimeError):
@@ -66,6 +66,7 @@ SIGNATURES = {
     "b200grbm_set_weights": ([_vp, _vp, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _i32, _i32,
                               _vp, _vp, _vp, _vp], _i32),
     "b200grbm_sweep_smem_bytes": ([_i32, _i32, _i32, _i32], C.c_int64),
+    "b200grbm_sweep_state_offset": ([_i32], _i32),
     "b200grbm_gibbs_sweeps": ([C.POINTER(SweepArgs), _vp], _i32),
     "b200grbm_last_launch_count": ([], _i32),
     "b200grbm_pack_f32": ([_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp], _i32),

@@ -26,10 +26,16 @@
 //   * Same-colour spins are never adjacent, so the parallel colour step equals the
 //     sequential sweep in visit order; W[p] is written in place and __syncthreads()
 //     separates rounds.
-//   * Uniforms: Philox4x32-10 keyed by (seed; visit position, sweep, global chain / 4) --
-//     one call feeds 4 chains of the lane -- so trajectories do not depend on CPL, CTA
-//     size, grid or GPU count.  Round keys are precomputed on the host into the kernel
-//     parameter block (uniform-register operands).
+//   * Uniforms: Philox4x32-10 keyed by (seed; visit position, sweep, global chain / 8) --
+//     one call yields the high 16 bits of the uniforms of 8 chains of the lane; the low 7
+//     bits live in a second stream that is only evaluated when a decision depends on them --
+//     so trajectories do not depend on CPL, CTA size, grid or GPU count.  Round keys are
+//     precomputed on the host into the kernel parameter block (uniform-register operands).
+//   * Lazy exact acceptance: the contract decision  fmaf(v, exp2_poly(x), v) < 1  is first
+//     bracketed with MUFU.EX2 and the 16-bit midpoint uniform; only when the bracket
+//     (2^-17 (1 + e) on v, 2^-20 relative on e) contains the threshold -- about 2e-5 of the
+//     decisions -- is the lane-task redone with the polynomial and the full 23-bit uniform.
+//     The result is bit-identical to evaluating the contract everywhere (oracle/oracle.c).
 #include "common.cuh"
 
 namespace b200grbm {
@@ -37,7 +43,8 @@ namespace b200grbm {
 enum { MODE_PHILOX_EXACT = 0, MODE_PHILOX_FAST = 1, MODE_SUPPLIED_EXACT = 2 };
 
 struct SweepParams {
-    const uint2 *tiles;       // [n_tiles][1 + width][threads]: row 0 {f0 bits, -}, rows 1.. {2J bits, nbr}
+    const uint2 *tiles;       // [n_tiles][1 + width][threads]: row 0 {f0 bits, -}, rows 1.. {2J bits, byte offset
+                              //  of the neighbour's state word in dynamic shared memory}
     const int2 *tile_info;    // [n_tiles] {first visit position, spins in this round}
     const int32_t *order;
     const float *coef;
@@ -111,34 +118,68 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__device__ __forceinline__ float uniform_from_bits(uint32_t bits)
+__device__ __forceinline__ float uniform_from_m23(uint32_t m23)
 {
-    // (bits >> 9) | 0x3f800000, then one exact add (spec header)
-    const float one_to_two = u2f((bits >> 9) | 0x3f800000u);
-    return __fadd_rn(one_to_two, -1.0f + B200GRBM_UNIFORM_HALF_ULP);
+    // as_float(m23 | 0x3f800000) - 1 + 2^-24, one exact add (spec header)
+    return __fadd_rn(u2f(m23 | 0x3f800000u), -1.0f + B200GRBM_UNIFORM_HALF_ULP);
 }
 
-template <bool FAST>
-__device__ __forceinline__ bool accept_plus(float f, float coef, float v)
+// halfword j (0..7) of a Philox call
+__device__ __forceinline__ uint32_t halfword(const uint32_t (&r)[4], int j)
+{
+    return (j & 1) ? (r[j >> 1] >> 16) : (r[j >> 1] & 0xffffu);
+}
+
+// (hw + 0.5) * 2^-16 : midpoint of the 128 uniforms that share the 16 high bits hw.
+// PRMT builds as_float(2^23 + hw); one exact FMA maps it to the midpoint.
+__device__ __forceinline__ float uniform_midpoint(const uint32_t (&r)[4], int j)
+{
+    const uint32_t big = __byte_perm(r[j >> 1], 0x4B000000u, (j & 1) ? 0x7632u : 0x7610u);
+    return __fmaf_rn(u2f(big), 0x1.0p-16f, -(128.0f - 0x1.0p-17f));
+}
+
+// The contract's decision (include/b200grbm_spec.h): +1 iff fmaf(v, exp2_poly(clamp(f coef)), v) < 1.
+__device__ __forceinline__ bool accept_exact(float f, float coef, float v)
 {
     float x = __fmul_rn(f, coef);
-    float e;
-    if (FAST) {
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
-    } else {
-        x = fminf(fmaxf(x, -B200GRBM_EXP2_CLAMP), B200GRBM_EXP2_CLAMP);
-        const float t = __fadd_rn(x, B200GRBM_EXP2_MAGIC);
-        const float nn = __fadd_rn(t, -B200GRBM_EXP2_MAGIC);
-        const float r = __fadd_rn(x, -nn);
-        float q = B200GRBM_EXP2_C5;
-        q = __fmaf_rn(q, r, B200GRBM_EXP2_C4);
-        q = __fmaf_rn(q, r, B200GRBM_EXP2_C3);
-        q = __fmaf_rn(q, r, B200GRBM_EXP2_C2);
-        q = __fmaf_rn(q, r, B200GRBM_EXP2_C1);
-        q = __fmaf_rn(q, r, B200GRBM_EXP2_C0);
-        e = u2f(f2u(q) + (f2u(t) << 23));
-    }
+    x = fminf(fmaxf(x, -B200GRBM_EXP2_CLAMP), B200GRBM_EXP2_CLAMP);
+    const float t = __fadd_rn(x, B200GRBM_EXP2_MAGIC);
+    const float nn = __fadd_rn(t, -B200GRBM_EXP2_MAGIC);
+    const float r = __fadd_rn(x, -nn);
+    float q = B200GRBM_EXP2_C5;
+    q = __fmaf_rn(q, r, B200GRBM_EXP2_C4);
+    q = __fmaf_rn(q, r, B200GRBM_EXP2_C3);
+    q = __fmaf_rn(q, r, B200GRBM_EXP2_C2);
+    q = __fmaf_rn(q, r, B200GRBM_EXP2_C1);
+    q = __fmaf_rn(q, r, B200GRBM_EXP2_C0);
+    const float e = u2f(f2u(q) + (f2u(t) << 23));
     return __fmaf_rn(v, e, v) < 1.0f;
+}
+
+// Bracketed decision.  d = vm (1 + e~) - 1 with e~ = MUFU.EX2; the sign of d is the contract's
+// decision whenever |d| exceeds the bracket  K1 (1 + e~) + K2:
+//   |v - vm| <= 2^-17 (Philox mode: vm is the 16-bit midpoint; supplied mode: vm = v)
+//   |e~ - e| <= 2^-20 e  (ex2.approx.ftz: 2^-22 relative; contract polynomial: 2.4e-7), roundings 2^-24
+//   => |v (1 + e) - vm (1 + e~)| <= 2^-17 (1 + e)(1 + 2^-19) + (d + 1) 2^-19  <  K1 (1 + e~) + K2 - 2^-24
+// with K1 = 2^-17 (1 + 2^-10), K2 = 2^-17.  `sure` accumulates over the lane-task.
+#define B200GRBM_LAZY_K1 0x1.004p-17f
+#define B200GRBM_LAZY_K2 0x1.0p-17f
+
+template <bool CHECK>
+__device__ __forceinline__ uint32_t decide_quick(float f, float coef, float vm, uint32_t &unsure)
+{
+    const float x = fminf(__fmul_rn(f, coef), B200GRBM_EXP2_CLAMP);   // upper clamp keeps 1 + e~ finite
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+    const float g = __fadd_rn(e, 1.0f);
+    const float d = __fmaf_rn(vm, g, -1.0f);
+    if (CHECK) {
+        // sign bit of  |d| - K2 - K1 g  marks the decision as inside its bracket; one funnel shift per
+        // decision collects the marks (dense: chain c -> bit c)
+        const float m = __fmaf_rn(g, -B200GRBM_LAZY_K1, __fadd_rn(fabsf(d), -B200GRBM_LAZY_K2));
+        unsure = __funnelshift_l(f2u(m), unsure, 1);
+    }
+    return f2u(d);   // bit 31 set <=> +1
 }
 
 // Bit of the in-kernel state word that holds chain c.  CPL = 28 leaves bit 7 of every byte
@@ -170,12 +211,139 @@ __device__ __forceinline__ uint32_t kernel_to_dense(uint32_t w)
 template <int CPL>
 struct SlotUnroll { static constexpr int value = CPL <= 8 ? 4 : 1; };
 
+// f[c] += j2 where bit bitpos(c) of w is set.  Written in PTX so that every bit -- bit 0 included, which the
+// C++ front end would canonicalise into a different test -- has the same and/setp/predicated-add shape and
+// ptxas folds seven tests into one R2P.
+template <int CPL, int C>
+__device__ __forceinline__ void add_slot_from(float (&f)[CPL], uint32_t w, float j2)
+{
+    if constexpr (C < CPL) {
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+            "and.b32 t, %2, %3;\n\t"
+            "setp.ne.s32 p, t, 0;\n\t"
+            "@p add.rn.f32 %0, %0, %1;\n\t}"
+            : "+f"(f[C])
+            : "f"(j2), "r"(w), "n"(1u << bitpos<CPL>(C)));
+        add_slot_from<CPL, C + 1>(f, w, j2);
+    }
+}
+
 template <int CPL>
 __device__ __forceinline__ void add_slot(float (&f)[CPL], uint32_t w, float j2)
 {
+    add_slot_from<CPL, 0>(f, w, j2);
+}
+
+template <int CPL, int C>
+__device__ __forceinline__ void init_slot_from(float (&f)[CPL], uint32_t w, float fz, float fa)
+{
+    if constexpr (C < CPL) {
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+            "and.b32 t, %3, %4;\n\t"
+            "setp.ne.s32 p, t, 0;\n\t"
+            "selp.f32 %0, %1, %2, p;\n\t}"
+            : "=f"(f[C])
+            : "f"(fa), "f"(fz), "r"(w), "n"(1u << bitpos<CPL>(C)));
+        init_slot_from<CPL, C + 1>(f, w, fz, fa);
+    }
+}
+
+// slot 0 doubles as the initialisation: f = f0 or f0 + 2J (one select instead of a move and an add)
+template <int CPL>
+__device__ __forceinline__ void init_slot(float (&f)[CPL], uint32_t w, float fz, float j2)
+{
+    init_slot_from<CPL, 0>(f, w, fz, __fadd_rn(fz, j2));
+}
+
+// state word at a byte offset from the start of dynamic shared memory (what the tables' .nbr field holds)
+__device__ __forceinline__ uint32_t lds_word(const unsigned char *smem, uint32_t byte_off)
+{
+    return *reinterpret_cast<const uint32_t *>(smem + byte_off);
+}
+
+// Cold paths: contract arithmetic for the decisions marked in `unsure` (usually one).  Out of line, fields
+// through local memory, and only the marked chains are redone: the warp that lands here is the straggler the
+// whole CTA waits for at the round barrier, so what matters is the latency of this path, not its size.
+template <int CPL, int SHIFT>
+__device__ __noinline__ uint32_t fix_word_philox(uint32_t neww, uint32_t unsure, const float *fl, float coef,
+                                                 uint32_t pp, uint32_t sweep, uint32_t blk8, const SweepParams &p)
+{
+    do {
+        const int c = 31 - __clz(unsure);
+        unsure &= ~(1u << c);
+        const int hidx = c + SHIFT;
+        uint32_t r[4], q[4];
+        philox4x32(pp, sweep, blk8 + (uint32_t)(hidx >> 3), B200GRBM_STREAM_SWEEP, p, r);
+        philox4x32(pp, sweep, blk8 + (uint32_t)(hidx >> 3), B200GRBM_STREAM_SWEEP_LO, p, q);
+        const int j = hidx & 7, sh = 16 * (j & 1);
+        const uint32_t wsel = (uint32_t)(j >> 1);
+        const uint32_t rw = wsel == 0 ? r[0] : wsel == 1 ? r[1] : wsel == 2 ? r[2] : r[3];
+        const uint32_t qw = wsel == 0 ? q[0] : wsel == 1 ? q[1] : wsel == 2 ? q[2] : q[3];
+        const float v = uniform_from_m23((((rw >> sh) & 0xffffu) << 7) | (((qw >> sh) & 0xffffu) >> 9));
+        const uint32_t bit = 1u << (CPL == 28 ? c + c / 7 : c);
+        neww = accept_exact(fl[c], coef, v) ? (neww | bit) : (neww & ~bit);
+    } while (unsure != 0);
+    return neww;
+}
+
+template <int CPL>
+__device__ __noinline__ uint32_t fix_word_supplied(uint32_t neww, uint32_t unsure, const float *fl, float coef,
+                                                   uint32_t pp, const SweepParams &p, int t, int chain0)
+{
+    do {
+        const int c = 31 - __clz(unsure);
+        unsure &= ~(1u << c);
+        const int cc = min(chain0 + c, p.chains - 1);
+        const float v = __ldg(p.uniforms + ((size_t)t * p.chains + cc) * p.n + pp);
+        const uint32_t bit = 1u << (CPL == 28 ? c + c / 7 : c);
+        neww = accept_exact(fl[c], coef, v) ? (neww | bit) : (neww & ~bit);
+    } while (unsure != 0);
+    return neww;
+}
+
+// Decisions of one lane-task: the new state word of visit position pp for the CPL chains of the group.
+// Chains are taken in descending order so that one funnel shift per decision (sign bit of d into bit 0)
+// assembles the word.  SHIFT = (first global chain of the group) mod 8, in {0, 4}: Philox blocks hold 8 chains.
+template <int CPL, int MODE, int SHIFT>
+__device__ __forceinline__ uint32_t decide_word(const float (&f)[CPL], float coef, uint32_t pp, uint32_t sweep,
+                                                uint32_t blk8, const SweepParams &p, int t, int chain0)
+{
+    constexpr int NC = (CPL + SHIFT + 7) / 8;
+    constexpr bool CHECK = MODE != MODE_PHILOX_FAST;
+    uint32_t neww = 0, unsure = 0;
+    if constexpr (MODE == MODE_SUPPLIED_EXACT) {
 #pragma unroll
-    for (int c = 0; c < CPL; ++c)
-        if (w & (1u << bitpos<CPL>(c))) f[c] = __fadd_rn(f[c], j2);
+        for (int c = CPL - 1; c >= 0; --c) {
+            const int cc = min(chain0 + c, p.chains - 1);
+            const float v = __ldg(p.uniforms + ((size_t)t * p.chains + cc) * p.n + pp);
+            if (CPL == 28 && (c + 1) % 7 == 0) neww <<= 1;
+            neww = __funnelshift_l(decide_quick<true>(f[c], coef, v, unsure), neww, 1);
+        }
+    } else {
+#pragma unroll
+        for (int call = NC - 1; call >= 0; --call) {
+            uint32_t r[4];
+            philox4x32(pp, sweep, blk8 + call, B200GRBM_STREAM_SWEEP, p, r);
+#pragma unroll
+            for (int j = 7; j >= 0; --j) {
+                const int c = 8 * call + j - SHIFT;
+                if (c < 0 || c >= CPL) continue;
+                if (CPL == 28 && (c + 1) % 7 == 0) neww <<= 1;
+                neww = __funnelshift_l(decide_quick<CHECK>(f[c], coef, uniform_midpoint(r, j), unsure), neww, 1);
+            }
+        }
+    }
+    if (CHECK && unsure != 0) {
+        // rare (about 6e-4 of the lane-tasks): a decision sits inside its bracket
+        float fl[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) fl[c] = f[c];
+        if constexpr (MODE == MODE_SUPPLIED_EXACT)
+            neww = fix_word_supplied<CPL>(neww, unsure, fl, coef, pp, p, t, chain0);
+        else
+            neww = fix_word_philox<CPL, SHIFT>(neww, unsure, fl, coef, pp, sweep, blk8, p);
+    }
+    return neww;
 }
 
 template <int CPL, int MODE>
@@ -193,7 +361,9 @@ __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ S
     const int chain0 = g * CPL;  // first chain of this group, local to the call
     const int nvalid = min(CPL, p.chains - chain0);
     const uint32_t dense_mask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
-    const uint32_t blk0 = p.chain_block0 + (uint32_t)(chain0 >> 2);
+    const uint32_t blk0 = p.chain_block0 + (uint32_t)(chain0 >> 2);   // global chain / 4 (initial-state stream)
+    const uint32_t blk8 = blk0 >> 1;                                   // global chain / 8 (sweep streams)
+    const bool shift4 = (blk0 & 1u) != 0;                              // group starts in the middle of a block of 8
     const uint32_t bar_addr = smem_u32(bars);
     const uint32_t stage_addr = smem_u32(stage0);
     const long long total_tiles = (long long)p.num_sweeps * p.n_tiles;
@@ -251,63 +421,54 @@ __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ S
         if (tid < info.y) {
             const int pp = info.x + tid;
             const uint32_t sweep = p.sweep_offset + (uint32_t)t;
-            // tile rows: 0 = f0, 1 .. width = neighbour slots
+            // tile rows: 0 = f0, 1 .. width = neighbour slots {2J bits, byte offset of the neighbour's state word}
             const uint2 *ep = reinterpret_cast<const uint2 *>(stage0 + s * p.tile_bytes) + tid;
             float f[CPL];
             const float fz = u2f(ep->x);
             ep += nthr;
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) f[c] = fz;
 
             if (SlotUnroll<CPL>::value == 4) {
-                // width is a multiple of 4 here (padding slots hold 2J = 0, nbr = 0)
+                // width is a multiple of 4 here (padding slots hold 2J = 0, nbr = own position)
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) f[c] = fz;
 #pragma unroll 1
                 for (int k = 0; k < p.width; k += 4) {
                     const uint2 e0 = ep[0], e1 = ep[nthr], e2 = ep[2 * nthr], e3 = ep[3 * nthr];
                     ep += 4 * nthr;
-                    const uint32_t w0 = W[e0.y], w1 = W[e1.y], w2 = W[e2.y], w3 = W[e3.y];
+                    const uint32_t w0 = lds_word(smem_raw, e0.y), w1 = lds_word(smem_raw, e1.y),
+                                   w2 = lds_word(smem_raw, e2.y), w3 = lds_word(smem_raw, e3.y);
                     add_slot<CPL>(f, w0, u2f(e0.x));
                     add_slot<CPL>(f, w1, u2f(e1.x));
                     add_slot<CPL>(f, w2, u2f(e2.x));
                     add_slot<CPL>(f, w3, u2f(e3.x));
                 }
             } else {
-                // software pipeline: entry / state word of slot k+1 are fetched while slot k's adds issue
-                uint2 e = *ep;
-                ep += nthr;
-                uint32_t w = W[e.y];
-#pragma unroll 1
-                for (int k = 1; k < p.width; ++k) {
-                    const uint2 en = *ep;
+                // slot 0 initialises, then two slots per iteration: both entries, then both state words, then
+                // 2 x CPL predicated adds.  No software pipeline across iterations -- the other warps of the
+                // scheduler cover the two shared-memory latencies, and a rotating pipeline costs register moves.
+                {
+                    const uint2 e0 = *ep;
                     ep += nthr;
-                    const uint32_t wn = W[en.y];
-                    add_slot<CPL>(f, w, u2f(e.x));
-                    e = en;
-                    w = wn;
+                    init_slot<CPL>(f, lds_word(smem_raw, e0.y), fz, u2f(e0.x));
                 }
-                add_slot<CPL>(f, w, u2f(e.x));
+                int k = 1;
+#pragma unroll 1
+                for (; k + 1 < p.width; k += 2) {
+                    const uint2 ea = ep[0], eb = ep[nthr];
+                    ep += 2 * nthr;
+                    const uint32_t wa = lds_word(smem_raw, ea.y), wb = lds_word(smem_raw, eb.y);
+                    add_slot<CPL>(f, wa, u2f(ea.x));
+                    add_slot<CPL>(f, wb, u2f(eb.x));
+                }
+                if (k < p.width) {
+                    const uint2 ea = *ep;
+                    add_slot<CPL>(f, lds_word(smem_raw, ea.y), u2f(ea.x));
+                }
             }
 
-            uint32_t neww = 0;
-#pragma unroll
-            for (int c4 = 0; c4 < CPL / 4; ++c4) {
-                uint32_t r[4];
-                if (MODE != MODE_SUPPLIED_EXACT)
-                    philox4x32((uint32_t)pp, sweep, blk0 + c4, B200GRBM_STREAM_SWEEP, p, r);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = 4 * c4 + j;
-                    float v;
-                    if (MODE == MODE_SUPPLIED_EXACT) {
-                        const int cc = min(chain0 + c, p.chains - 1);
-                        v = __ldg(p.uniforms + ((size_t)t * p.chains + cc) * p.n + pp);
-                    } else {
-                        v = uniform_from_bits(r[j]);
-                    }
-                    if (accept_plus<MODE == MODE_PHILOX_FAST>(f[c], coef, v)) neww |= 1u << bitpos<CPL>(c);
-                }
-            }
-            W[pp] = neww;   // bits of chains beyond nvalid are masked at write-back
+            W[pp] = shift4 ? decide_word<CPL, MODE, 4>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0)
+                           : decide_word<CPL, MODE, 0>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0);
+            // bits of chains beyond nvalid are masked at write-back
         }
         __syncthreads();
         if (++tile == p.n_tiles) {
@@ -362,6 +523,11 @@ static thread_local int32_t g_last_launches = 0;
 using namespace b200grbm;
 
 extern "C" int32_t b200grbm_last_launch_count(void) { return g_last_launches; }
+
+extern "C" int32_t b200grbm_sweep_state_offset(int32_t n_tiles)
+{
+    return 128 + (int32_t)(((int64_t)n_tiles * 8 + 127) / 128 * 128);
+}
 
 extern "C" int64_t b200grbm_sweep_smem_bytes(int32_t n, int32_t ell_width, int32_t threads, int32_t n_tiles)
 {

@@ -17,10 +17,11 @@ import torch.distributed as dist
 __all__ = ["shard_chains", "allreduce_statistics"]
 
 
-def shard_chains(total_chains: int, rank: int, world_size: int, align: int = 4) -> tuple[int, int]:
+def shard_chains(total_chains: int, rank: int, world_size: int, align: int = 8) -> tuple[int, int]:
     """Contiguous ``(offset, count)`` of global chain ids for ``rank``.  Offsets are multiples
-    of ``align`` (= 4: one Philox call feeds 4 consecutive chains, include/b200grbm_spec.h) so
-    every rank draws exactly the uniforms the single-GPU run would."""
+    of ``align`` (= 8: one Philox call feeds 8 consecutive chains, include/b200grbm_spec.h; the
+    kernel accepts any multiple of 4) so no Philox block is split between ranks and every rank
+    draws exactly the uniforms the single-GPU run would."""
     if not 0 <= rank < world_size:
         raise ValueError("rank out of range")
     blocks = -(-total_chains // align)

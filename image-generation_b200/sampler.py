@@ -26,7 +26,7 @@ from . import _lib
 from .topology import IsingGraph
 
 __all__ = ["BlockGibbsSampler", "PersistentChains", "SampleSet", "DeviceGraph", "plan_launch", "plan_threads",
-           "sweep_smem_bytes", "beta_schedule"]
+           "sweep_smem_bytes", "sweep_state_offset", "beta_schedule"]
 
 _LOG2E = 1.4426950408889634
 SUPPORTED_CPL = (4, 8, 16, 24, 28, 32)
@@ -51,6 +51,12 @@ def sweep_smem_bytes(n: int, ell_width: int, threads: int, n_tiles: int = 1) -> 
     """Dynamic shared memory of one sweep CTA: 2 mbarriers + round table + state words + 2 tile
     stages (mirrors b200grbm_sweep_smem_bytes, include/b200grbm.h)."""
     return 128 + (n_tiles * 8 + 127) // 128 * 128 + (n * 4 + 127) // 128 * 128 + 2 * (ell_width + 1) * threads * 8
+
+
+def sweep_state_offset(n_tiles: int) -> int:
+    """Byte offset of state word 0 in a sweep CTA's dynamic shared memory (mirrors
+    b200grbm_sweep_state_offset): the tiles' ``.nbr`` fields are this + 4 * visit position."""
+    return 128 + (n_tiles * 8 + 127) // 128 * 128
 
 
 def plan_threads(colour_sizes: Sequence[int], n: int, ell_width: int, smem_limit: int = SMEM_LIMIT) -> int:
@@ -190,9 +196,11 @@ class _TileSet:
         tiles = np.zeros((self.n_tiles, W + 1, T, 2), dtype=np.int32)
         p = np.arange(g.n)
         # padding slots (k >= degree, and the slot_pad filler) carry 2J = 0 and point at the lane's OWN
-        # position: the word read there is never written by another thread in the same round
+        # position: the word read there is never written by another thread in the same round.
+        # The field holds the byte offset of that state word in the CTA's shared memory (one LDS, no arithmetic).
+        base = sweep_state_offset(self.n_tiles)
         for k in range(W):
-            tiles[tile_of, 1 + k, lane_of, 1] = np.where(k < g.degree, g.ell_nbr[min(k, g.ell_width - 1), p], p)
+            tiles[tile_of, 1 + k, lane_of, 1] = base + 4 * np.where(k < g.degree, g.ell_nbr[min(k, g.ell_width - 1), p], p)
         ka, pa = np.divmod(g.slot_a.astype(np.int64), g.n_pad)
         kb, pb = np.divmod(g.slot_b.astype(np.int64), g.n_pad)
         i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B200GRBM_ABI_VERSION 1
+#define B200GRBM_ABI_VERSION 2
 
 #define B200GRBM_EINVAL (-1)   /* bad argument / shape */
 #define B200GRBM_EUNSUPPORTED (-2) /* configuration not compiled in (e.g. chains_per_lane) */
@@ -38,7 +38,7 @@ extern "C" {
 
 typedef struct b200grbm_ell_entry {
     uint32_t j2_bits; /* fp32 bits of 2*J_eff for this slot (0 for padding) */
-    uint32_t nbr;     /* neighbour visit position */
+    uint32_t nbr;     /* b200grbm_sweep_state_offset(n_tiles) + 4 * (neighbour visit position) */
 } b200grbm_ell_entry;
 
 const char *b200grbm_last_error(void);
@@ -51,7 +51,8 @@ int32_t b200grbm_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_m
  * Sampler tables ("tiles").  The sweep kernel streams, per colour round, one contiguous tile
  * of (1 + ell_width) x threads 8-byte entries through shared memory with the bulk-copy engine:
  *   tile[0][lane]                        : { fp32 bits of f0 = h_eff - sum_k J_eff, unused }
- *   tile[1 + k][lane]      k < ell_width : { fp32 bits of 2*J_eff, neighbour visit position }
+ *   tile[1 + k][lane]      k < ell_width : { fp32 bits of 2*J_eff, byte offset of the neighbour's state word
+ *                                            in the CTA's dynamic shared memory }
  * (ell_width = max degree, padded with zero slots to a multiple of 4 when chains_per_lane <= 8)
  * where lane = (visit position - first position of the round).  tile_info[t] = { first visit
  * position, number of spins } of round t; rounds never straddle a colour boundary.  The host
@@ -87,7 +88,7 @@ typedef struct b200grbm_sweep_args {
     int32_t chains_per_lane;   /* 4, 8, 16, 24, 28 or 32: chains bit-packed per state word */
     int32_t threads;           /* CTA size the tiles were built for, multiple of 32 in [64, 768] */
     int32_t accept;            /* B200GRBM_ACCEPT_* */
-    uint64_t chain_offset;     /* global id of chain 0 of this call (multiple of 4) */
+    uint64_t chain_offset;     /* global id of chain 0 of this call (multiple of 4; sharded runs use multiples of 8) */
     uint64_t seed;
     uint32_t sweep_offset;     /* Philox sweep counter of the first sweep */
     int32_t num_sweeps;
@@ -105,6 +106,10 @@ typedef struct b200grbm_sweep_args {
  * Runs num_sweeps colour-blocked heat-bath sweeps on `chains` independent chains.
  */
 int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *args, void *stream);
+
+/* byte offset of state word 0 inside a sweep CTA's dynamic shared memory (2 mbarriers + round table before it);
+ * the .nbr fields of the tiles are  this + 4 * position,  so a neighbour read is one LDS with no address arithmetic */
+int32_t b200grbm_sweep_state_offset(int32_t n_tiles);
 
 /* dynamic shared memory a sweep launch needs (round table + state + 2 tile stages); must fit the device's opt-in limit */
 int64_t b200grbm_sweep_smem_bytes(int32_t n, int32_t ell_width, int32_t threads, int32_t n_tiles);

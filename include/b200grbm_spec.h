@@ -32,11 +32,18 @@
  *
  * Uniforms: either supplied by the caller (float in (0,1)) or drawn from
  * Philox4x32-10 with
- *   key     = (seed_lo, seed_hi)
- *   counter = (visit position, sweep index, global chain id >> 2, stream)
- *   word    = global chain id & 3
- *   v       = as_float((bits >> 9) | 0x3f800000) - 1.0f + 2^-24   (exact)
- * stream 0 = sweep uniforms, stream 1 = initial state (bit 31 set -> +1).
+ *   key      = (seed_lo, seed_hi)
+ *   counter  = (visit position, sweep index, global chain id >> 3, stream)
+ *   halfword = global chain id & 7   (halfword j = bits 16 (j & 1) .. +15 of output word j >> 1)
+ *   m23      = (halfword of stream 0) << 7  |  (halfword of stream 2) >> 9
+ *   v        = as_float(m23 | 0x3f800000) - 1.0f + 2^-24   (exact; v in [2^-24, 1 - 2^-24])
+ * i.e. one Philox call carries the 16 high bits of the uniforms of 8 chains and a second
+ * stream carries the 7 low bits.  An implementation may decide from the high bits alone
+ * whenever the low bits cannot change the outcome (the sm_100a kernel does; the oracle
+ * always forms the full v) -- the contract is the decision with the full 23-bit v.
+ * stream 0 = sweep uniforms (high 16 bits), stream 2 = sweep uniforms (low 7 bits),
+ * stream 1 = initial state: counter = (visit position, 0, global chain id >> 2, 1),
+ *            word = global chain id & 3, bit 31 set -> +1.
  * The result therefore does not depend on launch geometry or GPU count.
  */
 #ifndef B200GRBM_SPEC_H
@@ -52,6 +59,7 @@
 
 #define B200GRBM_STREAM_SWEEP 0u
 #define B200GRBM_STREAM_INIT 1u
+#define B200GRBM_STREAM_SWEEP_LO 2u
 
 /* exp2 on [-0.5, 0.5], Remez fit of relative error, coefficients rounded to fp32 */
 #define B200GRBM_EXP2_C0 0x1.000002p+0f

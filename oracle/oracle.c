@@ -63,9 +63,10 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 static inline float as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline uint32_t as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
-float oracle_uniform_from_bits(uint32_t bits)
+/* v from the 23 mantissa bits m23 (spec header): as_float(m23 | 0x3f800000) - 1 + 2^-24, exact */
+float oracle_uniform_from_m23(uint32_t m23)
 {
-    float one_to_two = as_float((bits >> 9) | 0x3f800000u);
+    float one_to_two = as_float((m23 & 0x7fffffu) | 0x3f800000u);
     return (one_to_two - 1.0f) + B200GRBM_UNIFORM_HALF_ULP;
 }
 
@@ -92,16 +93,28 @@ int oracle_accept(float f, float coef, float v)
     return fmaf(v, e, v) < 1.0f;
 }
 
-static inline float draw_uniform(uint64_t seed, uint32_t pos, uint32_t sweep, uint64_t chain, uint32_t stream,
-                                 uint32_t *raw)
+static inline uint32_t halfword(const uint32_t out[4], unsigned j) { return (out[j >> 1] >> (16u * (j & 1u))) & 0xffffu; }
+
+/*
+ * Sweep uniforms of the 8 chains of block `blk8` (global chain id >> 3) at (pos, sweep):
+ * high 16 bits from stream 0, low 7 bits from stream 2 (spec header).
+ */
+void oracle_sweep_uniforms8(uint64_t seed, uint32_t pos, uint32_t sweep, uint32_t blk8, float v[8])
 {
-    uint32_t ctr[4] = { pos, sweep, (uint32_t)(chain >> 2), stream };
     uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
-    uint32_t out[4];
-    oracle_philox4x32_10(ctr, key, out);
-    uint32_t bits = out[chain & 3];
-    if (raw) *raw = bits;
-    return oracle_uniform_from_bits(bits);
+    uint32_t ctr[4] = { pos, sweep, blk8, B200GRBM_STREAM_SWEEP };
+    uint32_t hi[4], lo[4];
+    oracle_philox4x32_10(ctr, key, hi);
+    ctr[3] = B200GRBM_STREAM_SWEEP_LO;
+    oracle_philox4x32_10(ctr, key, lo);
+    for (unsigned j = 0; j < 8; ++j) v[j] = oracle_uniform_from_m23((halfword(hi, j) << 7) | (halfword(lo, j) >> 9));
+}
+
+float oracle_sweep_uniform(uint64_t seed, uint32_t pos, uint32_t sweep, uint64_t chain)
+{
+    float v[8];
+    oracle_sweep_uniforms8(seed, pos, sweep, (uint32_t)(chain >> 3), v);
+    return v[chain & 7];
 }
 
 /* Initial state from Philox stream 1: bit 31 of the chain's word set -> +1. */
@@ -110,9 +123,12 @@ void oracle_init_state(int n, int chains, int8_t *state, uint64_t seed, uint64_t
 #pragma omp parallel for schedule(static)
     for (int c = 0; c < chains; ++c) {
         for (int p = 0; p < n; ++p) {
-            uint32_t raw;
-            (void)draw_uniform(seed, (uint32_t)p, 0u, chain_offset + (uint64_t)c, B200GRBM_STREAM_INIT, &raw);
-            state[(size_t)c * n + p] = (raw >> 31) ? 1 : -1;
+            const uint64_t chain = chain_offset + (uint64_t)c;
+            uint32_t ctr[4] = { (uint32_t)p, 0u, (uint32_t)(chain >> 2), B200GRBM_STREAM_INIT };
+            uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+            uint32_t out[4];
+            oracle_philox4x32_10(ctr, key, out);
+            state[(size_t)c * n + p] = (out[chain & 3] >> 31) ? 1 : -1;
         }
     }
 }
@@ -134,19 +150,27 @@ void oracle_gibbs(int n, const int32_t *rowptr, const int32_t *col, const float 
         for (int k = rowptr[p]; k < rowptr[p + 1]; ++k) a = a - Jd[k];
         f0[p] = a;
     }
+    /* chains are walked in Philox blocks of 8 (global chain id >> 3) so that the two calls behind the
+     * uniforms of (position, sweep) are made once per block, as on the GPU */
+    const int64_t first_blk = (int64_t)(chain_offset >> 3), last_blk = (int64_t)((chain_offset + chains - 1) >> 3);
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int c = 0; c < chains; ++c) {
-        int8_t *s = state + (size_t)c * n;
+    for (int64_t b = first_blk; b <= last_blk; ++b) {
+        const int64_t g0 = b * 8 > (int64_t)chain_offset ? b * 8 : (int64_t)chain_offset;
+        const int64_t g1 = b * 8 + 8 < (int64_t)chain_offset + chains ? b * 8 + 8 : (int64_t)chain_offset + chains;
         for (int t = 0; t < num_sweeps; ++t) {
             const float cf = coef[t];
             for (int p = 0; p < n; ++p) {
-                float f = f0[p];
-                for (int k = rowptr[p]; k < rowptr[p + 1]; ++k)
-                    if (s[col[k]] > 0) f = f + 2.0f * Jd[k];
-                float v = uniforms ? uniforms[((size_t)t * chains + c) * n + p]
-                                   : draw_uniform(seed, (uint32_t)p, sweep_offset + (uint32_t)t,
-                                                  chain_offset + (uint64_t)c, B200GRBM_STREAM_SWEEP, NULL);
-                s[p] = oracle_accept(f, cf, v) ? 1 : -1;
+                float v8[8];
+                if (!uniforms) oracle_sweep_uniforms8(seed, (uint32_t)p, sweep_offset + (uint32_t)t, (uint32_t)b, v8);
+                for (int64_t gc = g0; gc < g1; ++gc) {
+                    const int64_t c = gc - (int64_t)chain_offset;
+                    int8_t *s = state + (size_t)c * n;
+                    float f = f0[p];
+                    for (int k = rowptr[p]; k < rowptr[p + 1]; ++k)
+                        if (s[col[k]] > 0) f = f + 2.0f * Jd[k];
+                    const float v = uniforms ? uniforms[((size_t)t * chains + c) * n + p] : v8[gc & 7];
+                    s[p] = oracle_accept(f, cf, v) ? 1 : -1;
+                }
             }
         }
     }
@@ -163,18 +187,24 @@ void oracle_gibbs_f64(int n, const int32_t *rowptr, const int32_t *col, const fl
                       int chains, int8_t *state, int num_sweeps, const double *beta, const float *uniforms,
                       uint64_t seed, uint64_t chain_offset, uint32_t sweep_offset)
 {
+    const int64_t first_blk = (int64_t)(chain_offset >> 3), last_blk = (int64_t)((chain_offset + chains - 1) >> 3);
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int c = 0; c < chains; ++c) {
-        int8_t *s = state + (size_t)c * n;
+    for (int64_t b = first_blk; b <= last_blk; ++b) {
+        const int64_t g0 = b * 8 > (int64_t)chain_offset ? b * 8 : (int64_t)chain_offset;
+        const int64_t g1 = b * 8 + 8 < (int64_t)chain_offset + chains ? b * 8 + 8 : (int64_t)chain_offset + chains;
         for (int t = 0; t < num_sweeps; ++t) {
             for (int p = 0; p < n; ++p) {
-                double f = (double)h[p];
-                for (int k = rowptr[p]; k < rowptr[p + 1]; ++k) f += (double)Jd[k] * (double)s[col[k]];
-                float v = uniforms ? uniforms[((size_t)t * chains + c) * n + p]
-                                   : draw_uniform(seed, (uint32_t)p, sweep_offset + (uint32_t)t,
-                                                  chain_offset + (uint64_t)c, B200GRBM_STREAM_SWEEP, NULL);
-                double pplus = 1.0 / (1.0 + exp(2.0 * beta[t] * f));
-                s[p] = ((double)v < pplus) ? 1 : -1;
+                float v8[8];
+                if (!uniforms) oracle_sweep_uniforms8(seed, (uint32_t)p, sweep_offset + (uint32_t)t, (uint32_t)b, v8);
+                for (int64_t gc = g0; gc < g1; ++gc) {
+                    const int64_t c = gc - (int64_t)chain_offset;
+                    int8_t *s = state + (size_t)c * n;
+                    double f = (double)h[p];
+                    for (int k = rowptr[p]; k < rowptr[p + 1]; ++k) f += (double)Jd[k] * (double)s[col[k]];
+                    const float v = uniforms ? uniforms[((size_t)t * chains + c) * n + p] : v8[gc & 7];
+                    const double pplus = 1.0 / (1.0 + exp(2.0 * beta[t] * f));
+                    s[p] = ((double)v < pplus) ? 1 : -1;
+                }
             }
         }
     }

@@ -39,8 +39,10 @@ def lib() -> C.CDLL:
     if _lib is None:
         build()
         _lib = C.CDLL(_LIB_PATH)
-        _lib.oracle_uniform_from_bits.restype = C.c_float
-        _lib.oracle_uniform_from_bits.argtypes = [C.c_uint32]
+        _lib.oracle_uniform_from_m23.restype = C.c_float
+        _lib.oracle_uniform_from_m23.argtypes = [C.c_uint32]
+        _lib.oracle_sweep_uniform.restype = C.c_float
+        _lib.oracle_sweep_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]
         _lib.oracle_exp2_poly.restype = C.c_float
         _lib.oracle_exp2_poly.argtypes = [C.c_float]
         _lib.oracle_accept.restype = C.c_int
@@ -61,8 +63,15 @@ def philox4x32_10(ctr: Sequence[int], key: Sequence[int]) -> list:
     return list(o)
 
 
-def uniform_from_bits(bits: int) -> float:
-    return float(lib().oracle_uniform_from_bits(C.c_uint32(bits)))
+def uniform_from_m23(m23: int) -> float:
+    """v = as_float(m23 | 0x3f800000) - 1 + 2^-24 for the 23 mantissa bits m23 (include/b200grbm_spec.h)."""
+    return float(lib().oracle_uniform_from_m23(C.c_uint32(m23)))
+
+
+def sweep_uniform(seed: int, pos: int, sweep: int, chain: int) -> float:
+    """The contract's sweep uniform of (visit position, sweep, global chain): high 16 bits from Philox
+    stream 0, low 7 bits from stream 2, blocks of 8 chains per call (include/b200grbm_spec.h)."""
+    return float(lib().oracle_sweep_uniform(C.c_uint64(seed), C.c_uint32(pos), C.c_uint32(sweep), C.c_uint64(chain)))
 
 
 def exp2_poly(x: float) -> float:

@@ -18,7 +18,7 @@ def test_shard_chains_partitions_exactly():
             assert sum(c for _, c in parts) == total
             pos = 0
             for off, cnt in parts:
-                assert off % 4 == 0                      # Philox blocks of 4 chains are never split
+                assert off % 8 == 0                      # Philox blocks of 8 chains are never split
                 if cnt:
                     assert off == pos
                     pos += cnt

@@ -75,6 +75,38 @@ def test_chain_offset_shards_reproduce_the_single_launch(cuda_device):
     assert np.array_equal(np.concatenate(parts), full.record.sample)
 
 
+@pytest.mark.parametrize("cpl,threads", [(4, 64), (8, 64), (16, 96), (24, 128), (28, 256), (32, 480)])
+def test_groups_that_start_inside_a_philox_block(cuda_device, cpl, threads):
+    """Sweep uniforms come in Philox blocks of 8 chains; a call whose first global chain is 4 mod 8 (and, for
+    28 chains per group, every other group) reads its halfwords shifted by four.  Also a colder schedule so
+    that large |x| reaches the bracket test's clamp."""
+    g = B.IsingGraph.pegasus(3)
+    h, J = _problem(g, 8, h_scale=0.5, j_scale=1.0)
+    chains, sweeps, seed, off = 90, 6, 0xABCDEF, 1004
+    csr = _oracle_csr(g)
+    beta = np.geomspace(0.2, 8.0, sweeps)
+    want = O.gibbs(csr, h, J, O.init_state(csr, chains, seed, chain_offset=off), beta, seed=seed, chain_offset=off)
+    s = B.BlockGibbsSampler(g, device=cuda_device, chain_offset=off)
+    s.device_graph.set_weights(torch.from_numpy(h), torch.from_numpy(J))
+    got = s._run(chains, None, None, None, beta, seed, None, None, plan=(cpl, threads)).record.sample
+    assert np.array_equal(got, want)
+
+
+def test_bracketed_decisions_fall_back_to_contract_arithmetic(cuda_device):
+    """The kernel decides from MUFU.EX2 and the 16 high bits of the uniform and re-evaluates a lane-task with
+    the contract polynomial and the full 23-bit uniform when a decision sits inside its error bracket
+    (about 2e-5 of the decisions).  3.7e7 decisions here -> several hundred fallbacks; every spin must still
+    equal the oracle, which always evaluates the contract."""
+    g = B.IsingGraph.pegasus(6)
+    h, J = _problem(g, 21)
+    chains, sweeps, seed = 1024, 50, 4242
+    csr = _oracle_csr(g)
+    want = O.gibbs(csr, h, J, O.init_state(csr, chains, seed), [1.0] * sweeps, seed=seed)
+    got = B.BlockGibbsSampler(g, device=cuda_device).sample_ising(h, J, num_reads=chains, num_sweeps=sweeps,
+                                                                 seed=seed).record.sample
+    assert np.array_equal(got, want)
+
+
 def test_checkpoint_graph_greedy_colouring_bit_exact(cuda_device, golden):
     z, meta = golden
     name = "Advantage2_system1_10_epochs"

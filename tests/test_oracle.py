@@ -22,10 +22,27 @@ def test_philox_known_answers(ctr, key, expect):
 
 
 def test_uniform_is_open_interval_and_exact():
-    assert O.uniform_from_bits(0) == 2.0 ** -24
-    assert O.uniform_from_bits(0xFFFFFFFF) == 1.0 - 2.0 ** -24
-    assert O.uniform_from_bits(1 << 9) == 2.0 ** -23 + 2.0 ** -24
-    assert O.uniform_from_bits(0x80000000) == 0.5 + 2.0 ** -24
+    assert O.uniform_from_m23(0) == 2.0 ** -24
+    assert O.uniform_from_m23(0x7FFFFF) == 1.0 - 2.0 ** -24
+    assert O.uniform_from_m23(1) == 2.0 ** -23 + 2.0 ** -24
+    assert O.uniform_from_m23(0x400000) == 0.5 + 2.0 ** -24
+
+
+def test_sweep_uniform_is_built_from_two_philox_streams():
+    """High 16 bits: halfword (chain & 7) of Philox(pos, sweep, chain >> 3, stream 0); low 7 bits: the top 7
+    bits of the same halfword of stream 2 (include/b200grbm_spec.h)."""
+    seed = 0x1234_5678_9ABC_DEF0
+    key = (seed & 0xFFFFFFFF, seed >> 32)
+    for pos, sweep, chain in [(0, 0, 0), (5, 3, 7), (5639, 999, 4095), (17, 2, 262143), (1, 1, 12)]:
+        hi = O.philox4x32_10((pos, sweep, chain >> 3, 0), key)
+        lo = O.philox4x32_10((pos, sweep, chain >> 3, 2), key)
+        j = chain & 7
+        hw = (hi[j >> 1] >> (16 * (j & 1))) & 0xFFFF
+        lw = (lo[j >> 1] >> (16 * (j & 1))) & 0xFFFF
+        m23 = (hw << 7) | (lw >> 9)
+        v = O.sweep_uniform(seed, pos, sweep, chain)
+        assert v == O.uniform_from_m23(m23) == (m23 + 0.5) * 2.0 ** -23
+        assert abs(v - (hw + 0.5) * 2.0 ** -16) < 2.0 ** -17      # the 16-bit midpoint brackets it
 
 
 def test_exp2_poly_accuracy_and_range():
@@ -115,8 +132,7 @@ def test_supplied_uniforms_equal_philox_when_identical():
     for t in range(sweeps):
         for c in range(chains):
             for p in range(n):
-                bits = O.philox4x32_10((p, t, c >> 2, 0), (seed, 0))[c & 3]
-                U[t, c, p] = O.uniform_from_bits(bits)
+                U[t, c, p] = O.sweep_uniform(seed, p, t, c)
     st0 = O.init_state(csr, chains, seed)
     a = O.gibbs(csr, h, J, st0, [1.0] * sweeps, seed=seed)
     b = O.gibbs(csr, h, J, st0, [1.0] * sweeps, uniforms=U)
