@@ -100,7 +100,7 @@ def cpu_port_rate(g, h, J, beta, target_seconds, threads=None):
     O.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = O.num_threads()
     csr = O.PositionCSR(g.n, g.edge_i, g.edge_j, g.order)
-    chains = 4 * cores
+    chains = 16 * cores            # the oracle threads over Philox blocks of 8 chains: two blocks per thread
     st = O.init_state(csr, chains, 1)
     t = time.perf_counter()
     O.gibbs(csr, h, J, st, [beta] * 4, seed=1, f64=True)                       # calibration pass
@@ -285,19 +285,20 @@ def run_b200(args):
         "bound": "smem", "kernel": "b200grbm::gibbs_kernel", "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
         "frac": achieved / smem_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one gibbs_kernel launch in the committed ncu --set full capture
-        # (profiles/r1_gibbs_v4_ncu_summary.txt; 20-sweep launch, the final state write mostly still sits in L2)
-        "traffic": 968704 + 153856, "traffic_note": "ncu capture of a 20-sweep launch; algorithmic HBM bytes per launch = state write 23.1 MB",
+        # (profiles/r1_gibbs_v5_ncu_summary.txt; 20-sweep launch, part of the final state write still sits in L2)
+        "traffic": 9082880 + 8229120, "traffic_note": "ncu capture of a 20-sweep launch; algorithmic HBM bytes per launch = state write 23.1 MB",
         "algorithmic_bytes_per_update": P16_MEAN_DEGREE + 1.0, "updates_per_launch": upd_per_launch,
         "kernel_ms": kernel_s * 1e3,
         "peak_source": f"SURVEY.md 8(d): n_SM({sms}) x 128 B/clk x SM clock sampled under load ({f_sm / 1e6:.0f} MHz)",
         "hbm": {"achieved": hbm_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": hbm_bytes / kernel_s / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
-        # the binding resource: warp-instruction issue.  56.6 warp instructions per 32 spin-updates is the count ncu
-        # reports for this kernel (smsp__inst_executed.sum / updates, profiles/r1_gibbs_v4_ncu_summary.txt)
-        "issue": {"warp_instr_per_32_updates": 56.6, "peak_updates_per_s": sms * 4 * 32 / 56.6 * f_sm,
-                  "frac": (upd_per_launch / kernel_s) / (sms * 4 * 32 / 56.6 * f_sm),
-                  "ncu_issue_active_frac": 0.77},
+        # the binding resource: warp-instruction issue.  41.7 warp instructions per 32 spin-updates is the count ncu
+        # reports for this kernel (smsp__inst_executed.sum / updates, profiles/r1_gibbs_v5_ncu_summary.txt;
+        # 56.6 before the lazy-acceptance kernel)
+        "issue": {"warp_instr_per_32_updates": 41.7, "peak_updates_per_s": sms * 4 * 32 / 41.7 * f_sm,
+                  "frac": (upd_per_launch / kernel_s) / (sms * 4 * 32 / 41.7 * f_sm),
+                  "ncu_issue_active_frac": 0.746},
         "note": "state is bit-packed (28 chains per word) so the kernel is issue-bound, not byte-bound; see DESIGN.md 5.1",
     }
     cpu_rate, cores, sample = cpu_port_rate(g, h, J, CFG["beta"], args.cpu_seconds)
@@ -318,9 +319,45 @@ def run_b200(args):
         "cpu_baseline": {"value": cpu_rate, "unit": "spin-updates/s", "cores": cores, "kind": "port", "sample": sample},
     }
     if not args.skip_extra:
+        line["sweep_variants"] = bench_sweep_variants(dev, g, h, J)
         line["mmd"] = bench_mmd(dev, peaks)
         line["dvae_step"] = bench_dvae_step(dev)
     print(json.dumps(line))
+
+
+def bench_sweep_variants(dev, g, h, J, iters=3):
+    """The sweep kernel off the headline configuration: fast (MUFU, 16-bit uniform) acceptance, an annealed
+    schedule on the same P16 problem, and the per-GPU shard of BASELINE.json configs[3] (Zephyr Z15, 32 768
+    chains, 100 sweeps).  Device-resident, CUDA events, no L2 flush (state and tables live in shared memory)."""
+    import torch
+
+    import image_generation_b200 as B
+
+    def timed(graph, hh, JJ, chains, sweeps, **kw):
+        s = B.BlockGibbsSampler(graph, device=dev, **kw)
+        s.device_graph.set_weights(torch.from_numpy(hh).to(dev), torch.from_numpy(JJ).to(dev))
+        out = (torch.empty((chains, graph.n), dtype=torch.int8, device=dev),
+               torch.empty(chains, dtype=torch.float64, device=dev))
+        s._run(chains, sweeps, None, None, None, None, None, None, out=out)
+        torch.cuda.synchronize(dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for a, b in ev:
+            a.record()
+            s._run(chains, sweeps, None, None, None, None, None, None, out=out)
+            b.record()
+        torch.cuda.synchronize(dev)
+        ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        return {"ms": ms, "spin_updates_per_s": chains * sweeps * graph.n / ms * 1e3, "chains": chains,
+                "sweeps": sweeps, "plan": list(s.last_plan)}
+
+    out = {"p16_fast_acceptance": timed(g, h, J, CFG["chains"], CFG["sweeps"], accept="fast"),
+           "p16_annealed_0.1_to_1": timed(g, h, J, CFG["chains"], CFG["sweeps"], beta_range=(0.1, 1.0))}
+    z = B.IsingGraph.zephyr(15)
+    rng = np.random.default_rng(15)
+    hz = (CFG["prefactor"] * rng.uniform(-0.05, 0.05, z.n)).astype(np.float32)
+    Jz = (CFG["prefactor"] * rng.uniform(-5.0, 5.0, z.n_edges)).astype(np.float32)
+    out["z15_shard_32768_chains"] = timed(z, hz, Jz, 32768, 100)
+    return out
 
 
 def bench_mmd(dev, peaks, m_each=8192, d=5640, iters=5):

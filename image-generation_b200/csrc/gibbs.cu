@@ -104,14 +104,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                            const SweepParams &p, uint32_t (&out)[4])
 {
+#ifdef B200_EXP_NOPHILOX     // timing experiment: a few integer ops instead of the generator
+    out[0] = c0 * 0x9E3779B9u ^ c1; out[1] = out[0] ^ (c2 << 3); out[2] = out[1] + c3; out[3] = out[2] ^ p.rk[0];
+    return;
+#endif
 #pragma unroll
     for (int r = 0; r < B200GRBM_PHILOX_ROUNDS; ++r) {
+#ifdef B200_EXP_MULHI        // timing experiment: separate high / low multiplies instead of one wide multiply
+        const uint32_t h0 = __umulhi(B200GRBM_PHILOX_M0, c0), l0 = B200GRBM_PHILOX_M0 * c0;
+        const uint32_t h1 = __umulhi(B200GRBM_PHILOX_M1, c2), l1 = B200GRBM_PHILOX_M1 * c2;
+        const uint32_t n0 = h1 ^ c1 ^ p.rk[2 * r];
+        const uint32_t n2 = h0 ^ c3 ^ p.rk[2 * r + 1];
+        c1 = l1;
+        c3 = l0;
+#else
         const uint64_t p0 = (uint64_t)B200GRBM_PHILOX_M0 * c0;
         const uint64_t p1 = (uint64_t)B200GRBM_PHILOX_M1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ p.rk[2 * r];
         const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ p.rk[2 * r + 1];
         c1 = (uint32_t)p1;
         c3 = (uint32_t)p0;
+#endif
         c0 = n0;
         c2 = n2;
     }
@@ -131,11 +144,11 @@ __device__ __forceinline__ uint32_t halfword(const uint32_t (&r)[4], int j)
 }
 
 // (hw + 0.5) * 2^-16 : midpoint of the 128 uniforms that share the 16 high bits hw.
-// PRMT builds as_float(2^23 + hw); one exact FMA maps it to the midpoint.
+// PRMT builds as_float(0x43000000 | hw) = 128 + hw 2^-16; one exact add maps it to the midpoint.
 __device__ __forceinline__ float uniform_midpoint(const uint32_t (&r)[4], int j)
 {
-    const uint32_t big = __byte_perm(r[j >> 1], 0x4B000000u, (j & 1) ? 0x7632u : 0x7610u);
-    return __fmaf_rn(u2f(big), 0x1.0p-16f, -(128.0f - 0x1.0p-17f));
+    const uint32_t big = __byte_perm(r[j >> 1], 0x43000000u, (j & 1) ? 0x7632u : 0x7610u);
+    return __fadd_rn(u2f(big), -(128.0f - 0x1.0p-17f));
 }
 
 // The contract's decision (include/b200grbm_spec.h): +1 iff fmaf(v, exp2_poly(clamp(f coef)), v) < 1.
@@ -165,10 +178,14 @@ __device__ __forceinline__ bool accept_exact(float f, float coef, float v)
 #define B200GRBM_LAZY_K1 0x1.004p-17f
 #define B200GRBM_LAZY_K2 0x1.0p-17f
 
+// x is NOT clamped here.  x > 128 gives e~ = g = d = +inf: sign clear = the contract's decision (its clamp at
+// 120 leaves e >= 2^120 > 1/v for every v >= 2^-24), and the mark m = (-inf) + inf is the canonical NaN
+// 0x7fffffff, sign clear = "sure".  x < -126 flushes e~ to 0, g = 1, d = vm - 1 < 0: also the contract's
+// decision.  One instruction less per decision on the ALU pipe, the busiest one in this phase.
 template <bool CHECK>
 __device__ __forceinline__ uint32_t decide_quick(float f, float coef, float vm, uint32_t &unsure)
 {
-    const float x = fminf(__fmul_rn(f, coef), B200GRBM_EXP2_CLAMP);   // upper clamp keeps 1 + e~ finite
+    const float x = __fmul_rn(f, coef);
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
     const float g = __fadd_rn(e, 1.0f);
@@ -346,8 +363,11 @@ __device__ __forceinline__ uint32_t decide_word(const float (&f)[CPL], float coe
     return neww;
 }
 
+#ifndef B200_SWEEP_MAX_THREADS
+#define B200_SWEEP_MAX_THREADS 768
+#endif
 template <int CPL, int MODE>
-__global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ SweepParams p)
+__global__ void __launch_bounds__(B200_SWEEP_MAX_THREADS, 1) gibbs_kernel(const __grid_constant__ SweepParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);                 // 2 mbarriers (16 B, padded to 128)
@@ -443,8 +463,8 @@ __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ S
                     add_slot<CPL>(f, w3, u2f(e3.x));
                 }
             } else {
-                // slot 0 initialises, then two slots per iteration: both entries, then both state words, then
-                // 2 x CPL predicated adds.  No software pipeline across iterations -- the other warps of the
+                // slot 0 initialises, then seven (or two) slots per iteration: the entries, then the state words,
+                // then 7 x CPL predicated adds.  No software pipeline across iterations -- the other warps of the
                 // scheduler cover the two shared-memory latencies, and a rotating pipeline costs register moves.
                 {
                     const uint2 e0 = *ep;
@@ -452,6 +472,23 @@ __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ S
                     init_slot<CPL>(f, lds_word(smem_raw, e0.y), fz, u2f(e0.x));
                 }
                 int k = 1;
+#ifdef B200_EXP_NOSLOTS      // timing experiment: acceptance phase only
+                k = p.width;
+#endif
+                const auto seven_slots = [&]() {
+                    uint2 e[7];
+                    uint32_t w[7];
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) e[i] = ep[i * nthr];
+                    ep += 7 * nthr;
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) w[i] = lds_word(smem_raw, e[i].y);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) add_slot<CPL>(f, w[i], u2f(e[i].x));
+                    k += 7;
+                };
+#pragma unroll 1
+                while (k + 7 <= p.width) seven_slots();       // Pegasus: 1 + 7 + 7 slots, Zephyr: 1 + 7 + 7 + 5
 #pragma unroll 1
                 for (; k + 1 < p.width; k += 2) {
                     const uint2 ea = ep[0], eb = ep[nthr];
@@ -466,11 +503,22 @@ __global__ void __launch_bounds__(768, 1) gibbs_kernel(const __grid_constant__ S
                 }
             }
 
+#ifdef B200_EXP_NOACCEPT      // timing experiment: neighbour loop only
+            {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) acc ^= f2u(f[c]);
+                W[pp] = acc & 0x7f7f7f7fu;
+            }
+#else
             W[pp] = shift4 ? decide_word<CPL, MODE, 4>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0)
                            : decide_word<CPL, MODE, 0>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0);
+#endif
             // bits of chains beyond nvalid are masked at write-back
         }
+#ifndef B200_EXP_NOBARRIER   // timing experiment only (tools/build_variant.sh): results are wrong without it
         __syncthreads();
+#endif
         if (++tile == p.n_tiles) {
             tile = 0;
             ++t;
