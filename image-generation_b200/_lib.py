@@ -75,6 +75,7 @@ SIGNATURES = {
     "b200grbm_energy_forward": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
     "b200grbm_energy_backward": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
     "b200grbm_energy_i8": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
+    "b200grbm_energy_packed": ([_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
     "b200grbm_mmd_forward_f32": ([_vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _vp], _i32),
     "b200grbm_mmd_pack_i8": ([_vp, _i32, _i32, _i32, _vp, _vp], _i32),
     "b200grbm_mmd_forward_i8": ([_vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _vp, _vp], _i32),

@@ -157,6 +157,72 @@ __global__ void energy_i8_kernel(const int8_t *__restrict__ s, int n, int n_edge
     if (threadIdx.x == 0) energy[blockIdx.x] = tot;
 }
 
+
+// Energies of the (<= 32) chains of one bit-packed group per CTA: E_c = sum_i h_i s_i + sum_e J_e s_i s_j
+// with s = +1 where the bit is set.  Per edge ONE pair of state words serves all chains of the group
+// (x = W[pi] ^ W[pj]: bit set <=> the two spins differ), so shared-memory traffic and the edge-list reads
+// are amortised 28-fold against the one-row-per-CTA int8 kernel above; accumulation in double:
+//   E_c = (sum_e J_e - 2 sum_{e: x_c = 1} J_e) + (2 sum_{i: bit_c = 1} h_i - sum_i h_i).
+__global__ void __launch_bounds__(512) energy_packed_kernel(const uint32_t *__restrict__ packed, int rows, int cpl, int n,
+                                                           int n_pad, int n_edges, const int32_t *__restrict__ edge_pi,
+                                                           const int32_t *__restrict__ edge_pj,
+                                                           const int32_t *__restrict__ order,
+                                                           const float *__restrict__ h, const float *__restrict__ j,
+                                                           double *__restrict__ energy)
+{
+    extern __shared__ uint32_t wrow[];
+    __shared__ double red[16][33];
+    const int g = blockIdx.x;
+    const uint32_t *row = packed + (size_t)g * n_pad;
+    for (int p = threadIdx.x; p < n; p += blockDim.x) wrow[p] = row[p];
+    __syncthreads();
+    double acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.0;
+    double base = 0.0;
+    for (int e = threadIdx.x; e < n_edges; e += blockDim.x) {
+        const double jd = (double)j[e];
+        const uint32_t x = wrow[edge_pi[e]] ^ wrow[edge_pj[e]];
+        base += jd;
+        const double m2 = -2.0 * jd;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (x & (1u << c)) acc[c] += m2;
+    }
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+        const double hd = (double)h[order[p]];
+        const uint32_t x = wrow[p];
+        base -= hd;
+        const double p2 = 2.0 * hd;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (x & (1u << c)) acc[c] += p2;
+    }
+    // block reduction: lanes first, then the warps through shared memory (column 32 = the common term)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        double v = acc[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][c] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+    if (lane == 0) red[warp][32] = base;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    if (threadIdx.x < 32) {
+        double v = 0.0, b = 0.0;
+        for (int w = 0; w < nw; ++w) {
+            v += red[w][threadIdx.x];
+            b += red[w][32];
+        }
+        const int r = g * cpl + threadIdx.x;
+        if (threadIdx.x < cpl && r < rows) energy[r] = v + b;
+    }
+}
+
 // thread per parameter, rows split over blockIdx.y; fp32 partial sums, one atomic per thread
 __global__ void energy_backward_kernel(const float *__restrict__ x, const float *__restrict__ g, int rows, int n,
                                        int n_edges, const int32_t *__restrict__ ei, const int32_t *__restrict__ ej,
@@ -302,6 +368,28 @@ extern "C" int32_t b200grbm_energy_i8(const int8_t *s_dev, int32_t rows, int32_t
     B200_CUDA(cudaFuncSetAttribute(energy_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     energy_i8_kernel<<<rows, 256, smem, (cudaStream_t)stream>>>(s_dev, n, n_edges, edge_i_dev, edge_j_dev, h_dev, j_dev,
                                                                 energy_dev);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int32_t b200grbm_energy_packed(const uint32_t *packed_dev, int32_t rows, int32_t chains_per_lane, int32_t n,
+                                          int32_t n_pad, int32_t n_edges, const int32_t *edge_pi_dev,
+                                          const int32_t *edge_pj_dev, const int32_t *order_dev, const float *h_dev,
+                                          const float *j_dev, double *energy_dev, void *stream)
+{
+    if (rows <= 0 || n <= 0 || n_edges < 0 || n_pad < n || chains_per_lane <= 0 || chains_per_lane > 32)
+        return fail(B200GRBM_EINVAL, "energy_packed: rows=%d n=%d n_pad=%d n_edges=%d chains_per_lane=%d", rows, n, n_pad,
+                    n_edges, chains_per_lane);
+    if (!packed_dev || !order_dev || !h_dev || !energy_dev || (n_edges > 0 && (!edge_pi_dev || !edge_pj_dev || !j_dev)))
+        return fail(B200GRBM_EINVAL, "energy_packed: NULL pointer argument");
+    B200_TRY(require_device());
+    const size_t smem = (size_t)n * 4;
+    if (smem > 160 * 1024) return fail(B200GRBM_EUNSUPPORTED, "energy_packed: n=%d too large for a shared-memory row", n);
+    B200_CUDA(cudaFuncSetAttribute(energy_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int groups = (rows + chains_per_lane - 1) / chains_per_lane;
+    energy_packed_kernel<<<groups, 512, smem, (cudaStream_t)stream>>>(packed_dev, rows, chains_per_lane, n, n_pad, n_edges,
+                                                                      edge_pi_dev, edge_pj_dev, order_dev, h_dev, j_dev,
+                                                                      energy_dev);
     B200_CUDA(cudaGetLastError());
     return 0;
 }

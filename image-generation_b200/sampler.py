@@ -325,6 +325,7 @@ class BlockGibbsSampler:
         self._edge_index: Optional[dict] = None
         self._coef_cache: dict = {}
         self._staging = None
+        self._packed_scratch: dict = {}
         self.last_launches = 0
         self.last_plan: tuple[int, int] = (0, 0)
 
@@ -487,13 +488,14 @@ class BlockGibbsSampler:
                 raise ValueError("initial_states must have shape (num_reads, n)")
             a.state_in_dev = _lib.ptr(init)
             keep.append(init)
+        packed = None
         if packed_io is not None:
             # persistent chains: resume from / write back to a caller-owned packed state
             if tuple(packed_io.shape) != (-(-num_reads // cpl), g.n_pad) or packed_io.dtype != torch.int32:
                 raise ValueError("packed_io must be int32 of shape (ceil(num_reads / chains_per_lane), n_pad)")
             if initial_states is None and resume:
                 a.packed_in_dev = _lib.ptr(packed_io)
-            a.packed_out_dev = _lib.ptr(packed_io)
+            packed = packed_io
         samples = None
         if want_int8:
             # `out` = caller-owned (samples int8 (reads, n), energies float64 (reads,)) buffers: no allocation per call
@@ -501,6 +503,16 @@ class BlockGibbsSampler:
             if tuple(samples.shape) != (num_reads, g.n) or samples.dtype != torch.int8 or not samples.is_contiguous():
                 raise ValueError("out[0] must be a contiguous int8 tensor of shape (num_reads, n)")
             a.state_out_dev = _lib.ptr(samples)
+            if packed is None:
+                # the sample energies are computed from the bit-packed copy of the final state (one pair of words
+                # per edge serves all chains of a group); the scratch buffer is kept per shape
+                key = (-(-num_reads // cpl), g.n_pad)
+                packed = self._packed_scratch.get(key)
+                if packed is None:
+                    self._packed_scratch.clear()
+                    packed = self._packed_scratch[key] = torch.empty(key, dtype=torch.int32, device=dev)
+        if packed is not None:
+            a.packed_out_dev = _lib.ptr(packed)
         lib = _lib.load()
         with torch.cuda.device(dev):
             _lib.check(lib.b200grbm_gibbs_sweeps(C.byref(a), _lib.current_stream(dev)))
@@ -508,9 +520,10 @@ class BlockGibbsSampler:
             energies = None
             if samples is not None:
                 energies = out[1] if out is not None else torch.empty(num_reads, dtype=torch.float64, device=dev)
-                _lib.check(lib.b200grbm_energy_i8(_lib.ptr(samples), num_reads, g.n, g.n_edges,
-                                                  _lib.ptr(dg.edge_i), _lib.ptr(dg.edge_j), _lib.ptr(dg.h_eff),
-                                                  _lib.ptr(dg.j_eff), _lib.ptr(energies), _lib.current_stream(dev)))
+                _lib.check(lib.b200grbm_energy_packed(_lib.ptr(packed), num_reads, cpl, g.n, g.n_pad, g.n_edges,
+                                                      _lib.ptr(dg.edge_pi), _lib.ptr(dg.edge_pj), _lib.ptr(dg.order),
+                                                      _lib.ptr(dg.h_eff), _lib.ptr(dg.j_eff), _lib.ptr(energies),
+                                                      _lib.current_stream(dev)))
                 self.last_launches += 1
         return SampleSet(self.variables, samples, energies,
                          info={"seed": int(seed), "chains_per_lane": cpl, "threads": threads,

@@ -154,6 +154,16 @@ int32_t b200grbm_energy_backward(const float *x_dev, const float *grad_energy_de
 int32_t b200grbm_energy_i8(const int8_t *s_dev, int32_t rows, int32_t n, int32_t n_edges,
                            const int32_t *edge_i_dev, const int32_t *edge_j_dev, const float *h_dev,
                            const float *j_dev, double *energy_dev, void *stream);
+/*
+ * The same energies from the sampler's bit-packed output (packed_out_dev of b200grbm_gibbs_sweeps:
+ * [groups][n_pad] words in visit-position order, bit c = chain c of the group): one CTA per group, one pair
+ * of state words per edge serves all chains_per_lane chains.  edge_pi/edge_pj = visit positions of the edge
+ * ends, order[p] = node at position p (h_dev is in node order), fp64 accumulation.
+ */
+int32_t b200grbm_energy_packed(const uint32_t *packed_dev, int32_t rows, int32_t chains_per_lane, int32_t n,
+                               int32_t n_pad, int32_t n_edges, const int32_t *edge_pi_dev,
+                               const int32_t *edge_pj_dev, const int32_t *order_dev, const float *h_dev,
+                               const float *j_dev, double *energy_dev, void *stream);
 
 /*
  * maximum_mean_discrepancy_loss(x, y, GaussianKernel(n_kernels)) -- third-party
