@@ -145,7 +145,7 @@ def run_b200(args):
 
     import image_generation_b200 as B
     from image_generation_b200.dist import allreduce_statistics
-    from image_generation_b200.stats import edge_statistics, pack_spins
+    from image_generation_b200.stats import sample_statistics
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -173,15 +173,13 @@ def run_b200(args):
     # caller-owned output buffers: the steady state allocates nothing (a cudaMalloc between the
     # start event and the launch would be charged to the kernel)
     out_bufs = (torch.empty((chains, g.n), dtype=torch.int8, device=dev), torch.empty(chains, dtype=torch.float64, device=dev))
-    packed_buf = [None]
 
     def step_device():
         ss = sampler._run(chains, sweeps, None, None, None, None, None, None, plan=plan, out=out_bufs)
         n_l = sampler.last_launches
-        packed_buf[0] = pack_spins(ss.samples_tensor, dg)
         sum_s.zero_(); sum_ss.zero_()
-        edge_statistics(packed_buf[0], chains, dg, out=(sum_s, sum_ss))
-        n_l += 3                                    # pack + edge + node statistics kernels
+        sample_statistics(ss, dg, out=(sum_s, sum_ss))
+        n_l += 2                                    # edge + node statistics kernels (on the sampler's packed state)
         if world > 1:
             a, b = allreduce_statistics([sum_s, sum_ss])
             sum_s.copy_(a); sum_ss.copy_(b)
@@ -213,14 +211,13 @@ def run_b200(args):
         ss = sampler._run(chains, sweeps, None, None, None, None, None, None, plan=plan, out=out_bufs)
         kev[k][1].record()
         n_l = sampler.last_launches
-        packed_buf[0] = pack_spins(ss.samples_tensor, dg)
         sum_s.zero_(); sum_ss.zero_()
-        edge_statistics(packed_buf[0], chains, dg, out=(sum_s, sum_ss))
+        sample_statistics(ss, dg, out=(sum_s, sum_ss))
         if world > 1:
             a, b = allreduce_statistics([sum_s, sum_ss])
             sum_s.copy_(a); sum_ss.copy_(b)
         ev[k][1].record()
-        launches["n"] += n_l + 3
+        launches["n"] += n_l + 2
     sync_all()
     t_wall1 = time.time()
     clk = clocks.stop(t_wall0, t_wall1)
@@ -333,7 +330,7 @@ def bench_sweep_variants(dev, g, h, J, iters=3):
 
     import image_generation_b200 as B
 
-    def timed(graph, hh, JJ, chains, sweeps, **kw):
+    def timed(graph, hh, JJ, chains, sweeps, stats=False, **kw):
         s = B.BlockGibbsSampler(graph, device=dev, **kw)
         s.device_graph.set_weights(torch.from_numpy(hh).to(dev), torch.from_numpy(JJ).to(dev))
         out = (torch.empty((chains, graph.n), dtype=torch.int8, device=dev),
@@ -347,8 +344,30 @@ def bench_sweep_variants(dev, g, h, J, iters=3):
             b.record()
         torch.cuda.synchronize(dev)
         ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-        return {"ms": ms, "spin_updates_per_s": chains * sweeps * graph.n / ms * 1e3, "chains": chains,
-                "sweeps": sweeps, "plan": list(s.last_plan)}
+        res = {"ms": ms, "spin_updates_per_s": chains * sweeps * graph.n / ms * 1e3, "chains": chains,
+               "sweeps": sweeps, "plan": list(s.last_plan)}
+        if stats:
+            # integer statistics (sum s_i, sum s_i s_j) straight from the sampler's packed final state
+            from image_generation_b200.stats import sample_statistics
+            ss = s._run(chains, 1, None, None, None, None, None, None, out=out)
+            bufs = (torch.zeros(graph.n, dtype=torch.int64, device=dev),
+                    torch.zeros(graph.n_edges, dtype=torch.int64, device=dev))
+            sample_statistics(ss, s.device_graph, out=bufs)
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                sample_statistics(ss, s.device_graph, out=bufs)
+            b.record()
+            torch.cuda.synchronize(dev)
+            st_ms = a.elapsed_time(b) / 10
+            packed_bytes = ss.packed.numel() * 4
+            res["statistics"] = {"ms": st_ms, "packed_state_bytes": packed_bytes,
+                                 "int8_state_bytes": chains * graph.n,
+                                 "packed_GBps": packed_bytes / st_ms / 1e6,
+                                 "note": "edge + node statistics kernels over the bit-packed state (N/8 bytes per "
+                                         "chain instead of the N bytes of SURVEY 8(d)'s stand-alone int8 form)"}
+        return res
 
     out = {"p16_fast_acceptance": timed(g, h, J, CFG["chains"], CFG["sweeps"], accept="fast"),
            "p16_annealed_0.1_to_1": timed(g, h, J, CFG["chains"], CFG["sweeps"], beta_range=(0.1, 1.0))}
@@ -356,7 +375,7 @@ def bench_sweep_variants(dev, g, h, J, iters=3):
     rng = np.random.default_rng(15)
     hz = (CFG["prefactor"] * rng.uniform(-0.05, 0.05, z.n)).astype(np.float32)
     Jz = (CFG["prefactor"] * rng.uniform(-5.0, 5.0, z.n_edges)).astype(np.float32)
-    out["z15_shard_32768_chains"] = timed(z, hz, Jz, 32768, 100)
+    out["z15_shard_32768_chains"] = timed(z, hz, Jz, 32768, 100, stats=True)
     return out
 
 

@@ -12,7 +12,7 @@ from typing import Sequence
 import torch
 
 from .grbm import GraphRestrictedBoltzmannMachine
-from .stats import SufficientStatistics, edge_statistics, pack_spins
+from .stats import SufficientStatistics, edge_statistics, pack_spins, sample_statistics
 
 __all__ = ["nll_loss", "PersistentQPUSampleHelper"]
 
@@ -65,7 +65,10 @@ def nll_loss(spins: torch.Tensor, grbm: GraphRestrictedBoltzmannMachine, sampler
     src = getattr(sample_set, "samples_tensor", None)
     model_rows = src if src is not None and src.device == spins.device else samples
     d_s, d_ss = edge_statistics(pack_spins(spins, dg), spins.shape[0], dg)
-    m_s, m_ss = edge_statistics(pack_spins(model_rows, dg), model_rows.shape[0], dg)
+    if getattr(sample_set, "packed", None) is not None and src is not None and src.device == spins.device:
+        m_s, m_ss = sample_statistics(sample_set, dg)          # straight from the sampler's packed state
+    else:
+        m_s, m_ss = edge_statistics(pack_spins(model_rows, dg), model_rows.shape[0], dg)
     counts = torch.tensor([spins.shape[0], model_rows.shape[0]], dtype=torch.int64, device=spins.device)
     # process_group: None -> the default group when torch.distributed is initialised; False -> never reduce
     if process_group is not False and torch.distributed.is_available() and torch.distributed.is_initialized():

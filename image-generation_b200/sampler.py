@@ -149,12 +149,25 @@ class SampleSet:
     vartype = "SPIN"
 
     def __init__(self, variables: Sequence, samples: Optional[torch.Tensor] = None,
-                 energies: Optional[torch.Tensor] = None, record: Optional[_Record] = None, info: Optional[dict] = None):
+                 energies: Optional[torch.Tensor] = None, record: Optional[_Record] = None, info: Optional[dict] = None,
+                 packed: Optional[torch.Tensor] = None, packed_is_current=None):
         self.variables = list(variables)
         self.samples_tensor = samples      # int8 (reads, n), node order, on the sampling device
         self.energies_tensor = energies    # float64 (reads,)
         self._record = record
         self.info = info or {}
+        self._packed = packed              # the sampler's bit-packed copy of the same states (scratch, reused per call)
+        self._packed_is_current = packed_is_current
+
+    @property
+    def packed(self) -> Optional[torch.Tensor]:
+        """``(groups, n_pad)`` int32 words of the final states (visit-position order, bit c = chain c of a
+        group of ``info["chains_per_lane"]``) while they are still the sampler's latest output; ``None`` once
+        the sampler has been called again (the buffer is reused).  Lets the integer statistics skip the
+        re-read and re-pack of the int8 samples."""
+        if self._packed is None or (self._packed_is_current is not None and not self._packed_is_current()):
+            return None
+        return self._packed
 
     @property
     def record(self) -> _Record:
@@ -326,6 +339,7 @@ class BlockGibbsSampler:
         self._coef_cache: dict = {}
         self._staging = None
         self._packed_scratch: dict = {}
+        self._generation = 0
         self.last_launches = 0
         self.last_plan: tuple[int, int] = (0, 0)
 
@@ -525,9 +539,12 @@ class BlockGibbsSampler:
                                                       _lib.ptr(dg.h_eff), _lib.ptr(dg.j_eff), _lib.ptr(energies),
                                                       _lib.current_stream(dev)))
                 self.last_launches += 1
+        self._generation += 1
+        gen = self._generation
         return SampleSet(self.variables, samples, energies,
                          info={"seed": int(seed), "chains_per_lane": cpl, "threads": threads,
-                               "num_sweeps": num_sweeps, "accept": self.accept})
+                               "num_sweeps": num_sweeps, "accept": self.accept},
+                         packed=packed, packed_is_current=lambda: self._generation == gen)
 
 
 class PersistentChains:

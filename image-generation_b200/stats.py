@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from .sampler import DeviceGraph
 
-__all__ = ["pack_spins", "edge_statistics", "SufficientStatistics"]
+__all__ = ["pack_spins", "edge_statistics", "sample_statistics", "SufficientStatistics"]
 
 
 def pack_spins(x: torch.Tensor, dg: DeviceGraph, chains_per_lane: int = 32) -> torch.Tensor:
@@ -61,6 +61,20 @@ def edge_statistics(packed: torch.Tensor, rows: int, dg: DeviceGraph, chains_per
             _lib.ptr(dg.order), _lib.ptr(sum_s), _lib.ptr(sum_ss) if g.n_edges else None,
             _lib.current_stream(packed.device)))
     return sum_s, sum_ss
+
+
+def sample_statistics(sample_set, dg: DeviceGraph, out: Optional[tuple] = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """Integer statistics of a sampler's :class:`SampleSet`.  While the set is the sampler's latest output its
+    bit-packed copy is used directly (no second pass over the int8 samples in HBM -- the statistics kernel
+    reads N / 8 bytes per chain instead of N); otherwise the int8 samples are packed first."""
+    rows = len(sample_set)
+    packed = getattr(sample_set, "packed", None)
+    if packed is not None and packed.device == dg.device:
+        return edge_statistics(packed, rows, dg, int(sample_set.info["chains_per_lane"]), out=out)
+    samples = sample_set.samples_tensor
+    if samples is None:
+        samples = torch.from_numpy(sample_set.record.sample)
+    return edge_statistics(pack_spins(samples.to(dg.device), dg), rows, dg, out=out)
 
 
 class SufficientStatistics(torch.autograd.Function):

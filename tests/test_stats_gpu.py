@@ -6,7 +6,7 @@ import torch
 
 import image_generation_b200 as B
 from image_generation_b200.losses import PersistentQPUSampleHelper, nll_loss
-from image_generation_b200.stats import edge_statistics, pack_spins
+from image_generation_b200.stats import edge_statistics, pack_spins, sample_statistics
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -51,6 +51,31 @@ def test_pack_and_integer_statistics_bit_exact(cuda_device, rows, cpl):
     # accumulation (+=): a second call doubles the counters -- checksum-of-checksums property
     got_s2, got_ss2 = edge_statistics(packed, rows, dg, cpl, out=(got_s, got_ss))
     assert np.array_equal(got_s2.cpu().numpy(), 2 * want_s)
+
+
+@pytest.mark.parametrize("reads", [5, 100, 300])
+def test_statistics_and_energies_from_the_samplers_packed_state(cuda_device, reads):
+    """The sampler hands its bit-packed final state to the statistics (no second pass over the int8 samples) and
+    computes record.energy from it; both must equal the oracle's values of the int8 samples, and the packed view
+    must retire once the sampler is called again (the buffer is reused)."""
+    g = B.IsingGraph.zephyr(3)
+    rng = np.random.default_rng(reads)
+    h = rng.uniform(-0.4, 0.4, g.n).astype(np.float32)
+    J = rng.uniform(-0.5, 0.5, g.n_edges).astype(np.float32)
+    s = B.BlockGibbsSampler(g, device=cuda_device)
+    ss = s.sample_ising(h, J, num_reads=reads, num_sweeps=7, seed=reads)
+    assert ss.packed is not None and ss.packed.shape[0] == -(-reads // ss.info["chains_per_lane"])
+    got_s, got_ss = sample_statistics(ss, s.device_graph)
+    samples = ss.record.sample
+    want_s, want_ss = O.edge_stats(g.n, g.edge_i, g.edge_j, samples)
+    assert np.array_equal(got_s.cpu().numpy(), want_s)
+    assert np.array_equal(got_ss.cpu().numpy()[: g.n_edges], want_ss)
+    np.testing.assert_allclose(ss.record.energy, O.energies(g.n, g.edge_i, g.edge_j, h, J, samples), rtol=1e-12, atol=1e-9)
+    ss2 = s.sample_ising(h, J, num_reads=reads, num_sweeps=1, seed=1)
+    assert ss.packed is None and ss2.packed is not None            # the first set's packed view has retired
+    got_s, got_ss = sample_statistics(ss, s.device_graph)          # falls back to packing the int8 samples
+    assert np.array_equal(got_s.cpu().numpy(), want_s)
+    assert np.array_equal(got_ss.cpu().numpy()[: g.n_edges], want_ss)
 
 
 def test_energy_forward_backward_match_oracle(cuda_device):
