@@ -60,6 +60,7 @@ struct SweepParams {
     uint32_t info_bytes;    // shared-memory bytes reserved for the round table (multiple of 128)
     uint32_t state_bytes;   // shared-memory bytes reserved for W (multiple of 128)
     uint32_t tile_bytes;    // (width + 1) * threads * 8
+    uint32_t resident;      // 1: all n_tiles tiles fit in shared memory and are copied once (small graphs)
     uint32_t rk[2 * B200GRBM_PHILOX_ROUNDS];
 };
 
@@ -321,11 +322,16 @@ __device__ __noinline__ uint32_t fix_word_supplied(uint32_t neww, uint32_t unsur
 // Decisions of one lane-task: the new state word of visit position pp for the CPL chains of the group.
 // Chains are taken in descending order so that one funnel shift per decision (sign bit of d into bit 0)
 // assembles the word.  SHIFT = (first global chain of the group) mod 8, in {0, 4}: Philox blocks hold 8 chains.
-template <int CPL, int MODE, int SHIFT>
+//
+// PRE (small groups, latency-bound): the Philox words were drawn by the caller before the neighbour loop and
+// arrive in R[call][word].
+template <int CPL, int MODE, int SHIFT, bool PRE>
 __device__ __forceinline__ uint32_t decide_word(const float (&f)[CPL], float coef, uint32_t pp, uint32_t sweep,
-                                                uint32_t blk8, const SweepParams &p, int t, int chain0)
+                                                uint32_t blk8, const SweepParams &p, int t, int chain0,
+                                                const uint32_t (&R)[2][4])
 {
     constexpr int NC = (CPL + SHIFT + 7) / 8;
+    static_assert(!PRE || NC <= 2, "pre-drawn Philox words: at most two calls per lane-task");
     constexpr bool CHECK = MODE != MODE_PHILOX_FAST;
     uint32_t neww = 0, unsure = 0;
     if constexpr (MODE == MODE_SUPPLIED_EXACT) {
@@ -340,7 +346,12 @@ __device__ __forceinline__ uint32_t decide_word(const float (&f)[CPL], float coe
 #pragma unroll
         for (int call = NC - 1; call >= 0; --call) {
             uint32_t r[4];
-            philox4x32(pp, sweep, blk8 + call, B200GRBM_STREAM_SWEEP, p, r);
+            if constexpr (PRE) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r[i] = R[call][i];
+            } else {
+                philox4x32(pp, sweep, blk8 + call, B200GRBM_STREAM_SWEEP, p, r);
+            }
 #pragma unroll
             for (int j = 7; j >= 0; --j) {
                 const int c = 8 * call + j - SHIFT;
@@ -392,7 +403,12 @@ __global__ void __launch_bounds__(B200_SWEEP_MAX_THREADS, 1) gibbs_kernel(const 
         mbar_init(bar_addr, 1);
         mbar_init(bar_addr + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (total_tiles > 0) {   // prologue: round 0 into stage 0
+        if (total_tiles > 0 && p.resident) {   // small graph: every round's tile, once
+            mbar_expect_tx(bar_addr, p.tile_bytes * (uint32_t)p.n_tiles);
+            for (int k = 0; k < p.n_tiles; ++k)
+                bulk_g2s(stage_addr + (uint32_t)k * p.tile_bytes,
+                         reinterpret_cast<const unsigned char *>(p.tiles) + (size_t)k * p.tile_bytes, p.tile_bytes, bar_addr);
+        } else if (total_tiles > 0) {          // prologue: round 0 into stage 0
             mbar_expect_tx(bar_addr, p.tile_bytes);
             bulk_g2s(stage_addr, p.tiles, p.tile_bytes, bar_addr);
         }
@@ -428,7 +444,7 @@ __global__ void __launch_bounds__(B200_SWEEP_MAX_THREADS, 1) gibbs_kernel(const 
         const uint32_t s = (uint32_t)q & 1u;
         // stage s^1 was last read in round q-1, which every thread left through the
         // __syncthreads() below -> safe to refill it now while round q computes
-        if (tid == 0 && q + 1 < total_tiles) {
+        if (tid == 0 && q + 1 < total_tiles && !p.resident) {
             const int next_tile = tile + 1 == p.n_tiles ? 0 : tile + 1;
             const uint32_t nb = bar_addr + 8u * (s ^ 1u);
             mbar_expect_tx(nb, p.tile_bytes);
@@ -436,25 +452,50 @@ __global__ void __launch_bounds__(B200_SWEEP_MAX_THREADS, 1) gibbs_kernel(const 
                      reinterpret_cast<const unsigned char *>(p.tiles) + (size_t)next_tile * p.tile_bytes, p.tile_bytes, nb);
         }
         const int2 info = tinfo[tile];
-        mbar_wait(bar_addr + 8u * s, (uint32_t)(q >> 1) & 1u);
+        // resident tables: one wait, before the first round (a copy round trip per round would otherwise be the
+        // critical path of the short rounds of a small graph)
+        if (!p.resident) mbar_wait(bar_addr + 8u * s, (uint32_t)(q >> 1) & 1u);
+        else if (q == 0) mbar_wait(bar_addr, 0u);
+        const uint32_t stage_idx = p.resident ? (uint32_t)tile : s;
 
         if (tid < info.y) {
             const int pp = info.x + tid;
             const uint32_t sweep = p.sweep_offset + (uint32_t)t;
             // tile rows: 0 = f0, 1 .. width = neighbour slots {2J bits, byte offset of the neighbour's state word}
-            const uint2 *ep = reinterpret_cast<const uint2 *>(stage0 + s * p.tile_bytes) + tid;
+            const uint2 *ep = reinterpret_cast<const uint2 *>(stage0 + stage_idx * p.tile_bytes) + tid;
             float f[CPL];
             const float fz = u2f(ep->x);
             ep += nthr;
 
+            // Small groups (few chains spread over many CTAs, e.g. the reference's 256 reads) are latency-bound: a
+            // round is one dependent chain  table entry -> state word -> adds -> Philox -> decision -> barrier.
+            // The Philox words do not depend on the state, so they are drawn first; the slots are fetched eight
+            // at a time (two shared-memory latencies per eight slots).
+            constexpr bool PRE = SlotUnroll<CPL>::value == 4 && MODE != MODE_SUPPLIED_EXACT;
+            uint32_t R[2][4];
+            if constexpr (PRE) {
+                philox4x32((uint32_t)pp, sweep, blk8, B200GRBM_STREAM_SWEEP, p, R[0]);
+                if ((CPL + 4 + 7) / 8 > 1 && shift4) philox4x32((uint32_t)pp, sweep, blk8 + 1, B200GRBM_STREAM_SWEEP, p, R[1]);
+            }
             if (SlotUnroll<CPL>::value == 4) {
                 // width is a multiple of 4 here (padding slots hold 2J = 0, nbr = own position)
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) f[c] = fz;
+                int k = 0;
 #pragma unroll 1
-                for (int k = 0; k < p.width; k += 4) {
+                for (; k + 8 <= p.width; k += 8) {
+                    uint2 e[8];
+                    uint32_t w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) e[i] = ep[i * nthr];
+                    ep += 8 * nthr;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w[i] = lds_word(smem_raw, e[i].y);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) add_slot<CPL>(f, w[i], u2f(e[i].x));
+                }
+                if (k < p.width) {
                     const uint2 e0 = ep[0], e1 = ep[nthr], e2 = ep[2 * nthr], e3 = ep[3 * nthr];
-                    ep += 4 * nthr;
                     const uint32_t w0 = lds_word(smem_raw, e0.y), w1 = lds_word(smem_raw, e1.y),
                                    w2 = lds_word(smem_raw, e2.y), w3 = lds_word(smem_raw, e3.y);
                     add_slot<CPL>(f, w0, u2f(e0.x));
@@ -511,8 +552,8 @@ __global__ void __launch_bounds__(B200_SWEEP_MAX_THREADS, 1) gibbs_kernel(const 
                 W[pp] = acc & 0x7f7f7f7fu;
             }
 #else
-            W[pp] = shift4 ? decide_word<CPL, MODE, 4>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0)
-                           : decide_word<CPL, MODE, 0>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0);
+            W[pp] = shift4 ? decide_word<CPL, MODE, 4, PRE>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R)
+                           : decide_word<CPL, MODE, 0, PRE>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R);
 #endif
             // bits of chains beyond nvalid are masked at write-back
         }
@@ -650,10 +691,15 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
         k1 += B200GRBM_PHILOX_W1;
     }
 
-    const size_t smem = (size_t)b200grbm_sweep_smem_bytes(a->n, a->ell_width, a->threads, a->n_tiles);
+    size_t smem = (size_t)b200grbm_sweep_smem_bytes(a->n, a->ell_width, a->threads, a->n_tiles);
     int dev = 0, smem_optin = 0;
     B200_CUDA(cudaGetDevice(&dev));
     B200_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    // small graphs: keep every round's tile resident instead of streaming through the 2-stage ring
+    const size_t smem_resident = smem + (size_t)(a->n_tiles > 2 ? a->n_tiles - 2 : 0) * p.tile_bytes;
+    p.resident = (a->n_tiles <= 2 || (smem_resident <= (size_t)smem_optin &&
+                                      (size_t)a->n_tiles * p.tile_bytes < (1u << 20))) ? 1u : 0u;
+    if (p.resident) smem = smem_resident;
     if (smem > (size_t)smem_optin)
         return fail(B200GRBM_EUNSUPPORTED,
                     "gibbs_sweeps: n=%d width=%d threads=%d need %zu B of shared memory (> %d); use fewer threads",

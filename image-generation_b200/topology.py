@@ -151,10 +151,18 @@ def _adjacency(n: int, ei: np.ndarray, ej: np.ndarray):
     return adj
 
 
-def greedy_colouring(n: int, ei: np.ndarray, ej: np.ndarray) -> np.ndarray:
-    """Smallest-last greedy colouring (4-5 colours on the reference's 256-node QPU
-    sub-graphs).  Used for graphs without a closed-form colouring."""
-    adj = _adjacency(n, ei, ej)
+def _greedy_in_order(adj, order, n: int) -> np.ndarray:
+    colour = -np.ones(n, dtype=np.int32)
+    for v in order:
+        used = {int(colour[u]) for u in adj[v] if colour[u] >= 0}
+        c = 0
+        while c in used:
+            c += 1
+        colour[v] = c
+    return colour
+
+
+def _smallest_last_order(adj, n: int) -> list:
     deg = [len(a) for a in adj]
     removed = [False] * n
     buckets: dict[int, set] = {}
@@ -163,7 +171,8 @@ def greedy_colouring(n: int, ei: np.ndarray, ej: np.ndarray) -> np.ndarray:
     order = []
     for _ in range(n):
         d = min(k for k, s in buckets.items() if s)
-        v = buckets[d].pop()
+        v = min(buckets[d])            # deterministic choice inside a bucket
+        buckets[d].discard(v)
         removed[v] = True
         order.append(v)
         for u in adj[v]:
@@ -171,14 +180,46 @@ def greedy_colouring(n: int, ei: np.ndarray, ej: np.ndarray) -> np.ndarray:
                 buckets[deg[u]].discard(u)
                 deg[u] -= 1
                 buckets.setdefault(deg[u], set()).add(u)
-    colour = -np.ones(n, dtype=np.int32)
-    for v in reversed(order):
-        used = {int(colour[u]) for u in adj[v] if colour[u] >= 0}
-        c = 0
-        while c in used:
-            c += 1
-        colour[v] = c
-    return colour
+    order.reverse()
+    return order
+
+
+def greedy_colouring(n: int, ei: np.ndarray, ej: np.ndarray, refine: Optional[int] = None) -> np.ndarray:
+    """Proper colouring for graphs without a closed form: smallest-last greedy, then *iterated greedy*
+    (Culberson): re-colour greedily with the vertices grouped by their current colour class, classes taken in
+    a new order -- the number of colours never grows and usually shrinks.  Every colour is one barrier-separated
+    round of the sweep kernel, so on the reference's 256-spin QPU sub-graphs a colour less is ~1/5 less latency
+    per sweep (the Advantage2 sub-graph goes from 6 classes, one of them 4 spins, to 4-5).  Deterministic
+    (fixed-seed permutations); ``refine`` = number of re-colouring passes (default scales down with size)."""
+    adj = _adjacency(n, ei, ej)
+    best = _greedy_in_order(adj, _smallest_last_order(adj, n), n)
+    if n == 0:
+        return best
+    if refine is None:
+        refine = int(min(200, max(0, 400_000 // (n + 2 * len(ei) + 1))))
+    rng = np.random.default_rng(0x6C6F7572)
+
+    def score(col):
+        counts = np.bincount(col)
+        return (len(counts), int(counts.max()) - int(counts.min()))
+
+    cur = best
+    for it in range(refine):
+        k = int(cur.max()) + 1
+        if k <= 2:
+            break
+        counts = np.bincount(cur, minlength=k)
+        if it % 3 == 0:
+            classes = list(np.argsort(-counts, kind="stable"))        # largest class first
+        elif it % 3 == 1:
+            classes = list(range(k - 1, -1, -1))                      # reverse
+        else:
+            classes = list(rng.permutation(k))
+        order = [v for c in classes for v in np.flatnonzero(cur == c).tolist()]
+        cur = _greedy_in_order(adj, order, n)
+        if score(cur) < score(best):
+            best = cur
+    return best
 
 
 @dataclass

@@ -48,9 +48,13 @@ def test_checkpoint_graphs_colour_with_few_colours(golden):
         ei, ej = z[name + "/edge_i"], z[name + "/edge_j"]
         col = greedy_colouring(256, ei, ej)
         assert not np.any(col[ei] == col[ej])
-        assert col.max() + 1 <= 6                  # 4-5 with smallest-last
+        counts = np.bincount(col)
+        assert len(counts) <= 5                    # 4-5 (iterated greedy; plain greedy gives 6
+        assert counts.min() >= 30                  # on Advantage2, with a 4-spin class that costs a whole round)
+        assert np.array_equal(col, greedy_colouring(256, ei, ej))      # deterministic
+        assert greedy_colouring(256, ei, ej, refine=0).max() + 1 >= len(counts)
         g = B.IsingGraph.build(256, ei, ej)
-        assert g.n_colours <= 6 and g.ell_width == np.bincount(np.concatenate([ei, ej])).max()
+        assert g.n_colours <= 5 and g.ell_width == np.bincount(np.concatenate([ei, ej])).max()
 
 
 def test_build_rejects_bad_graphs():

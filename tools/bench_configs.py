@@ -20,7 +20,12 @@ if args.lib:
     from image_generation_b200 import _lib
     _lib.LIB_PATH = os.path.abspath(args.lib)
 dev = torch.device("cuda:0")
-g = B.IsingGraph.zephyr(15) if args.graph == "z15" else B.IsingGraph.pegasus(16)
+if args.graph == "cfg1":       # the 256-spin Advantage2 subgraph of the reference's default checkpoint (BASELINE configs[0])
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "grbm_checkpoints.npz"))
+    name = "Advantage2_system1_10_epochs"
+    g = B.IsingGraph.build(256, z[name + "/edge_i"], z[name + "/edge_j"])
+else:
+    g = B.IsingGraph.zephyr(15) if args.graph == "z15" else B.IsingGraph.pegasus(16)
 rng = np.random.default_rng(0)
 h = (0.05 * rng.uniform(-0.05, 0.05, g.n)).astype(np.float32)
 J = (0.05 * rng.uniform(-5, 5, g.n_edges)).astype(np.float32)
