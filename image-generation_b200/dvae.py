@@ -159,6 +159,7 @@ class HybridDVAE:
         self.losses = {"mse_losses": [], "dvae_losses": []}
         self.overlap_sampling = True
         self._side_stream = None
+        self._prefetched = None              # negative-phase samples drawn ahead on the side stream
         self._dvae = self._grbm = self.sampler = None
         self._tpar: dict = {}
 
@@ -169,6 +170,7 @@ class HybridDVAE:
         raise AttributeError(name)
 
     def setup(self) -> None:
+        self._prefetched = None
         if self.LATENT_TO_DISCRETE in ["heaviside"] and self.N_REPLICAS != 1:
             raise ValueError("heaviside latent-to-discrete can only be used with n_replicas=1")
         if self.LATENT_TO_DISCRETE not in (None, "heaviside"):
@@ -186,6 +188,7 @@ class HybridDVAE:
                                                 weight_decay=self.BM_WEIGHT_DECAY)
 
     def train_init(self, n_epochs: int, n_batches: int) -> None:
+        self._prefetched = None
         self.losses["mse_losses"].clear()
         self.losses["dvae_losses"].clear()
         torch.manual_seed(self.RANDOM_SEED)
@@ -206,22 +209,25 @@ class HybridDVAE:
         self._dvae.train()
         self._grbm.train()
         R = self.N_REPLICAS
-        # The negative-phase samples depend only on the GRBM parameters, not on this batch: on a
-        # GPU they are drawn on a side stream while the encoder / decoder run on the main one
-        # (the sweep launch for 256 reads occupies ~64 of the 148 SMs).
+        # The negative-phase samples depend only on the GRBM parameters, not on this batch: on a GPU they are
+        # drawn on a side stream (the sweep launch for 256 reads occupies ~64 of the 148 SMs, and is a chain of
+        # dependent rounds -- latency, not throughput).  When this step does not update the GRBM, the samples of
+        # the NEXT step are launched right after this step's MMD forward, so they overlap the whole backward
+        # pass; otherwise they are launched at the top of the step and overlap the encoder / decoder forward.
+        # The order of sampler calls -- hence every seed -- is the same as without overlap.
         overlap = self.overlap_sampling and self.device.type == "cuda"
         if overlap:
             main = torch.cuda.current_stream(self.device)
             if self._side_stream is None:
                 self._side_stream = torch.cuda.Stream(self.device)
-            self._side_stream.wait_stream(main)
-            with torch.cuda.stream(self._side_stream), torch.no_grad():
-                samples = self._sample_prior()
+            if self._prefetched is None:
+                self._launch_prefetch(main)
         _, spins, recon = self._dvae(images, R)
 
         self._dvae_optimizer.zero_grad()
         mse = torch.nn.functional.mse_loss(recon, images.unsqueeze(1).expand(-1, R, -1, -1, -1))
         if overlap:
+            samples, self._prefetched = self._prefetched, None
             main.wait_stream(self._side_stream)
             samples.record_stream(main)
         else:
@@ -230,13 +236,16 @@ class HybridDVAE:
         spins = spins.reshape(-1, spins.shape[-1])
         mmd = maximum_mean_discrepancy_loss(x=spins, y=samples, kernel=self._tpar["kernel"], path=self.mmd_path)
         dvae_loss = mse + mmd
+        will_train_grbm = train_grbm(self._tpar["opt_step"], epoch)
+        if overlap and not will_train_grbm:
+            self._launch_prefetch(main)          # GRBM parameters stay as they are: next step's samples, now
         if record_losses:     # the reference logs .item() every step (:306,:324) -- a host sync
             self.losses["mse_losses"].append(mse.item())
             self.losses["dvae_losses"].append(dvae_loss.item())
         dvae_loss.backward()
         self._dvae_optimizer.step()
 
-        if train_grbm(self._tpar["opt_step"], epoch):
+        if will_train_grbm:
             self._grbm_optimizer.zero_grad()
             grbm_loss, self._tpar["sample_set"] = nll_loss(
                 spins=spins.detach(), grbm=self._grbm, sampler=self.sampler, sampler_kwargs=self.sampler_kwargs,
@@ -254,6 +263,12 @@ class HybridDVAE:
         self._tpar["opt_step"] = k + 1
         return mse
 
+    def _launch_prefetch(self, main) -> None:
+        """Draw the next negative-phase sample set on the side stream (after everything queued on ``main``)."""
+        self._side_stream.wait_stream(main)
+        with torch.cuda.stream(self._side_stream), torch.no_grad():
+            self._prefetched = self._sample_prior()
+
     def _sample_prior(self) -> torch.Tensor:
         return self._grbm.sample(self.sampler, prefactor=self.PREFACTOR, linear_range=self.linear_range,
                                  quadratic_range=self.quadratic_range, device=self.device,
@@ -264,6 +279,8 @@ class HybridDVAE:
         """Decoded GRBM samples, ``(num_reads, 1, 32, 32)`` in [0, 1] (src/model_wrapper.py:368-381)."""
         self._dvae.eval()
         self._grbm.eval()
+        if self._side_stream is not None:      # a prefetch in flight uses the sampler's tables and scratch
+            torch.cuda.current_stream(self.device).wait_stream(self._side_stream)
         samples = self._grbm.sample(self.sampler, prefactor=self.PREFACTOR, device=self.device,
                                     linear_range=self.linear_range, quadratic_range=self.quadratic_range,
                                     sample_params=self.sampler_kwargs)

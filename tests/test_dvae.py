@@ -81,6 +81,47 @@ def test_reference_shaped_training_steps(cuda_device, golden, mmd_path, packed):
     assert set(sd) == {"dvae.pth", "grbm.pth"} and "_encoder.conv.0.weight" in sd["dvae.pth"]
 
 
+@pytest.mark.gpu
+def test_prefetched_sampling_gives_the_same_training_run(cuda_device, golden):
+    """The negative-phase samples of the next step are drawn on a side stream during the backward pass (or during
+    the forward pass after a GRBM update).  The sequence of sampler calls, hence every seed and every sample, must
+    be the one of the plain sequential step: same losses and same GRBM parameters after steps that include the
+    GRBM updates at opt_step 0 and 10."""
+    z, _ = golden
+    name = "Advantage2_system1_10_epochs"
+    edges = list(zip(z[name + "/edge_i"].tolist(), z[name + "/edge_j"].tolist()))
+    runs = []
+    for overlap in (False, True):
+        torch.manual_seed(7)
+        model = HybridDVAE(range(256), edges, device=cuda_device, sampler_kwargs=dict(num_sweeps=50))
+        model.overlap_sampling = overlap
+        model.setup()
+        model.train_init(n_epochs=1, n_batches=13)
+        seeds = []
+        run = model.sampler._run
+
+        def logged(*a, _run=run, _seeds=seeds, **kw):
+            ss = _run(*a, **kw)
+            _seeds.append(ss.info["seed"])
+            return ss
+
+        model.sampler._run = logged
+        first = []
+        for k in range(13):
+            model.step((synthetic_batch(64, seed=k), None), epoch=0)
+            if k < 2:
+                first.append(model._grbm._linear.detach().cpu().numpy().copy())
+        runs.append((np.array(model.losses["dvae_losses"]), seeds, first, model._grbm._quadratic.detach().cpu().numpy()))
+    a, b = runs
+    assert len(a[1]) == 13 + 2                                 # 13 MMD sample sets + the NLL ones at opt_step 0 and 10
+    assert b[1][:15] == a[1] and len(b[1]) == 16               # same calls in the same order (+ the set drawn ahead for step 13)
+    np.testing.assert_allclose(a[0][:2], b[0][:2], rtol=1e-5)  # before float-atomic noise in the conv backward amplifies
+    for x, y in zip(a[2], b[2]):
+        np.testing.assert_allclose(x, y, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(a[0], b[0], rtol=5e-3)
+    np.testing.assert_allclose(a[3], b[3], rtol=5e-3, atol=1e-4)
+
+
 def test_save_load_round_trip(tmp_path):
     model = HybridDVAE(range(16), [(a, a + 1) for a in range(15)], device="cpu", parameters={"N_REPLICAS": 2})
     model.setup()

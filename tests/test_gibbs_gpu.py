@@ -92,17 +92,24 @@ def test_groups_that_start_inside_a_philox_block(cuda_device, cpl, threads):
     assert np.array_equal(got, want)
 
 
-def test_bracketed_decisions_fall_back_to_contract_arithmetic(cuda_device):
-    """The kernel decides from MUFU.EX2 and the 16 high bits of the uniform and re-evaluates a lane-task with
-    the contract polynomial and the full 23-bit uniform when a decision sits inside its error bracket
-    (about 2e-5 of the decisions).  3.7e7 decisions here -> several hundred fallbacks; every spin must still
-    equal the oracle, which always evaluates the contract."""
+@pytest.mark.parametrize("regime", ["beta1", "cold"])
+def test_bracketed_decisions_fall_back_to_contract_arithmetic(cuda_device, regime):
+    """The kernel decides from MUFU.EX2 and the 16 high bits of the uniform and re-evaluates a decision with
+    the contract polynomial and the full 23-bit uniform when it sits inside its error bracket (about 2e-5 of
+    the decisions).  3.5e7 decisions here -> several hundred fallbacks; every spin must still equal the oracle,
+    which always evaluates the contract.  "cold": strong couplings and beta up to 6, so that |x| runs through
+    the whole range of the exponential (past the contract's clamp at 120 and MUFU's overflow at 128)."""
     g = B.IsingGraph.pegasus(6)
-    h, J = _problem(g, 21)
     chains, sweeps, seed = 1024, 50, 4242
+    if regime == "cold":
+        h, J = _problem(g, 22, h_scale=0.5, j_scale=1.0)
+        beta = np.geomspace(0.05, 6.0, sweeps)
+    else:
+        h, J = _problem(g, 21)
+        beta = np.ones(sweeps)
     csr = _oracle_csr(g)
-    want = O.gibbs(csr, h, J, O.init_state(csr, chains, seed), [1.0] * sweeps, seed=seed)
-    got = B.BlockGibbsSampler(g, device=cuda_device).sample_ising(h, J, num_reads=chains, num_sweeps=sweeps,
+    want = O.gibbs(csr, h, J, O.init_state(csr, chains, seed), beta, seed=seed)
+    got = B.BlockGibbsSampler(g, device=cuda_device).sample_ising(h, J, num_reads=chains, beta_schedule=beta,
                                                                  seed=seed).record.sample
     assert np.array_equal(got, want)
 
