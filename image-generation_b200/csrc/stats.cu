@@ -332,8 +332,13 @@ extern "C" int32_t b200grbm_edge_stats(const uint32_t *packed_dev, int32_t rows,
                                                                 reinterpret_cast<unsigned long long *>(sum_ss_dev));
         B200_CUDA(cudaGetLastError());
     }
-    node_stats_kernel<<<dim3(nblocks, ygrid), 256, 0, st>>>(packed_dev, rows, cpl, n, n_pad, order_dev, gpb,
-                                                            reinterpret_cast<unsigned long long *>(sum_s_dev));
+    // the node axis is ~8x shorter than the edge axis: its own split of the group axis
+    int ysplit_n = (4 * sms + nblocks - 1) / nblocks;
+    if (ysplit_n > groups) ysplit_n = groups;
+    if (ysplit_n > 65535) ysplit_n = 65535;
+    const int gpb_n = (groups + ysplit_n - 1) / ysplit_n;
+    node_stats_kernel<<<dim3(nblocks, (groups + gpb_n - 1) / gpb_n), 256, 0, st>>>(
+        packed_dev, rows, cpl, n, n_pad, order_dev, gpb_n, reinterpret_cast<unsigned long long *>(sum_s_dev));
     B200_CUDA(cudaGetLastError());
     return 0;
 }

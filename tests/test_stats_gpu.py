@@ -36,7 +36,7 @@ def test_golden_energies_through_the_module(cuda_device, golden):
         np.testing.assert_allclose(got, want, rtol=1e-5)
 
 
-@pytest.mark.parametrize("rows,cpl", [(1, 32), (37, 32), (100, 28), (1024, 32)])
+@pytest.mark.parametrize("rows,cpl", [(1, 32), (37, 32), (100, 28), (1024, 32), (5000, 28)])   # >= 32 groups: staged rows
 def test_pack_and_integer_statistics_bit_exact(cuda_device, rows, cpl):
     g = B.IsingGraph.pegasus(3)
     rng = np.random.default_rng(rows)
