@@ -111,21 +111,12 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
 #endif
 #pragma unroll
     for (int r = 0; r < B200GRBM_PHILOX_ROUNDS; ++r) {
-#ifdef B200_EXP_MULHI        // timing experiment: separate high / low multiplies instead of one wide multiply
-        const uint32_t h0 = __umulhi(B200GRBM_PHILOX_M0, c0), l0 = B200GRBM_PHILOX_M0 * c0;
-        const uint32_t h1 = __umulhi(B200GRBM_PHILOX_M1, c2), l1 = B200GRBM_PHILOX_M1 * c2;
-        const uint32_t n0 = h1 ^ c1 ^ p.rk[2 * r];
-        const uint32_t n2 = h0 ^ c3 ^ p.rk[2 * r + 1];
-        c1 = l1;
-        c3 = l0;
-#else
         const uint64_t p0 = (uint64_t)B200GRBM_PHILOX_M0 * c0;
         const uint64_t p1 = (uint64_t)B200GRBM_PHILOX_M1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ p.rk[2 * r];
         const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ p.rk[2 * r + 1];
         c1 = (uint32_t)p1;
         c3 = (uint32_t)p0;
-#endif
         c0 = n0;
         c2 = n2;
     }
