@@ -61,6 +61,7 @@ struct SweepParams {
     uint32_t state_bytes;   // shared-memory bytes reserved for W (multiple of 128)
     uint32_t tile_bytes;    // (width + 1) * threads * 8
     uint32_t resident;      // 1: all n_tiles tiles fit in shared memory and are copied once (small graphs)
+    uint32_t single;        // 1: one tile stage per CTA, two CTAs per SM cover each other's copy latency
     uint32_t rk[2 * B200GRBM_PHILOX_ROUNDS];
 };
 
@@ -435,19 +436,35 @@ __global__ void __launch_bounds__(B200_SWEEP_MAX_THREADS, 1) gibbs_kernel(const 
         const uint32_t s = (uint32_t)q & 1u;
         // stage s^1 was last read in round q-1, which every thread left through the
         // __syncthreads() below -> safe to refill it now while round q computes
-        if (tid == 0 && q + 1 < total_tiles && !p.resident) {
-            const int next_tile = tile + 1 == p.n_tiles ? 0 : tile + 1;
-            const uint32_t nb = bar_addr + 8u * (s ^ 1u);
-            mbar_expect_tx(nb, p.tile_bytes);
-            bulk_g2s(stage_addr + (s ^ 1u) * p.tile_bytes,
-                     reinterpret_cast<const unsigned char *>(p.tiles) + (size_t)next_tile * p.tile_bytes, p.tile_bytes, nb);
+        if (tid == 0 && !p.resident) {
+            if (p.single) {
+                // one stage: the copy of round q can only start now (everyone has left round q-1); the SM's other
+                // CTA computes meanwhile
+                if (q > 0) {
+                    mbar_expect_tx(bar_addr, p.tile_bytes);
+                    bulk_g2s(stage_addr, reinterpret_cast<const unsigned char *>(p.tiles) + (size_t)tile * p.tile_bytes,
+                             p.tile_bytes, bar_addr);
+                }
+            } else if (q + 1 < total_tiles) {
+                const int next_tile = tile + 1 == p.n_tiles ? 0 : tile + 1;
+                const uint32_t nb = bar_addr + 8u * (s ^ 1u);
+                mbar_expect_tx(nb, p.tile_bytes);
+                bulk_g2s(stage_addr + (s ^ 1u) * p.tile_bytes,
+                         reinterpret_cast<const unsigned char *>(p.tiles) + (size_t)next_tile * p.tile_bytes, p.tile_bytes,
+                         nb);
+            }
         }
         const int2 info = tinfo[tile];
         // resident tables: one wait, before the first round (a copy round trip per round would otherwise be the
         // critical path of the short rounds of a small graph)
-        if (!p.resident) mbar_wait(bar_addr + 8u * s, (uint32_t)(q >> 1) & 1u);
-        else if (q == 0) mbar_wait(bar_addr, 0u);
-        const uint32_t stage_idx = p.resident ? (uint32_t)tile : s;
+        if (p.resident) {
+            if (q == 0) mbar_wait(bar_addr, 0u);
+        } else if (p.single) {
+            mbar_wait(bar_addr, (uint32_t)q & 1u);
+        } else {
+            mbar_wait(bar_addr + 8u * s, (uint32_t)(q >> 1) & 1u);
+        }
+        const uint32_t stage_idx = p.resident ? (uint32_t)tile : (p.single ? 0u : s);
 
         if (tid < info.y) {
             const int pp = info.x + tid;
@@ -691,12 +708,21 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
     p.resident = (a->n_tiles <= 2 || (smem_resident <= (size_t)smem_optin &&
                                       (size_t)a->n_tiles * p.tile_bytes < (1u << 20))) ? 1u : 0u;
     if (p.resident) smem = smem_resident;
+    // many groups, narrow CTAs: ONE tile stage per CTA and two CTAs per SM -- twice the warps per scheduler, each
+    // CTA's round barrier and copy latency covered by the other (Zephyr Z15: 2 x 384 threads instead of 1 x 480)
+    const int groups = (a->chains + a->chains_per_lane - 1) / a->chains_per_lane;
+    int smem_sm = 0;
+    B200_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    const size_t smem_single = smem - p.tile_bytes;
+    p.single = (!p.resident && a->threads <= 384 && groups >= 2 * (sm_count() > 0 ? sm_count() : 148) &&
+                2 * (smem_single + 1024) <= (size_t)smem_sm) ? 1u : 0u;
+    if (p.single) smem = smem_single;
     if (smem > (size_t)smem_optin)
         return fail(B200GRBM_EUNSUPPORTED,
                     "gibbs_sweeps: n=%d width=%d threads=%d need %zu B of shared memory (> %d); use fewer threads",
                     a->n, a->ell_width, a->threads, smem, smem_optin);
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int groups = (a->chains + a->chains_per_lane - 1) / a->chains_per_lane;
+    B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     fn<<<groups, a->threads, smem, (cudaStream_t)stream>>>(p);
     B200_CUDA(cudaGetLastError());
     g_last_launches = 1;

@@ -75,10 +75,13 @@ def test_argument_validation_happens_before_any_launch():
 
 
 def test_sweep_smem_formula_matches_library():
-    from image_generation_b200.sampler import plan_threads, sweep_smem_bytes
+    from image_generation_b200.sampler import plan_threads, sweep_smem_bytes, sweep_state_offset
     lib = _lib.load()
     for n, w, t, nt in ((5640, 15, 736, 8), (7440, 20, 480, 16), (256, 20, 128, 5), (9, 2, 64, 3), (50000, 20, 256, 200)):
         assert lib.b200grbm_sweep_smem_bytes(n, w, t, nt) == sweep_smem_bytes(n, w, t, nt)
+        # the tiles' .nbr fields are byte offsets from the start of the CTA's shared memory: host and kernel must agree
+        assert lib.b200grbm_sweep_state_offset(nt) == sweep_state_offset(nt)
+        assert sweep_state_offset(nt) % 128 == 0 and sweep_state_offset(nt) >= 128 + 8 * nt
     # the planner never exceeds the 227 KB opt-in limit
     for n, w, sizes in ((5640, 15, [1410] * 4), (7440, 20, [1860] * 4), (40000, 20, [10000] * 4)):
         t = plan_threads(sizes, n, w)

@@ -71,8 +71,11 @@ def test_build_rejects_bad_graphs():
 def test_plan_launch():
     # cfg2: 4096 chains on 148 SMs -> 28 chains per CTA fills 147 SMs in one wave
     assert B.plan_launch(4096, [1410] * 4, 148, 5640, 15)[0] == 28
-    cpl, threads = B.plan_launch(32768, [1860] * 4, 148, 7440, 20)
-    assert cpl in (28, 32) and threads % 32 == 0
+    assert B.plan_launch(4096, [1410] * 4, 148, 5640, 15) == (28, 736)
+    # many groups: two narrow single-stage CTAs per SM when that also needs fewer warp slots per sweep
+    assert B.plan_launch(32768, [1860] * 4, 148, 7440, 20) == (28, 384)       # Z15: 20 rounds x 3 < 16 rounds x 4
+    assert B.plan_launch(4096, [1860] * 4, 148, 7440, 20) == (28, 480)        # too few groups for two CTAs per SM
+    assert B.plan_launch(262144, [1410] * 4, 148, 5640, 15) == (28, 736)      # P16: 48 slots either way -> wide CTA
     for chains in (1, 5, 100, 4096, 262144):
         cpl, threads = B.plan_launch(chains, [7, 9], 148)
         assert cpl in (4, 8, 16, 24, 28, 32) and 64 <= threads <= 768
