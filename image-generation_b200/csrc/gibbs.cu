@@ -171,14 +171,17 @@ __device__ __forceinline__ bool accept_exact(float f, float coef, float v)
 #define B200GRBM_LAZY_K1 0x1.004p-17f
 #define B200GRBM_LAZY_K2 0x1.0p-17f
 
-// x is NOT clamped here.  x > 128 gives e~ = g = d = +inf: sign clear = the contract's decision (its clamp at
+// x is NOT clamped here (Philox modes: v >= 2^-24).  x > 128 gives e~ = g = d = +inf: sign clear = the contract's decision (its clamp at
 // 120 leaves e >= 2^120 > 1/v for every v >= 2^-24), and the mark m = (-inf) + inf is the canonical NaN
 // 0x7fffffff, sign clear = "sure".  x < -126 flushes e~ to 0, g = 1, d = vm - 1 < 0: also the contract's
 // decision.  One instruction less per decision on the ALU pipe, the busiest one in this phase.
-template <bool CHECK>
+// Supplied uniforms (CLAMP) may be any float in (0,1), also below 2^-120 where the contract's clamp matters: that
+// mode keeps the upper clamp, which makes g finite and the bracket argument unconditional.
+template <bool CHECK, bool CLAMP = false>
 __device__ __forceinline__ uint32_t decide_quick(float f, float coef, float vm, uint32_t &unsure)
 {
-    const float x = __fmul_rn(f, coef);
+    float x = __fmul_rn(f, coef);
+    if (CLAMP) x = fminf(x, B200GRBM_EXP2_CLAMP);
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
     const float g = __fadd_rn(e, 1.0f);
@@ -332,7 +335,7 @@ __device__ __forceinline__ uint32_t decide_word(const float (&f)[CPL], float coe
             const int cc = min(chain0 + c, p.chains - 1);
             const float v = __ldg(p.uniforms + ((size_t)t * p.chains + cc) * p.n + pp);
             if (CPL == 28 && (c + 1) % 7 == 0) neww <<= 1;
-            neww = __funnelshift_l(decide_quick<true>(f[c], coef, v, unsure), neww, 1);
+            neww = __funnelshift_l(decide_quick<true, true>(f[c], coef, v, unsure), neww, 1);
         }
     } else {
 #pragma unroll

@@ -47,6 +47,27 @@ def test_supplied_uniforms_bit_exact(cuda_device, cpl, threads):
     np.testing.assert_allclose(ss.record.energy, O.energies(g.n, g.edge_i, g.edge_j, h, J, want), rtol=1e-12, atol=1e-9)
 
 
+def test_supplied_uniforms_at_the_edges_of_the_interval(cuda_device):
+    """Supplied uniforms may be any float in (0, 1): values far below 2^-24 (where the contract's clamp of the
+    exponent at 120 decides), next to 1, and ordinary ones, against very large and very small fields."""
+    g = B.IsingGraph.pegasus(3)
+    h, J = _problem(g, 9, h_scale=1.0, j_scale=1.0)
+    chains, sweeps = 60, 5
+    rng = np.random.default_rng(10)
+    special = np.array([1e-38, 1e-36, 2.0 ** -121, 2.0 ** -119, 1e-30, 2.0 ** -24, 0.5, 1 - 2.0 ** -24, 0.999], dtype=np.float32)
+    U = rng.uniform(1e-6, 1 - 1e-6, size=(sweeps, chains, g.n)).astype(np.float32)
+    pick = rng.random(U.shape) < 0.5
+    U[pick] = rng.choice(special, size=int(pick.sum()))
+    init = rng.choice([-1, 1], size=(chains, g.n)).astype(np.int8)
+    beta = np.array([0.01, 0.5, 3.0, 8.0, 30.0])          # |x| from ~0 to far beyond the clamp
+    want = O.gibbs(_oracle_csr(g), h, J, init, beta, uniforms=U)
+    s = B.BlockGibbsSampler(g, device=cuda_device)
+    s.device_graph.set_weights(torch.from_numpy(h), torch.from_numpy(J))
+    for plan in ((28, 128), (8, 64)):
+        got = s._run(chains, None, None, None, beta, 0, init, torch.from_numpy(U), plan=plan).record.sample
+        assert np.array_equal(got, want), plan
+
+
 @pytest.mark.parametrize("cpl,threads", [(4, 128), (8, 64), (16, 96), (28, 256), (32, 480)])
 def test_philox_exact_mode_bit_exact_and_geometry_independent(cuda_device, cpl, threads):
     g = B.IsingGraph.pegasus(5)
