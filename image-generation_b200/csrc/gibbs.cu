@@ -168,8 +168,6 @@ __device__ __forceinline__ bool accept_exact(float f, float coef, float v)
 //   |e~ - e| <= 2^-20 e  (ex2.approx.ftz: 2^-22 relative; contract polynomial: 2.4e-7), roundings 2^-24
 //   => |v (1 + e) - vm (1 + e~)| <= 2^-17 (1 + e)(1 + 2^-19) + (d + 1) 2^-19  <  K1 (1 + e~) + K2 - 2^-24
 // with K1 = 2^-17 (1 + 2^-10), K2 = 2^-17.  `sure` accumulates over the lane-task.
-#define B200GRBM_LAZY_K1 0x1.004p-17f
-#define B200GRBM_LAZY_K2 0x1.0p-17f
 
 // x is NOT clamped here (Philox modes: v >= 2^-24).  x > 128 gives e~ = g = d = +inf: sign clear = the contract's decision (its clamp at
 // 120 leaves e >= 2^120 > 1/v for every v >= 2^-24), and the mark m = (-inf) + inf is the canonical NaN

@@ -72,4 +72,13 @@
 #define B200GRBM_EXP2_CLAMP 120.0f
 #define B200GRBM_UNIFORM_HALF_ULP 0x1.0p-24f
 
+/*
+ * NOT part of the contract: constants of the sm_100a kernel's evaluation strategy (csrc/gibbs.cu decide_quick),
+ * here so that the oracle's self-test of the bracket argument uses the same numbers.  With the 16-bit midpoint
+ * v_m and e~ = MUFU.EX2(x), g = 1 + e~, d = v_m g - 1, the sign of d is the contract's decision whenever
+ * |d| > K1 g + K2  (K1 = 2^-17 (1 + 2^-10), K2 = 2^-17); otherwise the contract arithmetic is evaluated.
+ */
+#define B200GRBM_LAZY_K1 0x1.004p-17f
+#define B200GRBM_LAZY_K2 0x1.0p-17f
+
 #endif /* B200GRBM_SPEC_H */

@@ -93,6 +93,56 @@ int oracle_accept(float f, float coef, float v)
     return fmaf(v, e, v) < 1.0f;
 }
 
+/*
+ * Self-test of the bracket argument behind the sm_100a kernel's lazy acceptance (csrc/gibbs.cu decide_quick,
+ * DESIGN.md section 3) -- CPU only, no GPU involved: the quick decision is formed from the 16 high bits of the
+ * uniform and an ADVERSARIAL exp2, e~ = 2^x (1 + rel), and compared with the contract's decision for every value
+ * of the 7 low bits.  Returns 0/1 when the mark says the decision is certain, -1 when it defers to the contract.
+ */
+int oracle_bracketed_decision(float f, float coef, uint32_t hw, double rel)
+{
+    const float x = f * coef;                              /* not clamped on the fast side (Philox modes) */
+    double et = exp2((double)x) * (1.0 + rel);
+    float e = et > 3.0e38 ? INFINITY : (float)et;
+    if (e < 1.17549435e-38f) e = 0.0f;                     /* ex2.approx.ftz flushes subnormal results */
+    const float g = e + 1.0f;
+    const float vm = ((float)hw + 0.5f) * 0x1.0p-16f;      /* exact */
+    const float d = fmaf(vm, g, -1.0f);
+    const float m = fmaf(g, -B200GRBM_LAZY_K1, fabsf(d) - B200GRBM_LAZY_K2);
+    if (!isnan(m) && signbit(m)) return -1;                /* the GPU's NaN (inf - inf) is 0x7fffffff: sign clear */
+    return (!isnan(d) && signbit(d)) ? 1 : 0;
+}
+
+/* n random (f, beta, hw) triples, half of them with hw placed next to the acceptance threshold; every decision the
+ * mark calls certain must equal the contract's for lo7 = 0, 127 and a random value.  Returns the number of
+ * violations; *deferred receives the number of deferred decisions. */
+int64_t oracle_bracket_selftest(int64_t n, uint64_t seed, double rel, int64_t *deferred)
+{
+    int64_t bad = 0, unsure = 0;
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t ctr[4] = { (uint32_t)i, (uint32_t)(i >> 32), 7u, 11u }, r[4];
+        oracle_philox4x32_10(ctr, key, r);
+        const float u0 = (float)(r[0] >> 8) * 0x1.0p-24f, u1 = (float)(r[1] >> 8) * 0x1.0p-24f;
+        const float f = (u0 - 0.5f) * 24.0f;                                   /* fields in [-12, 12] */
+        const float beta = 0.02f * exp2f(u1 * 10.0f);                          /* beta in [0.02, 20]: |x| up to ~700 */
+        const float coef = (float)(2.0 * (double)beta * 1.4426950408889634);
+        uint32_t hw = r[2] & 0xffffu;
+        if (i & 1) {                                                           /* next to the threshold 1 / (1 + 2^x) */
+            const double p = 1.0 / (1.0 + exp2((double)(f * coef)));
+            long t = (long)floor(p * 65536.0) + (long)(r[2] >> 16) % 5 - 2;
+            hw = (uint32_t)(t < 0 ? 0 : t > 65535 ? 65535 : t);
+        }
+        const int q = oracle_bracketed_decision(f, coef, hw, rel);
+        if (q < 0) { ++unsure; continue; }
+        const uint32_t lows[3] = { 0u, 127u, r[3] & 127u };
+        for (int k = 0; k < 3; ++k)
+            if (oracle_accept(f, coef, oracle_uniform_from_m23((hw << 7) | lows[k])) != q) ++bad;
+    }
+    if (deferred) *deferred = unsure;
+    return bad;
+}
+
 static inline uint32_t halfword(const uint32_t out[4], unsigned j) { return (out[j >> 1] >> (16u * (j & 1u))) & 0xffffu; }
 
 /*

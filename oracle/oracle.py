@@ -68,6 +68,16 @@ def uniform_from_m23(m23: int) -> float:
     return float(lib().oracle_uniform_from_m23(C.c_uint32(m23)))
 
 
+def bracket_selftest(n: int, seed: int, rel: float) -> tuple:
+    """(violations, deferred) of the lazy-acceptance bracket argument over ``n`` random decisions with an exp2
+    that is off by the relative error ``rel`` (oracle.c: oracle_bracket_selftest)."""
+    deferred = C.c_int64(0)
+    fn = lib().oracle_bracket_selftest
+    fn.restype = C.c_int64
+    fn.argtypes = [C.c_int64, C.c_uint64, C.c_double, C.POINTER(C.c_int64)]
+    return int(fn(n, seed, rel, C.byref(deferred))), int(deferred.value)
+
+
 def sweep_uniform(seed: int, pos: int, sweep: int, chain: int) -> float:
     """The contract's sweep uniform of (visit position, sweep, global chain): high 16 bits from Philox
     stream 0, low 7 bits from stream 2, blocks of 8 chains per call (include/b200grbm_spec.h)."""

@@ -45,6 +45,19 @@ def test_sweep_uniform_is_built_from_two_philox_streams():
         assert abs(v - (hw + 0.5) * 2.0 ** -16) < 2.0 ** -17      # the 16-bit midpoint brackets it
 
 
+def test_lazy_acceptance_bracket_never_contradicts_the_contract():
+    """The sm_100a kernel decides from the 16 high bits of the uniform and MUFU.EX2 and defers to the contract
+    arithmetic only inside a bracket.  CPU self-test of that argument with an ADVERSARIAL
+    exp2 -- relative error up to 2^-19, eight times the documented 2^-22 of ex2.approx -- over 4e6 decisions,
+    half of them placed next to the acceptance threshold, |x| up to ~700: a decision the mark calls certain must
+    equal the contract's for every value of the 7 low bits.  A grossly wrong exp2 (2^-12) must be caught."""
+    for rel in (0.0, 2.0 ** -22, -2.0 ** -22, 2.0 ** -19, -2.0 ** -19):
+        bad, deferred = O.bracket_selftest(800_000, 11, rel)
+        assert bad == 0, rel
+        assert 0 < deferred < 0.25 * 800_000          # only the near-threshold half is ever deferred
+    assert O.bracket_selftest(800_000, 11, 2.0 ** -12)[0] > 0
+
+
 def test_exp2_poly_accuracy_and_range():
     xs = np.linspace(-60, 60, 20001)
     got = np.array([O.exp2_poly(float(x)) for x in xs])
