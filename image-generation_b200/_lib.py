@@ -69,6 +69,7 @@ SIGNATURES = {
     "b200grbm_sweep_state_offset": ([_i32], _i32),
     "b200grbm_gibbs_sweeps": ([C.POINTER(SweepArgs), _vp], _i32),
     "b200grbm_last_launch_count": ([], _i32),
+    "b200grbm_ex2_probe": ([_f32, _f32, C.c_int64, C.POINTER(C.c_double), _vp], _i32),
     "b200grbm_pack_f32": ([_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp], _i32),
     "b200grbm_pack_i8": ([_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp], _i32),
     "b200grbm_edge_stats": ([_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
@@ -136,6 +137,19 @@ def device_info() -> dict:
     vals = [C.c_int32() for _ in range(4)]
     check(lib.b200grbm_device_info(*[C.byref(v) for v in vals]))
     return dict(sm_count=vals[0].value, cc=(vals[1].value, vals[2].value), smem_optin=vals[3].value)
+
+
+def ex2_max_rel_error(x_lo: float, x_hi: float, n: int = 1 << 24, device=None) -> float:
+    """Largest relative error of the hardware exp2 (``ex2.approx.ftz.f32``) over ``n`` arguments of
+    ``[x_lo, x_hi]`` -- the quantity the sweep kernel's acceptance bracket has to cover."""
+    import torch
+
+    lib = load()
+    out = C.c_double()
+    dev = torch.device("cuda" if device is None else device)
+    with torch.cuda.device(dev):
+        check(lib.b200grbm_ex2_probe(float(x_lo), float(x_hi), int(n), C.byref(out), current_stream(dev)))
+    return out.value
 
 
 def tensor_peak(kind: str = "i8", iters: int = 20000, device=None) -> float:

@@ -38,6 +38,8 @@
 //     The result is bit-identical to evaluating the contract everywhere (oracle/oracle.c).
 #include "common.cuh"
 
+#include <cstring>
+
 namespace b200grbm {
 
 enum { MODE_PHILOX_EXACT = 0, MODE_PHILOX_FAST = 1, MODE_SUPPLIED_EXACT = 2 };
@@ -589,6 +591,22 @@ __global__ void __launch_bounds__(B200_SWEEP_MAX_THREADS, 1) gibbs_kernel(const 
     }
 }
 
+// Measurement aid: largest relative error of ex2.approx.ftz.f32 (the MUFU.EX2 the lazy acceptance brackets
+// with) against double-precision exp2 over n evenly spaced fp32 arguments of [x_lo, x_hi].
+__global__ void ex2_probe_kernel(float x_lo, float x_hi, long long n, unsigned long long *max_bits)
+{
+    double worst = 0.0;
+    const double step = n > 1 ? ((double)x_hi - (double)x_lo) / (double)(n - 1) : 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float x = (float)((double)x_lo + step * (double)i);
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+        const double t = exp2((double)x);
+        if (t >= 1.1754943508222875e-38 && t <= 3.0e38) worst = fmax(worst, fabs((double)e - t) / t);
+    }
+    atomicMax(max_bits, (unsigned long long)__double_as_longlong(worst));   // non-negative doubles order like integers
+}
+
 typedef void (*gibbs_fn)(const SweepParams);
 
 template <int CPL>
@@ -621,6 +639,26 @@ static thread_local int32_t g_last_launches = 0;
 using namespace b200grbm;
 
 extern "C" int32_t b200grbm_last_launch_count(void) { return g_last_launches; }
+
+extern "C" int32_t b200grbm_ex2_probe(float x_lo, float x_hi, int64_t n, double *max_rel_err_out, void *stream)
+{
+    if (n <= 0 || !(x_hi >= x_lo) || max_rel_err_out == nullptr)
+        return fail(B200GRBM_EINVAL, "ex2_probe: n=%lld range [%g, %g]", (long long)n, (double)x_lo, (double)x_hi);
+    B200_TRY(require_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *dev = nullptr, host = 0;
+    B200_CUDA(cudaMallocAsync(&dev, sizeof(host), st));          // measurement aid: the one entry point that allocates
+    B200_CUDA(cudaMemsetAsync(dev, 0, sizeof(host), st));
+    ex2_probe_kernel<<<1184, 256, 0, st>>>(x_lo, x_hi, (long long)n, dev);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaMemcpyAsync(&host, dev, sizeof(host), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaFreeAsync(dev, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    double v;
+    memcpy(&v, &host, sizeof(v));
+    *max_rel_err_out = v;
+    return 0;
+}
 
 extern "C" int32_t b200grbm_sweep_state_offset(int32_t n_tiles)
 {

@@ -114,6 +114,13 @@ int32_t b200grbm_sweep_state_offset(int32_t n_tiles);
 /* dynamic shared memory a sweep launch needs (round table + state + 2 tile stages); must fit the device's opt-in limit */
 int64_t b200grbm_sweep_smem_bytes(int32_t n, int32_t ell_width, int32_t threads, int32_t n_tiles);
 
+/*
+ * Measurement aid for the sweep kernel's lazy acceptance: largest relative error of
+ * ex2.approx.ftz.f32 against double-precision exp2 over n evenly spaced fp32 arguments of [x_lo, x_hi]
+ * (normal results only).  max_rel_err_out is a HOST pointer; synchronises the stream.
+ */
+int32_t b200grbm_ex2_probe(float x_lo, float x_hi, int64_t n, double *max_rel_err_out, void *stream);
+
 /* number of kernel launches the last b200grbm_gibbs_sweeps call on this thread enqueued */
 int32_t b200grbm_last_launch_count(void);
 

@@ -113,6 +113,15 @@ def test_groups_that_start_inside_a_philox_block(cuda_device, cpl, threads):
     assert np.array_equal(got, want)
 
 
+def test_hardware_exp2_error_is_far_inside_the_bracket(cuda_device):
+    """MUFU.EX2 on this device against double-precision exp2: the lazy acceptance assumes 2^-22 (PTX ISA) and its
+    bracket tolerates 2^-17 (tests/test_oracle.py::test_lazy_acceptance_bracket_never_contradicts_the_contract)."""
+    worst = 0.0
+    for lo, hi in ((-1.0, 1.0), (-20.0, 20.0), (-126.0, 126.0), (100.0, 127.9), (-126.0, -100.0)):
+        worst = max(worst, _lib.ex2_max_rel_error(lo, hi, 1 << 24, cuda_device))
+    assert 0.0 < worst < 2.0 ** -21, worst
+
+
 @pytest.mark.parametrize("regime", ["beta1", "cold"])
 def test_bracketed_decisions_fall_back_to_contract_arithmetic(cuda_device, regime):
     """The kernel decides from MUFU.EX2 and the 16 high bits of the uniform and re-evaluates a decision with
