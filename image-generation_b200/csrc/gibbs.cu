@@ -26,10 +26,12 @@
 //   * Same-colour spins are never adjacent, so the parallel colour step equals the
 //     sequential sweep in visit order; W[p] is written in place and __syncthreads()
 //     separates rounds.
-//   * Uniforms: Philox4x32-10 keyed by (seed; visit position, sweep, global chain / 8) --
+//   * Uniforms: Philox4x32-10 keyed by (seed; visit position, global chain / 8, sweep) --
 //     one call yields the high 16 bits of the uniforms of 8 chains of the lane; the low 7
 //     bits live in a second stream that is only evaluated when a decision depends on them --
-//     so trajectories do not depend on CPL, CTA size, grid or GPU count.  Round keys are
+//     so trajectories do not depend on CPL, CTA size, grid or GPU count.  The chain block sits in counter
+//     word 1, which enters the first round only through an XOR: the calls of one lane-task (same position
+//     and sweep, consecutive blocks) share the multiplies of rounds 1-3 that do not depend on it.  Round keys are
 //     precomputed on the host into the kernel parameter block (uniform-register operands).
 //   * Lazy exact acceptance: the contract decision  fmaf(v, exp2_poly(x), v) < 1  is first
 //     bracketed with MUFU.EX2 and the 16-bit midpoint uniform; only when the bracket
@@ -286,8 +288,8 @@ __device__ __noinline__ uint32_t fix_word_philox(uint32_t neww, uint32_t unsure,
         unsure &= ~(1u << c);
         const int hidx = c + SHIFT;
         uint32_t r[4], q[4];
-        philox4x32(pp, sweep, blk8 + (uint32_t)(hidx >> 3), B200GRBM_STREAM_SWEEP, p, r);
-        philox4x32(pp, sweep, blk8 + (uint32_t)(hidx >> 3), B200GRBM_STREAM_SWEEP_LO, p, q);
+        philox4x32(pp, blk8 + (uint32_t)(hidx >> 3), sweep, B200GRBM_STREAM_SWEEP, p, r);
+        philox4x32(pp, blk8 + (uint32_t)(hidx >> 3), sweep, B200GRBM_STREAM_SWEEP_LO, p, q);
         const int j = hidx & 7, sh = 16 * (j & 1);
         const uint32_t wsel = (uint32_t)(j >> 1);
         const uint32_t rw = wsel == 0 ? r[0] : wsel == 1 ? r[1] : wsel == 2 ? r[2] : r[3];
@@ -345,7 +347,7 @@ __device__ __forceinline__ uint32_t decide_word(const float (&f)[CPL], float coe
 #pragma unroll
                 for (int i = 0; i < 4; ++i) r[i] = R[call][i];
             } else {
-                philox4x32(pp, sweep, blk8 + call, B200GRBM_STREAM_SWEEP, p, r);
+                philox4x32(pp, blk8 + call, sweep, B200GRBM_STREAM_SWEEP, p, r);
             }
 #pragma unroll
             for (int j = 7; j >= 0; --j) {
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(B200_SWEEP_MAX_THREADS, 1) gibbs_kernel(const 
 #pragma unroll
             for (int c4 = 0; c4 < CPL / 4; ++c4) {
                 uint32_t r[4];
-                philox4x32((uint32_t)pp, 0u, blk0 + c4, B200GRBM_STREAM_INIT, p, r);
+                philox4x32((uint32_t)pp, blk0 + c4, 0u, B200GRBM_STREAM_INIT, p, r);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) w |= (r[j] >> 31) << (4 * c4 + j);
             }
@@ -485,8 +487,8 @@ __global__ void __launch_bounds__(B200_SWEEP_MAX_THREADS, 1) gibbs_kernel(const 
             constexpr bool PRE = SlotUnroll<CPL>::value == 4 && MODE != MODE_SUPPLIED_EXACT;
             uint32_t R[2][4];
             if constexpr (PRE) {
-                philox4x32((uint32_t)pp, sweep, blk8, B200GRBM_STREAM_SWEEP, p, R[0]);
-                if ((CPL + 4 + 7) / 8 > 1 && shift4) philox4x32((uint32_t)pp, sweep, blk8 + 1, B200GRBM_STREAM_SWEEP, p, R[1]);
+                philox4x32((uint32_t)pp, blk8, sweep, B200GRBM_STREAM_SWEEP, p, R[0]);
+                if ((CPL + 4 + 7) / 8 > 1 && shift4) philox4x32((uint32_t)pp, blk8 + 1, sweep, B200GRBM_STREAM_SWEEP, p, R[1]);
             }
             if (SlotUnroll<CPL>::value == 4) {
                 // width is a multiple of 4 here (padding slots hold 2J = 0, nbr = own position)

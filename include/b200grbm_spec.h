@@ -33,7 +33,7 @@
  * Uniforms: either supplied by the caller (float in (0,1)) or drawn from
  * Philox4x32-10 with
  *   key      = (seed_lo, seed_hi)
- *   counter  = (visit position, sweep index, global chain id >> 3, stream)
+ *   counter  = (visit position, global chain id >> 3, sweep index, stream)
  *   halfword = global chain id & 7   (halfword j = bits 16 (j & 1) .. +15 of output word j >> 1)
  *   m23      = (halfword of stream 0) << 7  |  (halfword of stream 2) >> 9
  *   v        = as_float(m23 | 0x3f800000) - 1.0f + 2^-24   (exact; v in [2^-24, 1 - 2^-24])
@@ -42,7 +42,7 @@
  * whenever the low bits cannot change the outcome (the sm_100a kernel does; the oracle
  * always forms the full v) -- the contract is the decision with the full 23-bit v.
  * stream 0 = sweep uniforms (high 16 bits), stream 2 = sweep uniforms (low 7 bits),
- * stream 1 = initial state: counter = (visit position, 0, global chain id >> 2, 1),
+ * stream 1 = initial state: counter = (visit position, global chain id >> 2, 0, 1),
  *            word = global chain id & 3, bit 31 set -> +1.
  * The result therefore does not depend on launch geometry or GPU count.
  */

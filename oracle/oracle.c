@@ -152,7 +152,7 @@ static inline uint32_t halfword(const uint32_t out[4], unsigned j) { return (out
 void oracle_sweep_uniforms8(uint64_t seed, uint32_t pos, uint32_t sweep, uint32_t blk8, float v[8])
 {
     uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
-    uint32_t ctr[4] = { pos, sweep, blk8, B200GRBM_STREAM_SWEEP };
+    uint32_t ctr[4] = { pos, blk8, sweep, B200GRBM_STREAM_SWEEP };
     uint32_t hi[4], lo[4];
     oracle_philox4x32_10(ctr, key, hi);
     ctr[3] = B200GRBM_STREAM_SWEEP_LO;
@@ -174,7 +174,7 @@ void oracle_init_state(int n, int chains, int8_t *state, uint64_t seed, uint64_t
     for (int c = 0; c < chains; ++c) {
         for (int p = 0; p < n; ++p) {
             const uint64_t chain = chain_offset + (uint64_t)c;
-            uint32_t ctr[4] = { (uint32_t)p, 0u, (uint32_t)(chain >> 2), B200GRBM_STREAM_INIT };
+            uint32_t ctr[4] = { (uint32_t)p, (uint32_t)(chain >> 2), 0u, B200GRBM_STREAM_INIT };
             uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
             uint32_t out[4];
             oracle_philox4x32_10(ctr, key, out);

@@ -29,13 +29,13 @@ def test_uniform_is_open_interval_and_exact():
 
 
 def test_sweep_uniform_is_built_from_two_philox_streams():
-    """High 16 bits: halfword (chain & 7) of Philox(pos, sweep, chain >> 3, stream 0); low 7 bits: the top 7
+    """High 16 bits: halfword (chain & 7) of Philox(pos, chain >> 3, sweep, stream 0); low 7 bits: the top 7
     bits of the same halfword of stream 2 (include/b200grbm_spec.h)."""
     seed = 0x1234_5678_9ABC_DEF0
     key = (seed & 0xFFFFFFFF, seed >> 32)
     for pos, sweep, chain in [(0, 0, 0), (5, 3, 7), (5639, 999, 4095), (17, 2, 262143), (1, 1, 12)]:
-        hi = O.philox4x32_10((pos, sweep, chain >> 3, 0), key)
-        lo = O.philox4x32_10((pos, sweep, chain >> 3, 2), key)
+        hi = O.philox4x32_10((pos, chain >> 3, sweep, 0), key)
+        lo = O.philox4x32_10((pos, chain >> 3, sweep, 2), key)
         j = chain & 7
         hw = (hi[j >> 1] >> (16 * (j & 1))) & 0xFFFF
         lw = (lo[j >> 1] >> (16 * (j & 1))) & 0xFFFF
