@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .topology import IsingGraph
+from .topology import IsingGraph, round_cost
 
 __all__ = ["BlockGibbsSampler", "PersistentChains", "SampleSet", "DeviceGraph", "plan_launch", "plan_threads",
            "sweep_smem_bytes", "sweep_state_offset", "beta_schedule"]
@@ -60,21 +60,21 @@ def sweep_state_offset(n_tiles: int) -> int:
 
 
 def plan_threads(colour_sizes: Sequence[int], n: int, ell_width: int, smem_limit: int = SMEM_LIMIT) -> int:
-    """CTA size for the colour-round loop: among the multiples of 32 in [64, 768] whose two
-    tile stages fit in shared memory, take the largest one whose lane occupancy
-    ``min_c n_c / (ceil(n_c / T) T)`` is within 3 % of the best (more warps hide more latency:
-    measured on B200, P16: 736 threads (95.8 %) 4.81e11 updates/s vs 480 (97.9 %) 4.62e11)."""
+    """CTA size for the colour-round loop: among the multiples of 32 in [64, 768] whose two tile stages fit in
+    shared memory, the one with the lowest ``topology.round_cost`` -- rounds x warps per scheduler x a latency-hiding
+    penalty for narrow CTAs (measured on B200, P16: 736 threads 34.6 ms, 480 threads 36.4 ms at the same 48 warp
+    slots per sweep); ties go to the higher lane occupancy, then to the larger CTA."""
     sizes = [s for s in colour_sizes if s > 0] or [1]
     cands = []
     for t in range(64, 768 + 1, 32):
         n_tiles = sum(-(-s // t) for s in sizes)
         if sweep_smem_bytes(n, ell_width, t, n_tiles) > smem_limit:
             continue
-        cands.append((min(s / (-(-s // t) * t) for s in sizes), t))
+        occupancy = sum(sizes) / (n_tiles * t)
+        cands.append((round(round_cost(sizes, t), 6), -round(occupancy, 6), -t))
     if not cands:
         raise ValueError(f"graph with {n} spins and degree {ell_width} does not fit the sweep kernel's shared memory")
-    best = max(e for e, _ in cands)
-    return max(t for e, t in cands if e >= best - 0.03)
+    return -min(cands)[2]
 
 
 #: per-CTA cost model of a sweep launch, in "chains": time ~ waves * (weight * cpl + overhead).

@@ -24,6 +24,27 @@ def test_zephyr_z15_counts_and_colouring():
     assert np.bincount(col).tolist() == [1860] * 4
 
 
+def test_rounds_are_balanced_by_merging_colour_remainders():
+    """Pegasus P16: four colours of 1410 = 2 x 640 + 130 spins.  The visit order keeps the full chunks and merges
+    the four remainders into one independent class: 9 rounds of a 640-lane CTA instead of 8 of a 736-lane one
+    (45 instead of 48 warp slots per scheduler and sweep)."""
+    from image_generation_b200.topology import balance_rounds, round_cost
+    n, ei, ej, col = B.pegasus_graph(16)
+    g = B.IsingGraph.pegasus(16)
+    sizes = np.diff(g.colour_start).tolist()
+    assert sizes == [640] * 8 + [520]
+    assert not np.any(g.colour[ei] == g.colour[ej])                         # still a proper colouring
+    assert B.sampler.plan_threads(sizes, g.n, g.ell_width) == 640
+    assert round_cost(sizes, 640) < round_cost([1410] * 4, 736)
+    plain = B.IsingGraph.build(n, ei, ej, colour=col, balance=False)
+    assert np.diff(plain.colour_start).tolist() == [1410] * 4 and B.sampler.plan_threads([1410] * 4, n, 15) == 736
+    # nothing to gain on Zephyr Z15 (four colours of 1860, 480-lane CTAs) or on small graphs: colouring unchanged
+    nz, zi, zj, zc = B.zephyr_graph(15)
+    assert np.array_equal(balance_rounds(nz, zi, zj, zc, 20), zc)
+    assert np.diff(B.IsingGraph.pegasus(4).colour_start).tolist() == [66] * 4
+    assert np.array_equal(g.colour, B.IsingGraph.pegasus(16).colour)        # deterministic
+
+
 def test_ell_tables_are_consistent():
     g = B.IsingGraph.pegasus(3)
     assert g.n_pad % 32 == 0 and g.ell_width == g.degree.max()
@@ -72,6 +93,7 @@ def test_plan_launch():
     # cfg2: 4096 chains on 148 SMs -> 28 chains per CTA fills 147 SMs in one wave
     assert B.plan_launch(4096, [1410] * 4, 148, 5640, 15)[0] == 28
     assert B.plan_launch(4096, [1410] * 4, 148, 5640, 15) == (28, 736)
+    assert B.plan_launch(4096, [640] * 8 + [520], 148, 5640, 15) == (28, 640)   # P16 as IsingGraph.pegasus(16) orders it
     # many groups: two narrow single-stage CTAs per SM when that also needs fewer warp slots per sweep
     assert B.plan_launch(32768, [1860] * 4, 148, 7440, 20) == (28, 384)       # Z15: 20 rounds x 3 < 16 rounds x 4
     assert B.plan_launch(4096, [1860] * 4, 148, 7440, 20) == (28, 480)        # too few groups for two CTAs per SM
