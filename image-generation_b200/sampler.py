@@ -112,8 +112,8 @@ SMEM_PER_SM = 228 * 1024   # shared memory of one sm_100 SM (each resident CTA a
 def _plan_two_ctas(groups: int, colour_sizes: Sequence[int], sm_count: int, n: int, ell_width: int, threads: int) -> int:
     """Many chain groups: two narrow CTAs per SM, each with ONE tile stage (the launcher switches to that mode
     for <= 384 threads when both fit -- ``b200grbm_gibbs_sweeps``), give a scheduler twice the warps and let one
-    CTA's round barrier and copy latency be covered by the other.  Taken only when it also needs fewer warp
-    slots per sweep, ``rounds x ceil(warps / 4)``: Zephyr Z15 goes from 16 rounds x 4 (480 threads) to
+    CTA's round barrier and copy latency be covered by the other.  Taken only when ``topology.round_cost`` (warp
+    slots per sweep x latency-hiding penalty, with the warps of both CTAs counted) is lower: Zephyr Z15 goes from 16 rounds x 4 (480 threads) to
     20 rounds x 3 (384 threads; measured 44.9 -> 41.9 ms for 32 768 chains x 100 sweeps), Pegasus P16 stays
     at 8 rounds x 6 (736 threads: 48 slots either way, and the wide CTA measured 1 % faster)."""
     sizes = [s for s in colour_sizes if s > 0] or [1]
@@ -121,20 +121,18 @@ def _plan_two_ctas(groups: int, colour_sizes: Sequence[int], sm_count: int, n: i
     def rounds(t):
         return sum(-(-s // t) for s in sizes)
 
-    def slots(t):
-        return rounds(t) * -(-t // 128)
-
     tile = lambda t: (ell_width + 1) * t * 8
     if groups < 2 * sm_count or sweep_smem_bytes(n, ell_width, threads, rounds(threads)) \
             + max(0, rounds(threads) - 2) * tile(threads) <= SMEM_LIMIT:       # few groups, or resident tables
         return threads
-    best_t, best_slots = threads, slots(threads)
+    best_t, best_cost = threads, round_cost(sizes, threads)
     for t in range(384, 63, -32):
         single = sweep_smem_bytes(n, ell_width, t, rounds(t)) - tile(t)
         if 2 * (single + 1024) > SMEM_PER_SM:
             continue
-        if slots(t) < best_slots:
-            best_t, best_slots = t, slots(t)
+        cost = round_cost(sizes, t, ctas=2)
+        if cost < best_cost - 1e-9:
+            best_t, best_cost = t, cost
     return best_t
 
 

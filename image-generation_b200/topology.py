@@ -229,12 +229,13 @@ WARP_PENALTY = {1: 1.6, 2: 1.3, 3: 1.14, 4: 1.05, 5: 1.02, 6: 1.0}
 _SMEM_LIMIT = 227 * 1024
 
 
-def round_cost(class_sizes: Sequence[int], threads: int) -> float:
+def round_cost(class_sizes: Sequence[int], threads: int, ctas: int = 1) -> float:
     """Cost of one sweep for a CTA of ``threads`` lanes: rounds x warps per scheduler x latency-hiding penalty.
     Every independent class of the visit order is split into rounds of at most ``threads`` spins, and each round
-    costs every scheduler ``ceil(threads / 128)`` warp slots whatever the number of active lanes."""
+    costs every scheduler ``ceil(threads / 128)`` warp slots whatever the number of active lanes.  ``ctas`` CTAs
+    resident per SM multiply the warps that hide each other's latency, not the slots per chain."""
     w = -(-threads // 128)
-    return sum(-(-s // threads) for s in class_sizes if s > 0) * w * WARP_PENALTY.get(w, 1.0)
+    return sum(-(-s // threads) for s in class_sizes if s > 0) * w * WARP_PENALTY.get(min(6, w * ctas), 1.0)
 
 
 def _sweep_smem(n: int, width: int, threads: int, n_tiles: int) -> int:
@@ -262,6 +263,12 @@ def balance_rounds(n: int, ei: np.ndarray, ej: np.ndarray, colour: np.ndarray, w
     if not cands or k < 2:
         return colour
     plain = min(round_cost(sizes, t) for t in cands)
+    # the launcher can also run two narrow single-stage CTAs per SM (many chain groups): twice the warps per
+    # scheduler at the same slot count.  If the colouring as it is does at least as well that way, keep it.
+    for t in range(64, 385, 32):
+        single = _sweep_smem(n, width, t, sum(-(-s // t) for s in sizes)) - (width + 1) * t * 8
+        if 2 * (single + 1024) <= 228 * 1024:
+            plain = min(plain, round_cost(sizes, t, ctas=2))
     best = None
     for t in cands:
         if min(sizes) < t:
@@ -275,14 +282,35 @@ def balance_rounds(n: int, ei: np.ndarray, ej: np.ndarray, colour: np.ndarray, w
         return colour
     t = best[1]
     adj = _adjacency(n, ei, ej)
+    # spatial order: breadth-first rank from node 0 (restarted per component).  Remainders taken from segments of
+    # this order that lie far apart are compact clusters -- their neighbourhoods overlap, so few spins of the other
+    # colours get blocked -- and clusters of different colours do not touch.
+    rank = -np.ones(n, dtype=np.int64)
+    r_next = 0
+    for root in range(n):
+        if rank[root] >= 0:
+            continue
+        rank[root] = r_next
+        r_next += 1
+        frontier = [root]
+        while frontier:
+            nxt_frontier = []
+            for v in frontier:
+                for u in adj[v]:
+                    if rank[u] < 0:
+                        rank[u] = r_next
+                        r_next += 1
+                        nxt_frontier.append(u)
+            frontier = nxt_frontier
     blocked = np.zeros(n, dtype=bool)
     new = -np.ones(n, dtype=np.int32)
     nxt, leftovers = 0, []
     for ci in range(k):
         idx = np.flatnonzero(colour == ci)
         r = idx.size % t
+        by_rank = idx[np.argsort(rank[idx], kind="stable")]
         start = (idx.size * ci) // k                      # stagger the remainders of different colours
-        rot = np.concatenate([idx[start:], idx[:start]])
+        rot = np.concatenate([by_rank[start:], by_rank[:start]])
         chosen = [int(v) for v in rot if not blocked[v]][:r]
         if len(chosen) < r:
             return colour                                 # not enough mutually independent remainder spins

@@ -38,7 +38,8 @@ def test_rounds_are_balanced_by_merging_colour_remainders():
     assert round_cost(sizes, 640) < round_cost([1410] * 4, 736)
     plain = B.IsingGraph.build(n, ei, ej, colour=col, balance=False)
     assert np.diff(plain.colour_start).tolist() == [1410] * 4 and B.sampler.plan_threads([1410] * 4, n, 15) == 736
-    # nothing to gain on Zephyr Z15 (four colours of 1860, 480-lane CTAs) or on small graphs: colouring unchanged
+    # Zephyr Z15 (four colours of 1860): merging would give 15 rounds of 512 lanes (60 slots, 4 warps per scheduler),
+    # but the colouring as it is reaches 60 slots with two 384-lane CTAs per SM (6 warps): kept.  Small graphs: nothing to gain
     nz, zi, zj, zc = B.zephyr_graph(15)
     assert np.array_equal(balance_rounds(nz, zi, zj, zc, 20), zc)
     assert np.diff(B.IsingGraph.pegasus(4).colour_start).tolist() == [66] * 4
