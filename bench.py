@@ -283,19 +283,19 @@ def run_b200(args):
         "frac": achieved / smem_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one gibbs_kernel launch in the committed ncu --set full capture
         # (profiles/r1_gibbs_v5_ncu_summary.txt; 20-sweep launch, part of the final state write still sits in L2)
-        "traffic": 9806848 + 8990464, "traffic_note": "ncu capture of a 20-sweep launch; algorithmic HBM bytes per launch = state write 23.1 MB",
+        "traffic": 14288640 + 13467904, "traffic_note": "ncu capture of a 20-sweep launch; algorithmic HBM bytes per launch = state write 23.1 MB",
         "algorithmic_bytes_per_update": P16_MEAN_DEGREE + 1.0, "updates_per_launch": upd_per_launch,
         "kernel_ms": kernel_s * 1e3,
         "peak_source": f"SURVEY.md 8(d): n_SM({sms}) x 128 B/clk x SM clock sampled under load ({f_sm / 1e6:.0f} MHz)",
         "hbm": {"achieved": hbm_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": hbm_bytes / kernel_s / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
-        # the binding resource: warp-instruction issue.  41.1 warp instructions per 32 spin-updates is the count ncu
+        # the binding resource: warp-instruction issue.  40.5 warp instructions per 32 spin-updates is the count ncu
         # reports for this kernel (smsp__inst_executed.sum / updates, profiles/r1_gibbs_v5_ncu_summary.txt;
         # 56.6 before the lazy-acceptance kernel)
-        "issue": {"warp_instr_per_32_updates": 41.1, "peak_updates_per_s": sms * 4 * 32 / 41.1 * f_sm,
-                  "frac": (upd_per_launch / kernel_s) / (sms * 4 * 32 / 41.1 * f_sm),
-                  "ncu_issue_active_frac": 0.761},
+        "issue": {"warp_instr_per_32_updates": 40.5, "peak_updates_per_s": sms * 4 * 32 / 40.5 * f_sm,
+                  "frac": (upd_per_launch / kernel_s) / (sms * 4 * 32 / 40.5 * f_sm),
+                  "ncu_issue_active_frac": 0.764},
         "note": "state is bit-packed (28 chains per word) so the kernel is issue-bound, not byte-bound; see DESIGN.md 5.1",
     }
     cpu_rate, cores, sample = cpu_port_rate(g, h, J, CFG["beta"], args.cpu_seconds)

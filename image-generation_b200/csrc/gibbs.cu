@@ -371,11 +371,11 @@ __device__ __forceinline__ uint32_t decide_word(const float (&f)[CPL], float coe
     return neww;
 }
 
-#ifndef B200_SWEEP_MAX_THREADS
-#define B200_SWEEP_MAX_THREADS 768
-#endif
-template <int CPL, int MODE>
-__global__ void __launch_bounds__(B200_SWEEP_MAX_THREADS, 1) gibbs_kernel(const __grid_constant__ SweepParams p)
+// MAXT = largest CTA this instantiation may be launched with.  768 caps ptxas at 80 registers per thread (and is the
+// one two 384-thread CTAs per SM need); the 28-chain kernels also exist for MAXT = 640 -- 96 registers, a looser
+// schedule of the acceptance phase: 32.8 -> 32.0 ms on P16 (9 rounds of 640 lanes).
+template <int CPL, int MODE, int MAXT = 768>
+__global__ void __launch_bounds__(MAXT, 1) gibbs_kernel(const __grid_constant__ SweepParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);                 // 2 mbarriers (16 B, padded to 128)
@@ -621,8 +621,15 @@ static gibbs_fn pick_mode(int mode)
     }
 }
 
-static gibbs_fn pick(int cpl, int mode)
+static gibbs_fn pick(int cpl, int mode, int threads, bool one_cta_per_sm)
 {
+    if (cpl == 28 && threads <= 640 && one_cta_per_sm) {
+        switch (mode) {
+            case MODE_PHILOX_EXACT: return gibbs_kernel<28, MODE_PHILOX_EXACT, 640>;
+            case MODE_PHILOX_FAST: return gibbs_kernel<28, MODE_PHILOX_FAST, 640>;
+            default: return gibbs_kernel<28, MODE_SUPPLIED_EXACT, 640>;
+        }
+    }
     switch (cpl) {
         case 4: return pick_mode<4>(mode);
         case 8: return pick_mode<8>(mode);
@@ -702,8 +709,7 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
         return fail(B200GRBM_EINVAL, "gibbs_sweeps: supplied uniforms use the exact acceptance rule");
     const int mode = a->uniforms_dev != nullptr ? MODE_SUPPLIED_EXACT
                      : (a->accept == B200GRBM_ACCEPT_FAST ? MODE_PHILOX_FAST : MODE_PHILOX_EXACT);
-    gibbs_fn fn = pick(a->chains_per_lane, mode);
-    if (fn == nullptr)
+    if (pick(a->chains_per_lane, mode, a->threads, false) == nullptr)
         return fail(B200GRBM_EUNSUPPORTED, "gibbs_sweeps: chains_per_lane=%d not in {4,8,16,24,28,32}",
                     a->chains_per_lane);
     B200_TRY(require_device());
@@ -762,6 +768,7 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
         return fail(B200GRBM_EUNSUPPORTED,
                     "gibbs_sweeps: n=%d width=%d threads=%d need %zu B of shared memory (> %d); use fewer threads",
                     a->n, a->ell_width, a->threads, smem, smem_optin);
+    gibbs_fn fn = pick(a->chains_per_lane, mode, a->threads, !p.single);
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     fn<<<groups, a->threads, smem, (cudaStream_t)stream>>>(p);
