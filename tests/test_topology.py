@@ -46,6 +46,36 @@ def test_rounds_are_balanced_by_merging_colour_remainders():
     assert np.array_equal(g.colour, B.IsingGraph.pegasus(16).colour)        # deterministic
 
 
+def test_round_balancing_on_a_generic_four_colourable_lattice():
+    """King's graph 75 x 75 (8 neighbours, colours (x & 1, y & 1) of 1444 / 1406 / 1406 / 1369 spins): the same
+    arithmetic as Pegasus P16 -- every colour is two chunks of 640 plus a remainder, and the remainders can be
+    chosen mutually non-adjacent -- on a graph the generators know nothing about."""
+    from image_generation_b200.topology import balance_rounds
+    L = 75
+    idx = lambda x, y: x * L + y
+    ei, ej = [], []
+    for x in range(L):
+        for y in range(L):
+            for dx, dy in ((1, 0), (0, 1), (1, 1), (1, -1)):
+                if 0 <= x + dx < L and 0 <= y + dy < L:
+                    ei.append(idx(x, y))
+                    ej.append(idx(x + dx, y + dy))
+    ei, ej = np.array(ei, dtype=np.int32), np.array(ej, dtype=np.int32)
+    col = np.array([2 * (x & 1) + (y & 1) for x in range(L) for y in range(L)], dtype=np.int32)
+    new = balance_rounds(L * L, ei, ej, col, 8)
+    sizes = np.bincount(new).tolist()
+    assert not np.any(new[ei] == new[ej]) and new.min() == 0               # proper, every spin assigned
+    assert sizes == [640] * 8 + [505]
+    # a class is either a chunk of one colour or the merged remainders of all four
+    for c in range(8):
+        assert len(set(col[new == c].tolist())) == 1
+    assert sorted(np.bincount(col[new == 8]).tolist()) == sorted([1444 - 1280, 1406 - 1280, 1406 - 1280, 1369 - 1280])
+    g = B.IsingGraph.build(L * L, ei, ej, colour=col)
+    assert np.diff(g.colour_start).tolist() == sizes and B.sampler.plan_threads(sizes, g.n, g.ell_width) == 640
+    # the graph the sampler sees is the same graph: edges, degrees and a bijective visit order
+    assert sorted(g.order.tolist()) == list(range(L * L)) and g.n_edges == ei.size
+
+
 def test_ell_tables_are_consistent():
     g = B.IsingGraph.pegasus(3)
     assert g.n_pad % 32 == 0 and g.ell_width == g.degree.max()
