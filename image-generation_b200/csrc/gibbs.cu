@@ -22,21 +22,23 @@
 //     8-byte entries, contiguous in global memory -- and streamed through a 2-stage
 //     shared-memory ring by the bulk-copy engine (cp.async.bulk + mbarrier complete_tx,
 //     SASS UBLKCP): the copy of round q+1 overlaps the arithmetic of round q, so no warp
-//     ever waits on an L2 load inside the neighbour loop.
+//     ever waits on an L2 load inside the neighbour loop.  Two more modes, picked by the
+//     launcher: all tiles resident (small graphs), and one stage with two CTAs per SM.
 //   * Same-colour spins are never adjacent, so the parallel colour step equals the
 //     sequential sweep in visit order; W[p] is written in place and __syncthreads()
 //     separates rounds.
 //   * Uniforms: Philox4x32-10 keyed by (seed; visit position, global chain / 8, sweep) --
 //     one call yields the high 16 bits of the uniforms of 8 chains of the lane; the low 7
 //     bits live in a second stream that is only evaluated when a decision depends on them --
-//     so trajectories do not depend on CPL, CTA size, grid or GPU count.  The chain block sits in counter
-//     word 1, which enters the first round only through an XOR: the calls of one lane-task (same position
-//     and sweep, consecutive blocks) share the multiplies of rounds 1-3 that do not depend on it.  Round keys are
-//     precomputed on the host into the kernel parameter block (uniform-register operands).
+//     so trajectories do not depend on CPL, CTA size, grid or GPU count.  The chain block
+//     sits in counter word 1, which enters the first round only through an XOR: the calls
+//     of one lane-task (same position and sweep, consecutive blocks) share the multiplies
+//     of rounds 1-3 that do not depend on it.  Round keys are precomputed on the host into
+//     the kernel parameter block (uniform-register operands).
 //   * Lazy exact acceptance: the contract decision  fmaf(v, exp2_poly(x), v) < 1  is first
 //     bracketed with MUFU.EX2 and the 16-bit midpoint uniform; only when the bracket
 //     (2^-17 (1 + e) on v, 2^-20 relative on e) contains the threshold -- about 2e-5 of the
-//     decisions -- is the lane-task redone with the polynomial and the full 23-bit uniform.
+//     decisions -- is that decision redone with the polynomial and the full 23-bit uniform.
 //     The result is bit-identical to evaluating the contract everywhere (oracle/oracle.c).
 #include "common.cuh"
 
@@ -216,13 +218,12 @@ __device__ __forceinline__ uint32_t kernel_to_dense(uint32_t w)
     return (w & 0x7fu) | ((w >> 1) & 0x3f80u) | ((w >> 2) & 0x1fc000u) | ((w >> 3) & 0xfe00000u);
 }
 
-// Slots of a lane-task are consumed UNROLL at a time.  Large groups (CPL >= 16) hide the
-// LDS -> LDS dependency (entry, then the state word it points at) behind CPL predicated adds
-// per slot, so a 1-deep software pipeline is enough and keeps the register count at the
-// 80-register budget of a 736-thread CTA.  Small groups (CPL <= 8: few chains spread over
-// many CTAs, e.g. the reference's 256 reads) have almost no arithmetic per slot; there the
-// loads of four slots are issued together so a round costs two shared-memory latencies per
-// four slots instead of two per slot.
+// How a lane-task walks its neighbour slots.  Large groups (CPL >= 16, value 1): slot 0 initialises the
+// fields, then seven slots per loop iteration -- the other warps of the scheduler cover the LDS -> LDS
+// dependency (entry, then the state word it points at).  Small groups (CPL <= 8, value 4: few chains spread
+// over many CTAs, e.g. the reference's 256 reads) are latency-bound with one or two warps per scheduler: the
+// Philox words are drawn first and the loads of eight (then four) slots are issued together, so a round costs
+// two shared-memory latencies per batch instead of two per slot; the tables pad the width to a multiple of 4.
 template <int CPL>
 struct SlotUnroll { static constexpr int value = CPL <= 8 ? 4 : 1; };
 
