@@ -134,6 +134,32 @@ def test_plan_launch():
         assert cpl in (4, 8, 16, 24, 28, 32) and 64 <= threads <= 768
 
 
+def test_planner_invariants_over_random_graph_shapes():
+    """Whatever the class sizes, chain count and degree: the plan is launchable (CTA size a multiple of 32 in
+    [64, 768], two tile stages -- or, for the narrow two-CTA plans, one -- fit in shared memory, chains per lane
+    supported) and never costs more than the widest feasible CTA."""
+    from image_generation_b200.sampler import SMEM_LIMIT, SMEM_PER_SM, plan_threads, sweep_smem_bytes
+    from image_generation_b200.topology import round_cost
+    rng = np.random.default_rng(42)
+    for _ in range(300):
+        k = int(rng.integers(1, 12))
+        sizes = [int(x) for x in rng.integers(1, 2500, size=k)]
+        n, width = sum(sizes), int(rng.integers(1, 24))
+        if n * 4 > 100 * 1024:
+            continue
+        chains = int(rng.choice([1, 7, 256, 4096, 50000, 262144]))
+        cpl, t = B.plan_launch(chains, sizes, 148, n, width)
+        assert cpl in (4, 8, 16, 24, 28, 32) and t % 32 == 0 and 64 <= t <= 768
+        rounds = sum(-(-s // t) for s in sizes)
+        two_stage = sweep_smem_bytes(n, width, t, rounds)
+        if two_stage > SMEM_LIMIT:                      # only the single-stage two-CTA plan may exceed it
+            assert t <= 384 and 2 * (two_stage - (width + 1) * t * 8 + 1024) <= SMEM_PER_SM
+        t1 = plan_threads(sizes, n, width)
+        assert sweep_smem_bytes(n, width, t1, sum(-(-s // t1) for s in sizes)) <= SMEM_LIMIT
+        feasible = [c for c in range(64, 769, 32) if sweep_smem_bytes(n, width, c, sum(-(-s // c) for s in sizes)) <= SMEM_LIMIT]
+        assert round_cost(sizes, t1) <= min(round_cost(sizes, c) for c in feasible) + 1e-9
+
+
 def test_beta_schedule():
     assert np.all(B.beta_schedule(5) == 1.0)
     s = B.beta_schedule(4, (0.1, 1.0))
