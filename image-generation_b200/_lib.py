@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libb200grbm.so")
 
 ACCEPT_EXACT = 0
 ACCEPT_FAST = 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class B200Error(RuntimeError):
@@ -75,13 +75,20 @@ SIGNATURES = {
     "b200grbm_edge_stats": ([_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
     "b200grbm_energy_forward": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
     "b200grbm_energy_backward": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _i32),
+    "b200grbm_energy_grad_x": ([_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
     "b200grbm_energy_i8": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
     "b200grbm_energy_packed": ([_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
     "b200grbm_mmd_forward_f32": ([_vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _vp], _i32),
     "b200grbm_mmd_pack_i8": ([_vp, _i32, _i32, _i32, _vp, _vp], _i32),
+    "b200grbm_mmd_hist_i8": ([_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "b200grbm_mmd_eval_hist": ([_vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _vp], _i32),
     "b200grbm_mmd_forward_i8": ([_vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _vp, _vp], _i32),
-    "b200grbm_mmd_coef_i8": ([_vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _f32, _f32, _vp, _vp, _vp, _i32,
-                              _vp], _i32),
+    "b200grbm_spin_extract_f32": ([_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _f32, _vp], _i32),
+    "b200grbm_spin_extract_i8": ([_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _f32, _vp], _i32),
+    "b200grbm_transpose_i8": ([_vp, _i32, _i32, _i32, _vp, _i32, _vp], _i32),
+    "b200grbm_mmd_coef_i8": ([_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _f32, _f32, _vp, _vp,
+                              _i32, _i32, _i32, _vp, _vp, _vp], _i32),
+    "b200grbm_mmd_grad_i8": ([_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp], _i32),
     "b200grbm_gemm_bf16_tn": ([_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp], _i32),
     "b200grbm_mmd_forward_bf16": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _vp], _i32),
     "b200grbm_mmd_coef_bf16": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _f32, _f32, _vp, _vp, _i32,

@@ -12,18 +12,21 @@
 //   * contracts them with tcgen05.mma.kind::i8 (int8 x int8 -> int32, exact) into a
 //     128 x 256 accumulator tile in TMEM (two accumulator stages = all 512 columns, so the
 //     epilogue of tile t overlaps the MMAs of tile t+1),
-//   * and in the epilogue maps each Gram entry through a (D+1)-entry look-up table held in
-//     shared memory -- LUT[h] = distance (pass 1, for the data-dependent bandwidth) or
-//     sum_u exp(-t_h / (bw * mult_u)) (pass 2), computed once in float64 -- and reduces the
-//     xx / yy / xy block sums in registers.  Nothing of size m^2 touches HBM.
-// Only the upper triangle of 128 x 256 tiles is visited (the kernel matrix is symmetric).
+//   * forward (TC_PASS_HIST): the epilogue counts the Gram entries of the tile per Hamming distance
+//     (mmd_hist.cuh: shared-memory integer atomics, three (D+1)-bin histograms xx / yy / xy); ONE pass
+//     yields the distance sum for the data-dependent bandwidth AND the three block sums, evaluated
+//     afterwards in float64 by mmd_eval_hist_kernel.  Nothing of size m^2 touches HBM;
+//   * backward (TC_PASS_COEF): the epilogue maps each entry through a (D+1)-entry look-up table of
+//     dk/dt-coefficients and writes them as 2 or 3 int8 fixed-point digit planes for the int8 GEMM
+//     of gemm_i8.cu, together with their exact integer row sums.
+// Only the upper triangle of 128 x 256 tiles is visited in the forward pass (the kernel matrix is
+// symmetric); `shard_rank / shard_world` deal the tiles of the enumeration round-robin over ranks.
 //
 // Warp roles (320 threads, one persistent CTA per SM): warp 0 lane 0 = TMA producer,
 // warp 1 = TMEM allocator + (lane 0) MMA issuer, warps 2..9 = epilogue (two column halves x
 // four TMEM lane quarters).
-#include "tc_common.cuh"
+#include "mmd_hist.cuh"
 
-#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -41,7 +44,7 @@ constexpr int TC_THREADS = 320;
 constexpr int EPI_WARPS = 8;
 constexpr uint32_t TMEM_COLS = 512;
 
-enum { TC_PASS_DIST = 0, TC_PASS_KERNEL = 1, TC_PASS_COEF = 2 };
+enum { TC_PASS_HIST = 0, TC_PASS_COEF = 2 };
 constexpr int TC_MAX_SB = 136;          // up to 16 super-blocks per side (m <= 65536)
 constexpr int TC_SB_ROWS = 32, TC_SB_COLS = 16;   // tiles per super-block: 32 x 128 rows, 16 x 256 columns
 
@@ -51,14 +54,17 @@ struct TcParams {
     int tiles_m, tiles_n, j0, p0, total_tiles;
     int stages;
     int pass;
-    const float *lut;   // [d + 1]
-    double *sums;       // [4]
-    // TC_PASS_COEF: backward coefficients A[a][b] = w * c(h_ab), written as a bf16 (hi, lo) pair
-    int tiles_mx;       // row tiles covering the x rows
-    int m_pad;          // row pitch (elements) of coef_hi / coef_lo, multiple of 64
-    float w_xx, w_xy;
-    __nv_bfloat16 *coef_hi, *coef_lo;
-    // L2-sized super-blocks of the tile triangle (forward passes): 4096 x 4096 entries = 32 x 16 tiles per
+    int shard_rank, shard_world;        // forward: this launch contracts tiles t = shard_rank (mod shard_world)
+    unsigned long long *hist;           // TC_PASS_HIST: [3][d + 1] ordered-pair counts per Hamming distance
+    // TC_PASS_COEF: backward coefficients A[a][b] = w * c(h_ab) as n_planes base-256 int8 digits (most significant
+    // plane first), rows row0 .. row0 + n_rows - 1 of the stacked matrix against every column
+    const float *lut;                   // [d + 1]  c(h) / max|c| * Q
+    int row0, n_rows, tiles_rows;       // row tiles covering the requested rows
+    int m_pad, rows_alloc, n_planes;    // plane p = planes + p * rows_alloc * m_pad, row pitch m_pad
+    float r_xx, r_xy;                   // w_xx / max(|w_xx|, |w_xy|), w_xy / max(...)
+    int8_t *planes;
+    long long *rowsum;                  // [n_rows] integer row sums of the quantised coefficients (accumulating)
+    // L2-sized super-blocks of the tile triangle (forward pass): 4096 x 4096 entries = 32 x 16 tiles per
     // block pair, so the rows a wave of CTAs touches (2 x 23 MB at D = 5640) stay resident in one L2 partition
     int sb_count;                       // 0 -> plain column-major triangle
     int sb_start[TC_MAX_SB + 1];
@@ -66,18 +72,11 @@ struct TcParams {
 };
 
 // upper-triangle tile enumeration: column tile j ascending, row tiles i = 0 .. min(tiles_m, 2j+2) - 1
-// LUT index = Hamming distance (D - a.b) / 2; clamped so that rows that are not +-1 (caller error)
-// can never read outside the table
-__device__ __forceinline__ int lut_index(int two_d, int gram, int d)
-{
-    return min(max((two_d - 2 * gram) >> 2, 0), d);
-}
-
 __device__ __forceinline__ void tile_coords(const TcParams &p, int t, int &i, int &j)
 {
-    if (p.pass == TC_PASS_COEF) {          // full rectangle: x rows against every column
-        i = t % p.tiles_mx;
-        j = t / p.tiles_mx;
+    if (p.pass == TC_PASS_COEF) {          // full rectangle: the requested rows against every column
+        i = t % p.tiles_rows;
+        j = t / p.tiles_rows;
         return;
     }
     int tm = p.tiles_m, j0 = p.j0, p0 = p.p0, ibase = 0, jbase = 0;
@@ -112,6 +111,12 @@ __device__ __forceinline__ void tile_coords(const TcParams &p, int t, int &i, in
     j += jbase;
 }
 
+// tiles of this launch: local index u -> global enumeration index
+__device__ __forceinline__ int local_tiles(const TcParams &p)
+{
+    return p.total_tiles > p.shard_rank ? (p.total_tiles - p.shard_rank + p.shard_world - 1) / p.shard_world : 0;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                     const TcParams p)
 {
@@ -122,13 +127,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
     unsigned char *stage_base = smem;                                        // S x 48 KB, 1024-aligned
-    float *lut = reinterpret_cast<float *>(smem + (size_t)S * STAGE_BYTES);  // d + 1 floats
-    const size_t lut_bytes = ((size_t)(p.d + 1) * 4 + 15) / 16 * 16;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE_BYTES + lut_bytes);
+    // d + 1 words: histogram counters (forward) or the coefficient table (backward)
+    uint32_t *table = reinterpret_cast<uint32_t *>(smem + (size_t)S * STAGE_BYTES);
+    const size_t table_bytes = ((size_t)(p.d + 1) * 4 + 15) / 16 * 16;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE_BYTES + table_bytes);
     // bars: full[S], empty[S], tmem_full[2], tmem_empty[2]; then the TMEM base address
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 4);
     const uint32_t full0 = smem_addr(bars), empty0 = full0 + 8u * S, tfull0 = empty0 + 8u * S, tempty0 = tfull0 + 16u;
-    __shared__ double red[3][EPI_WARPS];
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { bar_init(full0 + 8u * s, 1); bar_init(empty0 + 8u * s, 1); }
@@ -136,32 +141,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)),
-                     "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 1) tmem_alloc(smem_addr(tmem_slot), TMEM_COLS);
+    if (p.pass == TC_PASS_COEF) {
+        for (int k = threadIdx.x; k <= p.d; k += blockDim.x) table[k] = f2u(p.lut[k]);
+    } else {
+        for (int k = threadIdx.x; k <= p.d; k += blockDim.x) table[k] = 0u;
     }
-    for (int k = threadIdx.x; k <= p.d; k += blockDim.x) lut[k] = p.lut[k];
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    const int n_local = local_tiles(p);
+    const int row_origin = p.pass == TC_PASS_COEF ? p.row0 : 0;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int u = blockIdx.x; u < n_local; u += gridDim.x) {
                 int ti, tj;
-                tile_coords(p, t, ti, tj);
+                tile_coords(p, u * p.shard_world + p.shard_rank, ti, tj);
                 for (int kb = 0; kb < p.n_kblocks; ++kb) {
                     bar_wait(empty0 + 8u * s, ph ^ 1u);
                     const uint32_t fb = full0 + 8u * s;
                     const uint32_t a_dst = smem_addr(stage_base + (size_t)s * STAGE_BYTES);
                     bar_expect_tx(fb, STAGE_BYTES);
-                    tma_load_2d(a_dst, &tmap, kb * BK, ti * BM, fb);
+                    tma_load_2d(a_dst, &tmap, kb * BK, row_origin + ti * BM, fb);
                     tma_load_2d(a_dst + A_BYTES, &tmap, kb * BK, tj * BN, fb);
                     tma_load_2d(a_dst + A_BYTES + A_BYTES, &tmap, kb * BK, tj * BN + 128, fb);
                     if (++s == S) { s = 0; ph ^= 1u; }
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
             int s = 0;
             uint32_t ph = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            for (int u = blockIdx.x; u < n_local; u += gridDim.x, ++it) {
                 const uint32_t acc = (uint32_t)it & 1u, acc_ph = ((uint32_t)it >> 1) & 1u;
                 bar_wait(tempty0 + 8u * acc, acc_ph ^ 1u);          // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -196,77 +202,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
             }
         }
     } else {
-        // ===================== epilogue: TMEM -> LUT -> block sums =====================
+        // ===================== epilogue =====================
         const int ew = warp - 2;                 // 0..7
         const int quarter = warp & 3;            // TMEM lane quarter this warp may access
         const int half = ew >> 2;                // column half of the accumulator
-        double s_xx = 0.0, s_yy = 0.0, s_xy = 0.0;
+        const int epi_tid = threadIdx.x - 64;
         const int two_d = 2 * p.d;
+        HistAccumulator hacc = {table, p.hist, p.d, -1};
+        const float *lut = reinterpret_cast<const float *>(table);
         int it = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        for (int u = blockIdx.x; u < n_local; u += gridDim.x, ++it) {
             int ti, tj;
-            tile_coords(p, t, ti, tj);
+            tile_coords(p, u * p.shard_world + p.shard_rank, ti, tj);
             const uint32_t acc = (uint32_t)it & 1u, acc_ph = ((uint32_t)it >> 1) & 1u;
-            const int row0 = ti * BM, col0 = tj * BN;
+            const int row0 = row_origin + ti * BM, col0 = tj * BN;
             const int row = row0 + quarter * 32 + lane;
-            const bool strict_upper = ti < 2 * tj;          // every column of the tile is right of every row
-            const bool rows_x = row0 + BM <= p.m_x, rows_y = row0 >= p.m_x;
-            const bool cols_x = col0 + BN <= p.m_x, cols_y = col0 >= p.m_x;
-            const bool pure = strict_upper && (row0 + BM <= p.m) && (col0 + BN <= p.m) && (rows_x || rows_y) &&
-                              (cols_x || cols_y);
+            bool pure = false;
+            if (p.pass == TC_PASS_HIST) {
+                const bool strict_upper = ti < 2 * tj;          // every column of the tile is right of every row
+                const bool rows_x = row0 + BM <= p.m_x, rows_y = row0 >= p.m_x;
+                const bool cols_x = col0 + BN <= p.m_x, cols_y = col0 >= p.m_x;
+                pure = strict_upper && (row0 + BM <= p.m) && (col0 + BN <= p.m) && (rows_x || rows_y) && (cols_x || cols_y);
+                if (pure) {
+                    const int type = rows_x && cols_x ? HIST_XX : (rows_y && cols_y ? HIST_YY : HIST_XY);
+                    if (type != hacc.type) {         // uniform over the epilogue threads: same tile sequence
+                        hacc.flush(epi_tid, EPI_WARPS * 32);
+                        hacc.type = type;
+                    }
+                }
+            }
             bar_wait(tfull0 + 8u * acc, acc_ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float a_xx = 0.f, a_yy = 0.f, a_xy = 0.f;
+            long long row_q = 0;
 #pragma unroll 1
             for (int chunk = 0; chunk < 4; ++chunk) {
                 uint32_t v[32];
                 const int cbase = half * 128 + chunk * 32;
                 __syncwarp();                                   // tcgen05.ld is .sync.aligned
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + (uint32_t)cbase, v);
-                if (p.pass == TC_PASS_COEF) {
-                    // 32 consecutive coefficients of this thread's row -> bf16 hi / lo halves, 64 B each
-                    if (row < p.m_x) {
-                        uint32_t hi[16], lo[16];
-#pragma unroll
-                        for (int c = 0; c < 32; c += 2) {
-                            float cf[2];
-#pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                const int col = col0 + cbase + c + q;
-                                const float raw = lut[lut_index(two_d, (int)v[c + q], p.d)];
-                                cf[q] = (col < p.m && col != row) ? raw * (col < p.m_x ? p.w_xx : p.w_xy) : 0.f;
-                            }
-                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(cf[0], cf[1]);
-                            const __nv_bfloat162 l2 = __floats2bfloat162_rn(cf[0] - __low2float(h2), cf[1] - __high2float(h2));
-                            hi[c >> 1] = *reinterpret_cast<const uint32_t *>(&h2);
-                            lo[c >> 1] = *reinterpret_cast<const uint32_t *>(&l2);
-                        }
-                        const size_t off = (size_t)row * p.m_pad + (size_t)(col0 + cbase);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (col0 + cbase + 8 * q < p.m_pad) {
-                                *reinterpret_cast<uint4 *>(p.coef_hi + off + 8 * q) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-                                *reinterpret_cast<uint4 *>(p.coef_lo + off + 8 * q) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-                            }
-                        }
-                    }
-                } else if (pure) {
-                    float part = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) part += lut[lut_index(two_d, (int)v[c], p.d)];
-                    a_xx += part;            // sorted into its block after the loop
-                } else {
+                if (p.pass == TC_PASS_HIST) {
+                    hist_count_chunk(v, pure, hacc, two_d, row, col0 + cbase, p.m_x, p.m);
+                } else if (row - p.row0 < p.n_rows) {
+                    // 32 consecutive coefficients of this thread's row -> base-256 digits, 32 bytes per plane
+                    uint32_t dig[3][8];
+                    int part = 0;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const int col = col0 + cbase + c;
-                        if (row < p.m && col < p.m && col >= row) {
-                            const float kv = lut[lut_index(two_d, (int)v[c], p.d)];
-                            const bool rx = row < p.m_x, cx = col < p.m_x;
-                            const float w = col == row ? 1.f : 2.f;
-                            if (p.pass == TC_PASS_DIST) a_xx += w * kv;
-                            else if (rx && cx) a_xx += w * kv;
-                            else if (!rx && !cx) a_yy += w * kv;
-                            else a_xy += kv;
+                        int q = 0;
+                        if (col < p.m && col != row)
+                            q = __float2int_rn(lut[hamming_index(two_d, (int)v[c], p.d)] * (col < p.m_x ? p.r_xx : p.r_xy));
+                        part += q;
+                        // signed base-256 digits, least significant first: q = d0 + 256 d1 + 65536 d2
+                        const int d0 = (q << 24) >> 24, q1 = (q - d0) >> 8;
+                        const int d1 = (q1 << 24) >> 24, d2 = (q1 - d1) >> 8;
+                        const int sh = 8 * (c & 3);
+                        if ((c & 3) == 0) { dig[0][c >> 2] = 0u; dig[1][c >> 2] = 0u; dig[2][c >> 2] = 0u; }
+                        dig[0][c >> 2] |= (uint32_t)(d0 & 0xff) << sh;
+                        dig[1][c >> 2] |= (uint32_t)(d1 & 0xff) << sh;
+                        dig[2][c >> 2] |= (uint32_t)(d2 & 0xff) << sh;
+                    }
+                    row_q += part;
+                    if (col0 + cbase < p.m_pad) {              // m_pad is a multiple of 128: whole 32-byte groups
+                        const size_t off = (size_t)(row - p.row0) * p.m_pad + (size_t)(col0 + cbase);
+                        const size_t plane_stride = (size_t)p.rows_alloc * p.m_pad;
+                        const auto store_plane = [&](int pl, const uint32_t (&src)[8]) {
+                            uint4 *dst = reinterpret_cast<uint4 *>(p.planes + (size_t)pl * plane_stride + off);
+                            dst[0] = make_uint4(src[0], src[1], src[2], src[3]);
+                            dst[1] = make_uint4(src[4], src[5], src[6], src[7]);
+                        };
+                        if (p.n_planes == 3) {                     // plane 0 = most significant digit
+                            store_plane(0, dig[2]);
+                            store_plane(1, dig[1]);
+                            store_plane(2, dig[0]);
+                        } else {
+                            store_plane(0, dig[1]);
+                            store_plane(1, dig[0]);
                         }
                     }
                 }
@@ -275,59 +286,116 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) bar_arrive(tempty0 + 8u * acc);
-            if (pure) {
-                const double v2 = 2.0 * (double)a_xx;
-                if (p.pass == TC_PASS_DIST) s_xx += v2;
-                else if (rows_x && cols_x) s_xx += v2;
-                else if (rows_y && cols_y) s_yy += v2;
-                else s_xy += (double)a_xx;
-            } else {
-                s_xx += (double)a_xx; s_yy += (double)a_yy; s_xy += (double)a_xy;
-            }
+            if (p.pass == TC_PASS_COEF && row - p.row0 < p.n_rows && row_q != 0)
+                atomicAdd(reinterpret_cast<unsigned long long *>(p.rowsum + (row - p.row0)), (unsigned long long)row_q);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s_xx += __shfl_xor_sync(0xffffffffu, s_xx, o);
-            s_yy += __shfl_xor_sync(0xffffffffu, s_yy, o);
-            s_xy += __shfl_xor_sync(0xffffffffu, s_xy, o);
-        }
-        if (lane == 0) { red[0][ew] = s_xx; red[1][ew] = s_yy; red[2][ew] = s_xy; }
+        if (p.pass == TC_PASS_HIST) hacc.flush(epi_tid, EPI_WARPS * 32);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x < 3) {
-        double tot = 0.0;
-        for (int w = 0; w < EPI_WARPS; ++w) tot += red[threadIdx.x][w];
-        if (p.pass == TC_PASS_DIST) { if (threadIdx.x == 0) atomicAdd(p.sums + 3, tot); }
-        else if (p.pass == TC_PASS_KERNEL && tot != 0.0) atomicAdd(p.sums + threadIdx.x, tot);
-    }
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
-// LUT over the Hamming distance h = 0..d:  t_h = 2 sqrt(h) (or 4h when squared)
-__global__ void mmd_lut_kernel(int pass, int d, int m, int n_kernels, float mul_factor, int squared, float bandwidth,
-                               const double *sums, float *lut)
+// distance of two +-1 rows at Hamming distance h:  ||a - b|| = 2 sqrt(h)  (squared: 4 h)
+__device__ __forceinline__ double hamming_to_t(int h, int squared) { return squared ? 4.0 * (double)h : 2.0 * sqrt((double)h); }
+
+__device__ double block_reduce_sum(double v, double *scratch)
 {
-    const int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h > d) return;
-    const double t = squared ? 4.0 * (double)h : 2.0 * sqrt((double)h);
-    if (pass == TC_PASS_DIST) { lut[h] = (float)t; return; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) t += scratch[w];    // same order in every thread
+    return t;
+}
+
+// Histograms -> sums[4] = { sum_{a,b in x} k, sum_{a,b in y} k, sum_{a in x, b in y} k, sum_ab t_ab } in float64.
+// One block; the reductions run in a fixed order, so the result is bit-reproducible.
+__global__ void __launch_bounds__(1024) mmd_eval_hist_kernel(const unsigned long long *__restrict__ hist, int d, int m,
+                                                             int n_kernels, float mul_factor, int squared, float bandwidth,
+                                                             double *__restrict__ sums)
+{
+    __shared__ double scratch[32];
+    const size_t stride = (size_t)d + 1;
+    double dist = 0.0;
+    for (int h = threadIdx.x; h <= d; h += blockDim.x)
+        dist += hamming_to_t(h, squared) * ((double)hist[h] + (double)hist[stride + h] + 2.0 * (double)hist[2 * stride + h]);
+    dist = block_reduce_sum(dist, scratch);
+    const double mm = (double)m;
+    const double bw = bandwidth > 0.f ? (double)bandwidth : dist / (mm * mm - mm);
+    double inv_b[16];
+    for (int u = 0; u < n_kernels; ++u) inv_b[u] = 1.0 / (bw * pow((double)mul_factor, (double)(u - n_kernels / 2)));
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int h = threadIdx.x; h <= d; h += blockDim.x) {
+        const unsigned long long c0 = hist[h], c1 = hist[stride + h], c2 = hist[2 * stride + h];
+        if ((c0 | c1 | c2) == 0ull) continue;
+        const double t = hamming_to_t(h, squared);
+        double k = 0.0;
+        for (int u = 0; u < n_kernels; ++u) k += exp(-t * inv_b[u]);
+        s[0] += k * (double)c0;
+        s[1] += k * (double)c1;
+        s[2] += k * (double)c2;
+    }
+    for (int b = 0; b < 3; ++b) {
+        const double tot = block_reduce_sum(s[b], scratch);
+        if (threadIdx.x == 0) sums[b] = tot;
+    }
+    if (threadIdx.x == 0) sums[3] = dist;
+}
+
+// Backward coefficient table over the Hamming distance:  c(h) = (dk/dt)(dt/d||.||)/||.||  (multiplies x_a - z_b;
+// zero where the rows coincide), normalised to  lut[h] = c(h) / max|c| * Q  with Q the largest magnitude the
+// n_planes base-256 digits represent.  scale_out[0] = max|c| * max(|w_xx|, |w_xy|) / Q  undoes it after the GEMM.
+__global__ void __launch_bounds__(1024) mmd_coef_lut_kernel(int d, int m, int n_kernels, float mul_factor, int squared,
+                                                            float bandwidth, const double *__restrict__ sums, float w_xx,
+                                                            float w_xy, int n_planes, float *__restrict__ lut,
+                                                            double *__restrict__ scale_out)
+{
+    __shared__ double scratch[32];
     const double mm = (double)m;
     const double bw = bandwidth > 0.f ? (double)bandwidth : sums[3] / (mm * mm - mm);
-    double k = 0.0, dk = 0.0;                       // k(t) and dk/dt
-    for (int u = 0; u < n_kernels; ++u) {
-        const double b = bw * pow((double)mul_factor, (double)(u - n_kernels / 2));
-        const double e = exp(-t / b);
-        k += e;
-        dk -= e / b;
+    double cmax = 0.0;
+    for (int h = threadIdx.x; h <= d; h += blockDim.x) {
+        double c = 0.0;
+        if (h > 0) {
+            const double t = hamming_to_t(h, squared);
+            double dk = 0.0;
+            for (int u = 0; u < n_kernels; ++u) {
+                const double b = bw * pow((double)mul_factor, (double)(u - n_kernels / 2));
+                dk -= exp(-t / b) / b;
+            }
+            c = squared ? 2.0 * dk : dk / t;
+        }
+        cmax = fmax(cmax, fabs(c));
     }
-    if (pass == TC_PASS_KERNEL) { lut[h] = (float)k; return; }
-    // TC_PASS_COEF: (dk/dt) (dt/d||.||) / ||.||  -> multiplies (x_a - z_b);  zero where the rows coincide
-    lut[h] = h == 0 ? 0.f : (float)(squared ? 2.0 * dk : dk / t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = cmax;
+    __syncthreads();
+    cmax = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) cmax = fmax(cmax, scratch[w]);
+    const double Q = n_planes >= 3 ? 8355711.0 : 32639.0;        // 127 * (65536 + 256 + 1) / 127 * (256 + 1)
+    const double norm = cmax > 0.0 ? Q / cmax : 0.0;
+    for (int h = threadIdx.x; h <= d; h += blockDim.x) {
+        double c = 0.0;
+        if (h > 0) {
+            const double t = hamming_to_t(h, squared);
+            double dk = 0.0;
+            for (int u = 0; u < n_kernels; ++u) {
+                const double b = bw * pow((double)mul_factor, (double)(u - n_kernels / 2));
+                dk -= exp(-t / b) / b;
+            }
+            c = squared ? 2.0 * dk : dk / t;
+        }
+        lut[h] = (float)(c * norm);
+    }
+    if (threadIdx.x == 0) scale_out[0] = cmax * fmax(fabs((double)w_xx), fabs((double)w_xy)) / Q;
 }
 
 // sign-pack fp32 rows into the zero-padded int8 matrix the TMA descriptor reads
@@ -374,9 +442,9 @@ int32_t make_tensor_map_2d(CUtensorMap *map, const void *base, CUtensorMapDataTy
     return 0;
 }
 
-// CTA-pair version of the forward passes (mmd_tc2.cu)
-int32_t launch_gram_i8_2cta(const CUtensorMap &tmap, int m_x, int m, int d, int d_pad, int pass, const float *lut,
-                            double *sums, cudaStream_t st);
+// CTA-pair version of the forward pass (mmd_tc2.cu)
+int32_t launch_gram_i8_2cta(const CUtensorMap &tmap, int m_x, int m, int d, int d_pad, unsigned long long *hist,
+                            int shard_rank, int shard_world, cudaStream_t st);
 
 // Forward tile shape.  Measured on B200 (8192 + 8192 rows): while the sample matrix fits in L2 the single-CTA
 // kernel and the CTA-pair kernel run at the same k-block rate (742 vs 750 clk per 128-byte k-block at
@@ -389,6 +457,25 @@ static bool use_pair_kernel(int m, int d_pad)
     if (env != nullptr && env[0] == '2') return true;
     const int tiles = (m + 255) / 256;
     return tiles * (tiles + 1) / 2 >= 74 && (size_t)m * (size_t)d_pad > (size_t)100 << 20;
+}
+
+static int32_t gram_smem(int d, int *stages_out, size_t *smem_out, const char *who)
+{
+    int dev = 0, smem_optin = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t table_bytes = ((size_t)(d + 1) * 4 + 15) / 16 * 16;
+    int stages = 4;
+    size_t smem = 0;
+    for (; stages >= 2; --stages) {
+        smem = (size_t)stages * STAGE_BYTES + table_bytes + (2 * stages + 4) * 8 + 16;
+        if (smem + 1024 <= (size_t)smem_optin) break;
+    }
+    if (stages < 2)
+        return fail(B200GRBM_EUNSUPPORTED, "%s: d=%d needs a %zu B table, too large for shared memory", who, d, table_bytes);
+    *stages_out = stages;
+    *smem_out = smem + 1024;
+    return 0;
 }
 
 }  // namespace b200grbm
@@ -408,37 +495,28 @@ extern "C" int32_t b200grbm_mmd_pack_i8(const float *z_dev, int32_t m, int32_t d
     return 0;
 }
 
-extern "C" int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,
-                                           int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth,
-                                           float *lut_dev, double *sums_dev, void *stream)
+extern "C" int32_t b200grbm_mmd_hist_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,
+                                        int32_t shard_rank, int32_t shard_world, uint64_t *hist_dev, void *stream)
 {
     if (m_x <= 0 || m_y <= 0 || d <= 0 || d_pad < d || d_pad % 16 != 0)
-        return fail(B200GRBM_EINVAL, "mmd_forward_i8: m_x=%d m_y=%d d=%d d_pad=%d", m_x, m_y, d, d_pad);
-    if (n_kernels < 1 || n_kernels > 16 || !(mul_factor > 0.f))
-        return fail(B200GRBM_EINVAL, "mmd_forward_i8: n_kernels=%d mul_factor=%g", n_kernels, mul_factor);
-    if (!z_dev || !lut_dev || !sums_dev) return fail(B200GRBM_EINVAL, "mmd_forward_i8: NULL pointer argument");
+        return fail(B200GRBM_EINVAL, "mmd_hist_i8: m_x=%d m_y=%d d=%d d_pad=%d", m_x, m_y, d, d_pad);
+    if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world)
+        return fail(B200GRBM_EINVAL, "mmd_hist_i8: shard %d of %d", shard_rank, shard_world);
+    if (!z_dev || !hist_dev) return fail(B200GRBM_EINVAL, "mmd_hist_i8: NULL pointer argument");
     if ((reinterpret_cast<uintptr_t>(z_dev) & 15u) != 0)
-        return fail(B200GRBM_EINVAL, "mmd_forward_i8: z_dev must be 16-byte aligned (TMA)");
+        return fail(B200GRBM_EINVAL, "mmd_hist_i8: z_dev must be 16-byte aligned (TMA)");
     B200_TRY(require_device());
     cudaStream_t st = (cudaStream_t)stream;
     const int m = m_x + m_y;
-
-    int dev = 0, smem_optin = 0;
-    B200_CUDA(cudaGetDevice(&dev));
-    B200_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const size_t lut_bytes = ((size_t)(d + 1) * 4 + 15) / 16 * 16;
-    int stages = 4;
+    int stages = 0;
     size_t smem = 0;
-    for (; stages >= 2; --stages) {
-        smem = (size_t)stages * STAGE_BYTES + lut_bytes + (2 * stages + 4) * 8 + 16;
-        if (smem + 1024 <= (size_t)smem_optin) break;
-    }
-    if (stages < 2)
-        return fail(B200GRBM_EUNSUPPORTED, "mmd_forward_i8: d=%d needs a %zu B look-up table, too large for shared memory", d,
-                    lut_bytes);
+    B200_TRY(gram_smem(d, &stages, &smem, "mmd_hist_i8"));
 
     CUtensorMap tmap;
     B200_TRY(make_tensor_map_2d(&tmap, z_dev, CU_TENSOR_MAP_DATA_TYPE_UINT8, (uint64_t)d_pad, (uint64_t)m, (uint64_t)d_pad, BK, 128));
+    if (use_pair_kernel(m, d_pad))
+        return launch_gram_i8_2cta(tmap, m_x, m, d, d_pad, reinterpret_cast<unsigned long long *>(hist_dev), shard_rank,
+                                   shard_world, st);
 
     TcParams p = {};
     p.m_x = m_x; p.m = m; p.d = d;
@@ -449,8 +527,9 @@ extern "C" int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int
     p.p0 = p.j0 * (p.j0 + 1);
     p.total_tiles = p.p0 + (p.tiles_n - p.j0) * p.tiles_m;
     p.stages = stages;
-    p.lut = lut_dev;
-    p.sums = sums_dev;
+    p.pass = TC_PASS_HIST;
+    p.shard_rank = shard_rank; p.shard_world = shard_world;
+    p.hist = reinterpret_cast<unsigned long long *>(hist_dev);
     {   // super-block order (column block outer, row block inner); same tile set, L2-friendly order
         const int nb = (p.tiles_n + TC_SB_COLS - 1) / TC_SB_COLS;
         const char *env = getenv("B200GRBM_MMD_ORDER");
@@ -474,92 +553,100 @@ extern "C" int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int
             p.sb_start[k] = start;
             p.sb_count = k;
             if (start != p.total_tiles)
-                return fail(B200GRBM_EINVAL, "mmd_forward_i8: internal tile enumeration mismatch (%d vs %d)", start, p.total_tiles);
+                return fail(B200GRBM_EINVAL, "mmd_hist_i8: internal tile enumeration mismatch (%d vs %d)", start, p.total_tiles);
         }
     }
-
-    B200_CUDA(cudaFuncSetAttribute(mmd_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + 1024)));
+    B200_CUDA(cudaFuncSetAttribute(mmd_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int sms = sm_count() > 0 ? sm_count() : 148;
-    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-    B200_CUDA(cudaMemsetAsync(sums_dev, 0, 4 * sizeof(double), st));
-    const int lut_blocks = (d + 1 + 255) / 256;
-    const bool pair = use_pair_kernel(m, d_pad);
-    if (!(bandwidth > 0.f)) {
-        mmd_lut_kernel<<<lut_blocks, 256, 0, st>>>(TC_PASS_DIST, d, m, n_kernels, mul_factor, squared, bandwidth, sums_dev,
-                                                   lut_dev);
-        B200_CUDA(cudaGetLastError());
-        if (pair) {
-            B200_TRY(launch_gram_i8_2cta(tmap, m_x, m, d, d_pad, TC_PASS_DIST, lut_dev, sums_dev, st));
-        } else {
-            p.pass = TC_PASS_DIST;
-            mmd_gram_i8_kernel<<<grid, TC_THREADS, smem + 1024, st>>>(tmap, p);
-            B200_CUDA(cudaGetLastError());
-        }
-    }
-    mmd_lut_kernel<<<lut_blocks, 256, 0, st>>>(TC_PASS_KERNEL, d, m, n_kernels, mul_factor, squared, bandwidth, sums_dev,
-                                               lut_dev);
+    const int n_local = p.total_tiles > shard_rank ? (p.total_tiles - shard_rank + shard_world - 1) / shard_world : 0;
+    if (n_local == 0) return 0;
+    const int grid = n_local < sms ? n_local : sms;
+    mmd_gram_i8_kernel<<<grid, TC_THREADS, smem, st>>>(tmap, p);
     B200_CUDA(cudaGetLastError());
-    if (pair) {
-        B200_TRY(launch_gram_i8_2cta(tmap, m_x, m, d, d_pad, TC_PASS_KERNEL, lut_dev, sums_dev, st));
-    } else {
-        p.pass = TC_PASS_KERNEL;
-        mmd_gram_i8_kernel<<<grid, TC_THREADS, smem + 1024, st>>>(tmap, p);
-        B200_CUDA(cudaGetLastError());
-    }
     return 0;
 }
 
+extern "C" int32_t b200grbm_mmd_eval_hist(const uint64_t *hist_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t n_kernels,
+                                          float mul_factor, int32_t squared, float bandwidth, double *sums_dev, void *stream)
+{
+    if (m_x <= 0 || m_y <= 0 || d <= 0) return fail(B200GRBM_EINVAL, "mmd_eval_hist: m_x=%d m_y=%d d=%d", m_x, m_y, d);
+    if (n_kernels < 1 || n_kernels > 16 || !(mul_factor > 0.f))
+        return fail(B200GRBM_EINVAL, "mmd_eval_hist: n_kernels=%d mul_factor=%g", n_kernels, mul_factor);
+    if (!hist_dev || !sums_dev) return fail(B200GRBM_EINVAL, "mmd_eval_hist: NULL pointer argument");
+    B200_TRY(require_device());
+    mmd_eval_hist_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long *>(hist_dev), d,
+                                                              m_x + m_y, n_kernels, mul_factor, squared, bandwidth, sums_dev);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,
+                                           int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth,
+                                           uint64_t *hist_dev, double *sums_dev, void *stream)
+{
+    if (n_kernels < 1 || n_kernels > 16 || !(mul_factor > 0.f))
+        return fail(B200GRBM_EINVAL, "mmd_forward_i8: n_kernels=%d mul_factor=%g", n_kernels, mul_factor);
+    if (!hist_dev || !sums_dev) return fail(B200GRBM_EINVAL, "mmd_forward_i8: NULL pointer argument");
+    if (m_x <= 0 || m_y <= 0 || d <= 0) return fail(B200GRBM_EINVAL, "mmd_forward_i8: m_x=%d m_y=%d d=%d", m_x, m_y, d);
+    B200_TRY(require_device());
+    B200_CUDA(cudaMemsetAsync(hist_dev, 0, 3 * ((size_t)d + 1) * sizeof(uint64_t), (cudaStream_t)stream));
+    B200_TRY(b200grbm_mmd_hist_i8(z_dev, m_x, m_y, d, d_pad, 0, 1, hist_dev, stream));
+    return b200grbm_mmd_eval_hist(hist_dev, m_x, m_y, d, n_kernels, mul_factor, squared, bandwidth, sums_dev, stream);
+}
+
 extern "C" int32_t b200grbm_mmd_coef_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,
-                                        int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth,
-                                        const double *sums_dev, float w_xx, float w_xy, float *lut_dev,
-                                        void *coef_hi_dev, void *coef_lo_dev, int32_t m_pad, void *stream)
+                                        int32_t row0, int32_t n_rows, int32_t n_kernels, float mul_factor, int32_t squared,
+                                        float bandwidth, const double *sums_dev, float w_xx, float w_xy, float *lut_dev,
+                                        int8_t *planes_dev, int32_t n_planes, int32_t rows_alloc, int32_t m_pad,
+                                        int64_t *rowsum_dev, double *scale_dev, void *stream)
 {
     if (m_x <= 0 || m_y <= 0 || d <= 0 || d_pad < d || d_pad % 16 != 0)
         return fail(B200GRBM_EINVAL, "mmd_coef_i8: m_x=%d m_y=%d d=%d d_pad=%d", m_x, m_y, d, d_pad);
     const int m = m_x + m_y;
-    if (m_pad < m || m_pad % 64 != 0) return fail(B200GRBM_EINVAL, "mmd_coef_i8: m_pad=%d must be a multiple of 64 >= m=%d", m_pad, m);
+    if (row0 < 0 || n_rows <= 0 || row0 + n_rows > m_x)
+        return fail(B200GRBM_EINVAL, "mmd_coef_i8: rows [%d, %d) must lie inside the x block (m_x=%d)", row0, row0 + n_rows, m_x);
+    if (m_pad < m || m_pad % 128 != 0) return fail(B200GRBM_EINVAL, "mmd_coef_i8: m_pad=%d must be a multiple of 128 >= m=%d", m_pad, m);
+    if (n_planes < 2 || n_planes > 3) return fail(B200GRBM_EINVAL, "mmd_coef_i8: n_planes=%d must be 2 or 3", n_planes);
+    if (rows_alloc < n_rows) return fail(B200GRBM_EINVAL, "mmd_coef_i8: rows_alloc=%d < n_rows=%d", rows_alloc, n_rows);
     if (n_kernels < 1 || n_kernels > 16 || !(mul_factor > 0.f))
         return fail(B200GRBM_EINVAL, "mmd_coef_i8: n_kernels=%d mul_factor=%g", n_kernels, mul_factor);
-    if (!z_dev || !lut_dev || !sums_dev || !coef_hi_dev || !coef_lo_dev)
+    if (!z_dev || !lut_dev || !sums_dev || !planes_dev || !rowsum_dev || !scale_dev)
         return fail(B200GRBM_EINVAL, "mmd_coef_i8: NULL pointer argument");
-    if (((reinterpret_cast<uintptr_t>(z_dev) | reinterpret_cast<uintptr_t>(coef_hi_dev) | reinterpret_cast<uintptr_t>(coef_lo_dev)) & 15u) != 0)
-        return fail(B200GRBM_EINVAL, "mmd_coef_i8: z_dev / coef buffers must be 16-byte aligned");
+    if (((reinterpret_cast<uintptr_t>(z_dev) | reinterpret_cast<uintptr_t>(planes_dev)) & 15u) != 0)
+        return fail(B200GRBM_EINVAL, "mmd_coef_i8: z_dev / planes_dev must be 16-byte aligned");
     B200_TRY(require_device());
     cudaStream_t st = (cudaStream_t)stream;
-    int dev = 0, smem_optin = 0;
-    B200_CUDA(cudaGetDevice(&dev));
-    B200_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const size_t lut_bytes = ((size_t)(d + 1) * 4 + 15) / 16 * 16;
-    int stages = 4;
+    int stages = 0;
     size_t smem = 0;
-    for (; stages >= 2; --stages) {
-        smem = (size_t)stages * STAGE_BYTES + lut_bytes + (2 * stages + 4) * 8 + 16;
-        if (smem + 1024 <= (size_t)smem_optin) break;
-    }
-    if (stages < 2) return fail(B200GRBM_EUNSUPPORTED, "mmd_coef_i8: d=%d look-up table does not fit shared memory", d);
+    B200_TRY(gram_smem(d, &stages, &smem, "mmd_coef_i8"));
     CUtensorMap tmap;
     B200_TRY(make_tensor_map_2d(&tmap, z_dev, CU_TENSOR_MAP_DATA_TYPE_UINT8, (uint64_t)d_pad, (uint64_t)m, (uint64_t)d_pad, BK, 128));
+    const float wmax = fmaxf(fabsf(w_xx), fabsf(w_xy));
     TcParams p = {};
     p.m_x = m_x; p.m = m; p.d = d;
     p.n_kblocks = (d_pad + BK - 1) / BK;
     p.tiles_m = (m + BM - 1) / BM;
     p.tiles_n = (m_pad + BN - 1) / BN;        // cover the zero padding columns as well
-    p.tiles_mx = (m_x + BM - 1) / BM;
-    p.total_tiles = p.tiles_mx * p.tiles_n;
+    p.row0 = row0; p.n_rows = n_rows;
+    p.tiles_rows = (n_rows + BM - 1) / BM;
+    p.total_tiles = p.tiles_rows * p.tiles_n;
     p.stages = stages;
     p.pass = TC_PASS_COEF;
+    p.shard_rank = 0; p.shard_world = 1;
     p.lut = lut_dev;
-    p.sums = const_cast<double *>(sums_dev);
-    p.m_pad = m_pad; p.w_xx = w_xx; p.w_xy = w_xy;
-    p.coef_hi = reinterpret_cast<__nv_bfloat16 *>(coef_hi_dev);
-    p.coef_lo = reinterpret_cast<__nv_bfloat16 *>(coef_lo_dev);
-    B200_CUDA(cudaFuncSetAttribute(mmd_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + 1024)));
+    p.m_pad = m_pad; p.rows_alloc = rows_alloc; p.n_planes = n_planes;
+    p.r_xx = wmax > 0.f ? w_xx / wmax : 0.f;
+    p.r_xy = wmax > 0.f ? w_xy / wmax : 0.f;
+    p.planes = planes_dev;
+    p.rowsum = reinterpret_cast<long long *>(rowsum_dev);
+    B200_CUDA(cudaFuncSetAttribute(mmd_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int sms = sm_count() > 0 ? sm_count() : 148;
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-    mmd_lut_kernel<<<(d + 1 + 255) / 256, 256, 0, st>>>(TC_PASS_COEF, d, m, n_kernels, mul_factor, squared, bandwidth, sums_dev,
-                                                        lut_dev);
+    B200_CUDA(cudaMemsetAsync(rowsum_dev, 0, (size_t)n_rows * sizeof(int64_t), st));
+    mmd_coef_lut_kernel<<<1, 1024, 0, st>>>(d, m, n_kernels, mul_factor, squared, bandwidth, sums_dev, w_xx, w_xy, n_planes,
+                                            lut_dev, scale_dev);
     B200_CUDA(cudaGetLastError());
-    mmd_gram_i8_kernel<<<grid, TC_THREADS, smem + 1024, st>>>(tmap, p);
+    mmd_gram_i8_kernel<<<grid, TC_THREADS, smem, st>>>(tmap, p);
     B200_CUDA(cudaGetLastError());
     return 0;
 }

@@ -10,7 +10,7 @@
 //   their own TMA producer and epilogue.  Barriers: full[s] lives in the leader (2 arrivals +
 //   both CTAs' transaction bytes), empty[s] / tmem_full[a] are arrived in both CTAs by the
 //   multicast tcgen05.commit, tmem_empty[a] lives in the leader (2 x 8 epilogue warps).
-#include "tc_common.cuh"
+#include "mmd_hist.cuh"
 
 namespace b200grbm {
 
@@ -25,9 +25,8 @@ struct PairParams {
     int n_kblocks;
     int tiles, total_tiles;   // 256 x 256 pair-tiles per side; upper triangle count
     int stages;
-    int pass;                 // 0 = distance sum, 1 = kernel sums
-    const float *lut;
-    double *sums;
+    int shard_rank, shard_world;          // this launch contracts pair-tiles t = shard_rank (mod shard_world)
+    unsigned long long *hist;             // [3][d + 1] ordered-pair counts per Hamming distance (mmd_hist.cuh)
 };
 
 // upper triangle enumerated row by row: pair-tile t -> (I, J) with J >= I
@@ -53,12 +52,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     const int S = p.stages;
-    float *lut = reinterpret_cast<float *>(smem + (size_t)S * P_STAGE_BYTES);
+    uint32_t *bins = reinterpret_cast<uint32_t *>(smem + (size_t)S * P_STAGE_BYTES);     // d + 1 counters
     const size_t lut_bytes = ((size_t)(p.d + 1) * 4 + 15) / 16 * 16;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * P_STAGE_BYTES + lut_bytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 4);
     const uint32_t full0 = smem_addr(bars), empty0 = full0 + 8u * S, tfull0 = empty0 + 8u * S, tempty0 = tfull0 + 16u;
-    __shared__ double red[3][P_EPI_WARPS];
+    const int n_local = p.total_tiles > p.shard_rank ? (p.total_tiles - p.shard_rank + p.shard_world - 1) / p.shard_world : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { bar_init(full0 + 8u * s, 2); bar_init(empty0 + 8u * s, 1); }
@@ -67,7 +66,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     }
     if (warp == 1) tmem_alloc_2cta(smem_addr(tmem_slot), 512);
-    for (int k = threadIdx.x; k <= p.d; k += blockDim.x) lut[k] = p.lut[k];
+    for (int k = threadIdx.x; k <= p.d; k += blockDim.x) bins[k] = 0u;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     cluster_sync_all();                      // the peer's barriers are initialised before anyone arrives remotely
@@ -79,9 +78,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int t = pair; t < p.total_tiles; t += n_pairs) {
+            for (int u = pair; u < n_local; u += n_pairs) {
                 int I, J;
-                pair_tile_coords(p.tiles, t, I, J);
+                pair_tile_coords(p.tiles, u * p.shard_world + p.shard_rank, I, J);
                 const int a_row = I * 256 + (int)rank * 128, b_row = J * 256 + (int)rank * 128;
                 for (int kb = 0; kb < p.n_kblocks; ++kb) {
                     bar_wait(empty0 + 8u * s, ph ^ 1u);                       // own stage free (multicast commit)
@@ -101,7 +100,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
             const uint32_t idesc = umma_idesc_i8(256, 256);
             int s = 0, it = 0;
             uint32_t ph = 0;
-            for (int t = pair; t < p.total_tiles; t += n_pairs, ++it) {
+            for (int u = pair; u < n_local; u += n_pairs, ++it) {
                 const uint32_t acc = (uint32_t)it & 1u, acc_ph = ((uint32_t)it >> 1) & 1u;
                 bar_wait(tempty0 + 8u * acc, acc_ph ^ 1u);               // both epilogues drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -121,15 +120,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
             }
         }
     } else {
-        // ===================== epilogue (both CTAs): TMEM -> LUT -> block sums =====================
+        // ===================== epilogue (both CTAs): TMEM -> Hamming histograms =====================
         const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
-        double s_xx = 0.0, s_yy = 0.0, s_xy = 0.0;
+        const int epi_tid = threadIdx.x - 64;
         const int two_d = 2 * p.d;
         const uint32_t lead_tempty0 = mapa_cluster(tempty0, 0);
+        HistAccumulator hacc = {bins, p.hist, p.d, -1};
         int it = 0;
-        for (int t = pair; t < p.total_tiles; t += n_pairs, ++it) {
+        for (int u = pair; u < n_local; u += n_pairs, ++it) {
             int I, J;
-            pair_tile_coords(p.tiles, t, I, J);
+            pair_tile_coords(p.tiles, u * p.shard_world + p.shard_rank, I, J);
             const uint32_t acc = (uint32_t)it & 1u, acc_ph = ((uint32_t)it >> 1) & 1u;
             const int row0 = I * 256 + (int)rank * 128, col0 = J * 256;
             const int row = row0 + quarter * 32 + lane;
@@ -138,66 +138,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
             const bool cols_x = col0 + 256 <= p.m_x, cols_y = col0 >= p.m_x;
             const bool pure = strict_upper && (row0 + 128 <= p.m) && (col0 + 256 <= p.m) && (rows_x || rows_y) &&
                               (cols_x || cols_y);
+            if (pure) {
+                const int type = rows_x && cols_x ? HIST_XX : (rows_y && cols_y ? HIST_YY : HIST_XY);
+                if (type != hacc.type) {             // uniform over this CTA's epilogue threads
+                    hacc.flush(epi_tid, P_EPI_WARPS * 32);
+                    hacc.type = type;
+                }
+            }
             bar_wait(tfull0 + 8u * acc, acc_ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float a_xx = 0.f, a_yy = 0.f, a_xy = 0.f;
 #pragma unroll 1
             for (int chunk = 0; chunk < 4; ++chunk) {
                 uint32_t v[32];
                 const int cbase = half * 128 + chunk * 32;
                 __syncwarp();
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + (uint32_t)cbase, v);
-                if (pure) {
-                    float part = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) part += lut[min(max((two_d - 2 * (int)v[c]) >> 2, 0), p.d)];
-                    a_xx += part;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int col = col0 + cbase + c;
-                        if (row < p.m && col < p.m && col >= row) {
-                            const float kv = lut[min(max((two_d - 2 * (int)v[c]) >> 2, 0), p.d)];
-                            const bool rx = row < p.m_x, cx = col < p.m_x;
-                            const float w = col == row ? 1.f : 2.f;
-                            if (p.pass == 0) a_xx += w * kv;
-                            else if (rx && cx) a_xx += w * kv;
-                            else if (!rx && !cx) a_yy += w * kv;
-                            else a_xy += kv;
-                        }
-                    }
-                }
+                hist_count_chunk(v, pure, hacc, two_d, row, col0 + cbase, p.m_x, p.m);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) bar_arrive_cluster(lead_tempty0 + 8u * acc);   // the leader's MMA thread waits for both CTAs
-            if (pure) {
-                const double v2 = 2.0 * (double)a_xx;
-                if (p.pass == 0) s_xx += v2;
-                else if (rows_x && cols_x) s_xx += v2;
-                else if (rows_y && cols_y) s_yy += v2;
-                else s_xy += (double)a_xx;
-            } else {
-                s_xx += (double)a_xx; s_yy += (double)a_yy; s_xy += (double)a_xy;
-            }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s_xx += __shfl_xor_sync(0xffffffffu, s_xx, o);
-            s_yy += __shfl_xor_sync(0xffffffffu, s_yy, o);
-            s_xy += __shfl_xor_sync(0xffffffffu, s_xy, o);
-        }
-        if (lane == 0) { red[0][ew] = s_xx; red[1][ew] = s_yy; red[2][ew] = s_xy; }
+        hacc.flush(epi_tid, P_EPI_WARPS * 32);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x < 3) {
-        double tot = 0.0;
-        for (int w = 0; w < P_EPI_WARPS; ++w) tot += red[threadIdx.x][w];
-        if (p.pass == 0) { if (threadIdx.x == 0) atomicAdd(p.sums + 3, tot); }
-        else if (tot != 0.0) atomicAdd(p.sums + threadIdx.x, tot);
-    }
     cluster_sync_all();                      // neither CTA frees TMEM / exits while the peer may still touch it
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -206,8 +172,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 }
 
 // launched from b200grbm_mmd_forward_i8 (mmd_tc.cu)
-int32_t launch_gram_i8_2cta(const CUtensorMap &tmap, int m_x, int m, int d, int d_pad, int pass, const float *lut,
-                            double *sums, cudaStream_t st)
+int32_t launch_gram_i8_2cta(const CUtensorMap &tmap, int m_x, int m, int d, int d_pad, unsigned long long *hist,
+                            int shard_rank, int shard_world, cudaStream_t st)
 {
     int dev = 0, smem_optin = 0;
     B200_CUDA(cudaGetDevice(&dev));
@@ -226,13 +192,14 @@ int32_t launch_gram_i8_2cta(const CUtensorMap &tmap, int m_x, int m, int d, int 
     p.tiles = (m + 255) / 256;
     p.total_tiles = p.tiles * (p.tiles + 1) / 2;
     p.stages = stages;
-    p.pass = pass;
-    p.lut = lut;
-    p.sums = sums;
+    p.shard_rank = shard_rank; p.shard_world = shard_world;
+    p.hist = hist;
     B200_CUDA(cudaFuncSetAttribute(mmd_gram_i8_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int sms = sm_count() > 0 ? sm_count() : 148;
     int pairs = sms / 2;
-    if (pairs > p.total_tiles) pairs = p.total_tiles;
+    const int n_local = p.total_tiles > shard_rank ? (p.total_tiles - shard_rank + shard_world - 1) / shard_world : 0;
+    if (n_local == 0) return 0;
+    if (pairs > n_local) pairs = n_local;
     mmd_gram_i8_2cta_kernel<<<2 * pairs, P_THREADS, smem, st>>>(tmap, p);     // __cluster_dims__(2,1,1)
     B200_CUDA(cudaGetLastError());
     return 0;

@@ -1,0 +1,127 @@
+// Fused spin extraction: ONE pass over the encoder output (or the sampler's int8 samples) emits every layout the
+// hot path consumes downstream.
+//
+// Reference sites: `spins = spins.reshape(-1, n)` (src/model_wrapper.py:318) feeds both
+// maximum_mean_discrepancy_loss (:320) and, detached, nll_loss (:332-342).  The encoder's straight-through spins are
+// +-1 up to ~1e-7 residue (src/utils/common.py:162-173), so both consumers work on sign(x):
+//   rows    int8 [row_off + r][d_pad]      the Gram operand of the tcgen05 MMD kernels (zero-padded columns)
+//   zt      int8 [i][row_off + r]          the same matrix transposed: B operand of the backward GEMM (gemm_i8.cu)
+//   packed  u32  [r / 32][pos[i]]          bit-packed words in visit-position order for the integer edge statistics
+// Each output is optional.  HBM-bound: reads rows x d x sizeof(T) once; every store is a full 16-byte (rows, zt when the
+// row offset is 16-aligned) or 4-byte (packed) transaction.
+#include "common.cuh"
+
+namespace b200grbm {
+
+constexpr int SX_ROWS = 128, SX_COLS = 64;      // tile: 128 rows x 64 spins, 4 statistics groups of 32 rows
+
+template <typename T>
+__global__ void __launch_bounds__(256) spin_extract_kernel(const T *__restrict__ x, int rows, int d, int8_t *__restrict__ out_rows,
+                                                           int d_pad, int row_off, int8_t *__restrict__ zt, int zt_pitch,
+                                                           uint32_t *__restrict__ packed, const int32_t *__restrict__ pos,
+                                                           int n_pad, int32_t *__restrict__ nonspin, float tol)
+{
+    // +4 bytes of row padding: the transposed reads below walk a column with a stride of 68 bytes (17 words)
+    __shared__ __align__(16) int8_t tile[SX_ROWS][SX_COLS + 4];
+    const int r0 = blockIdx.y * SX_ROWS, c0 = blockIdx.x * SX_COLS;
+    int bad = 0;
+    for (int k = threadIdx.x; k < SX_ROWS * SX_COLS; k += blockDim.x) {
+        const int r = k / SX_COLS, c = k % SX_COLS;
+        int8_t v = 0;
+        if (r0 + r < rows && c0 + c < d) {
+            const T xv = x[(size_t)(r0 + r) * d + c0 + c];
+            v = xv > (T)0 ? (int8_t)1 : (int8_t)-1;
+            if (nonspin != nullptr && !(fabsf(fabsf((float)xv) - 1.0f) <= tol)) bad = 1;     // also catches NaN
+        }
+        tile[r][c] = v;
+    }
+    if (nonspin != nullptr && __syncthreads_or(bad) && threadIdx.x == 0) atomicAdd(nonspin, 1);
+    __syncthreads();
+    if (out_rows != nullptr) {          // 128 rows x 4 segments of 16 bytes
+        for (int k = threadIdx.x; k < SX_ROWS * (SX_COLS / 16); k += blockDim.x) {
+            const int r = k / (SX_COLS / 16), s = k % (SX_COLS / 16);
+            if (r0 + r < rows && c0 + 16 * s < d_pad) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(&tile[r][16 * s]);
+                *reinterpret_cast<uint4 *>(out_rows + (size_t)(row_off + r0 + r) * d_pad + c0 + 16 * s) =
+                    make_uint4(src[0], src[1], src[2], src[3]);
+            }
+        }
+    }
+    if (zt != nullptr) {
+        if (((row_off + r0) & 15) == 0) {       // 64 spins x 8 segments of 16 rows
+            for (int k = threadIdx.x; k < SX_COLS * (SX_ROWS / 16); k += blockDim.x) {
+                const int c = k / (SX_ROWS / 16), s = k % (SX_ROWS / 16);
+                if (c0 + c >= d || r0 + 16 * s >= rows) continue;
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w[j >> 2] |= (uint32_t)(uint8_t)tile[16 * s + j][c] << (8 * (j & 3));
+                int8_t *dst = zt + (size_t)(c0 + c) * zt_pitch + row_off + r0 + 16 * s;
+                if (r0 + 16 * s + 16 <= rows) {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                } else {                         // last rows of this input: never write into the next block's columns
+                    for (int j = 0; r0 + 16 * s + j < rows; ++j) dst[j] = tile[16 * s + j][c];
+                }
+            }
+        } else {                                 // unaligned row offset (ragged m_x): byte stores, row index fastest
+            for (int k = threadIdx.x; k < SX_COLS * SX_ROWS; k += blockDim.x) {
+                const int c = k / SX_ROWS, r = k % SX_ROWS;
+                if (c0 + c < d && r0 + r < rows) zt[(size_t)(c0 + c) * zt_pitch + row_off + r0 + r] = tile[r][c];
+            }
+        }
+    }
+    if (packed != nullptr) {            // 4 groups x 64 spins = 256 words, one per thread
+        const int g = threadIdx.x / SX_COLS, c = threadIdx.x % SX_COLS;
+        if (g < SX_ROWS / 32 && c0 + c < d && r0 + 32 * g < rows) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w |= (tile[32 * g + j][c] > 0 ? 1u : 0u) << j;      // rows beyond `rows` hold 0
+            packed[(size_t)((r0 >> 5) + g) * n_pad + pos[c0 + c]] = w;
+        }
+    }
+}
+
+template <typename T>
+static int32_t spin_extract_impl(const T *x_dev, int32_t rows, int32_t d, int8_t *rows_dev, int32_t d_pad, int32_t row_off,
+                                 int8_t *zt_dev, int32_t zt_pitch, uint32_t *packed_dev, const int32_t *pos_dev, int32_t n_pad,
+                                 int32_t *nonspin_dev, float tol, void *stream)
+{
+    if (rows <= 0 || d <= 0 || row_off < 0) return fail(B200GRBM_EINVAL, "spin_extract: rows=%d d=%d row_off=%d", rows, d, row_off);
+    if (!x_dev) return fail(B200GRBM_EINVAL, "spin_extract: NULL input");
+    if (rows_dev != nullptr && (d_pad < d || d_pad % 16 != 0 || (reinterpret_cast<uintptr_t>(rows_dev) & 15u) != 0))
+        return fail(B200GRBM_EINVAL, "spin_extract: rows output needs d_pad=%d a multiple of 16 >= d=%d and 16-byte alignment", d_pad, d);
+    if (zt_dev != nullptr && (zt_pitch < row_off + rows || zt_pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(zt_dev) & 15u) != 0))
+        return fail(B200GRBM_EINVAL, "spin_extract: zt output needs a pitch (%d) that is a multiple of 16 >= row_off + rows = %d", zt_pitch,
+                    row_off + rows);
+    if (packed_dev != nullptr && (pos_dev == nullptr || n_pad < d))
+        return fail(B200GRBM_EINVAL, "spin_extract: packed output needs pos_dev and n_pad=%d >= d=%d", n_pad, d);
+    B200_TRY(require_device());
+    const int cols = rows_dev != nullptr ? d_pad : d;       // the row output also zero-fills its padding columns
+    dim3 grid((cols + SX_COLS - 1) / SX_COLS, (rows + SX_ROWS - 1) / SX_ROWS);
+    if (grid.y > 65535) return fail(B200GRBM_EUNSUPPORTED, "spin_extract: %d rows exceed grid.y; split the call", rows);
+    spin_extract_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, rows, d, rows_dev, d_pad, row_off, zt_dev, zt_pitch,
+                                                                   packed_dev, pos_dev, n_pad, nonspin_dev, tol);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200grbm
+
+using namespace b200grbm;
+
+extern "C" int32_t b200grbm_spin_extract_f32(const float *x_dev, int32_t rows, int32_t d, int8_t *rows_dev, int32_t d_pad,
+                                             int32_t row_off, int8_t *zt_dev, int32_t zt_pitch, uint32_t *packed_dev,
+                                             const int32_t *pos_dev, int32_t n_pad, int32_t *nonspin_dev, float tol,
+                                             void *stream)
+{
+    return spin_extract_impl<float>(x_dev, rows, d, rows_dev, d_pad, row_off, zt_dev, zt_pitch, packed_dev, pos_dev, n_pad,
+                                    nonspin_dev, tol, stream);
+}
+
+extern "C" int32_t b200grbm_spin_extract_i8(const int8_t *x_dev, int32_t rows, int32_t d, int8_t *rows_dev, int32_t d_pad,
+                                            int32_t row_off, int8_t *zt_dev, int32_t zt_pitch, uint32_t *packed_dev,
+                                            const int32_t *pos_dev, int32_t n_pad, int32_t *nonspin_dev, float tol,
+                                            void *stream)
+{
+    return spin_extract_impl<int8_t>(x_dev, rows, d, rows_dev, d_pad, row_off, zt_dev, zt_pitch, packed_dev, pos_dev, n_pad,
+                                     nonspin_dev, tol, stream);
+}

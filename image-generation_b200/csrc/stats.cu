@@ -248,9 +248,51 @@ __global__ void energy_backward_kernel(const float *__restrict__ x, const float 
     }
 }
 
+// dE_r/dx_ri = linear_i + sum_{e ni i} quadratic_e x_r,other(e), times the incoming gradient g_r.  One CTA per row:
+// the row and its gradient accumulators live in shared memory, the edge list is streamed once.
+__global__ void energy_grad_x_kernel(const float *__restrict__ x, const float *__restrict__ g, int n, int n_edges,
+                                     const int32_t *__restrict__ ei, const int32_t *__restrict__ ej,
+                                     const float *__restrict__ linear, const float *__restrict__ quadratic,
+                                     float *__restrict__ grad_x)
+{
+    extern __shared__ float rowbuf[];
+    float *row = rowbuf, *acc = rowbuf + n;
+    const float *xr = x + (size_t)blockIdx.x * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { row[i] = xr[i]; acc[i] = linear[i]; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n_edges; e += blockDim.x) {
+        const int a = ei[e], b = ej[e];
+        const float q = quadratic[e];
+        atomicAdd(acc + a, q * row[b]);
+        atomicAdd(acc + b, q * row[a]);
+    }
+    __syncthreads();
+    const float gr = g[blockIdx.x];
+    float *out = grad_x + (size_t)blockIdx.x * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = gr * acc[i];
+}
+
 }  // namespace b200grbm
 
 using namespace b200grbm;
+
+extern "C" int32_t b200grbm_energy_grad_x(const float *x_dev, const float *grad_energy_dev, int32_t rows, int32_t n,
+                                          int32_t n_edges, const int32_t *edge_i_dev, const int32_t *edge_j_dev,
+                                          const float *linear_dev, const float *quadratic_dev, float *grad_x_dev,
+                                          void *stream)
+{
+    if (rows <= 0 || n <= 0 || n_edges < 0) return fail(B200GRBM_EINVAL, "energy_grad_x: rows=%d n=%d n_edges=%d", rows, n, n_edges);
+    if (!x_dev || !grad_energy_dev || !linear_dev || !grad_x_dev || (n_edges > 0 && (!edge_i_dev || !edge_j_dev || !quadratic_dev)))
+        return fail(B200GRBM_EINVAL, "energy_grad_x: NULL pointer argument");
+    B200_TRY(require_device());
+    const size_t smem = 2 * sizeof(float) * (size_t)n;
+    if (smem > 200 * 1024) return fail(B200GRBM_EUNSUPPORTED, "energy_grad_x: n=%d too large for a shared-memory row", n);
+    B200_CUDA(cudaFuncSetAttribute(energy_grad_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    energy_grad_x_kernel<<<rows, 256, smem, (cudaStream_t)stream>>>(x_dev, grad_energy_dev, n, n_edges, edge_i_dev, edge_j_dev,
+                                                                    linear_dev, quadratic_dev, grad_x_dev);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int32_t b200grbm_set_weights(const float *linear_dev, const float *quadratic_dev, int32_t n, int32_t n_edges,
                                         float prefactor, float h_lo, float h_hi, float j_lo, float j_hi,

@@ -49,25 +49,35 @@ class _EnergyFunction(torch.autograd.Function):
                 _lib.ptr(x2), rows, n, n_edges, _lib.ptr(edge_i) if n_edges else None,
                 _lib.ptr(edge_j) if n_edges else None, _lib.ptr(lin), _lib.ptr(quad) if n_edges else None,
                 _lib.ptr(out), _lib.current_stream(x.device)))
-        ctx.save_for_backward(x2, edge_i, edge_j)
+        ctx.save_for_backward(x2, edge_i, edge_j, lin, quad)
         ctx.n_edges = n_edges
+        ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
         return out.reshape(lead)
 
     @staticmethod
     def backward(ctx, grad_out):
-        x2, edge_i, edge_j = ctx.saved_tensors
+        x2, edge_i, edge_j, lin, quad = ctx.saved_tensors
         rows, n = x2.shape
         n_edges = ctx.n_edges
         g = grad_out.reshape(-1).to(torch.float32).contiguous()
-        grad_lin = torch.zeros(n, dtype=torch.float32, device=x2.device)
-        grad_quad = torch.zeros(n_edges, dtype=torch.float32, device=x2.device)
+        grad_x = grad_lin = grad_quad = None
         lib = _lib.load()
         with torch.cuda.device(x2.device):
-            _lib.check(lib.b200grbm_energy_backward(
-                _lib.ptr(x2), _lib.ptr(g), rows, n, n_edges, _lib.ptr(edge_i) if n_edges else None,
-                _lib.ptr(edge_j) if n_edges else None, _lib.ptr(grad_lin),
-                _lib.ptr(grad_quad) if n_edges else None, _lib.current_stream(x2.device)))
-        return None, grad_lin, grad_quad, None, None
+            st = _lib.current_stream(x2.device)
+            ei, ej = (_lib.ptr(edge_i), _lib.ptr(edge_j)) if n_edges else (None, None)
+            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+                grad_lin = torch.zeros(n, dtype=torch.float32, device=x2.device)
+                grad_quad = torch.zeros(n_edges, dtype=torch.float32, device=x2.device)
+                _lib.check(lib.b200grbm_energy_backward(_lib.ptr(x2), _lib.ptr(g), rows, n, n_edges, ei, ej,
+                                                        _lib.ptr(grad_lin), _lib.ptr(grad_quad) if n_edges else None, st))
+            if ctx.needs_input_grad[0]:
+                # the plugin's forward is differentiable in x as well (the reference detaches its spins,
+                # src/model_wrapper.py:333, but any other caller must not silently get a zero gradient)
+                grad_x = torch.empty((rows, n), dtype=torch.float32, device=x2.device)
+                _lib.check(lib.b200grbm_energy_grad_x(_lib.ptr(x2), _lib.ptr(g), rows, n, n_edges, ei, ej, _lib.ptr(lin),
+                                                      _lib.ptr(quad) if n_edges else None, _lib.ptr(grad_x), st))
+                grad_x = grad_x.reshape(ctx.x_shape).to(ctx.x_dtype)
+        return grad_x, grad_lin, grad_quad, None, None
 
 
 class GraphRestrictedBoltzmannMachine(torch.nn.Module):
@@ -162,6 +172,14 @@ class GraphRestrictedBoltzmannMachine(torch.nn.Module):
             if k in state_dict and state_dict[k].shape != getattr(self, name).shape:
                 setattr(self, name, torch.empty_like(state_dict[k], device=getattr(self, name).device))
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        # the energy kernels index a shared-memory row of n floats with these buffers: a malformed checkpoint must be
+        # an error here, not an out-of-bounds device read later
+        n, ei, ej = self._linear.shape[0], self._edge_idx_i, self._edge_idx_j
+        if ei.shape != self._quadratic.shape or ej.shape != self._quadratic.shape:
+            raise ValueError(f"checkpoint edge buffers {tuple(ei.shape)} / {tuple(ej.shape)} do not match _quadratic "
+                             f"{tuple(self._quadratic.shape)}")
+        if ei.numel() and not bool(((ei >= 0) & (ei < ej) & (ej < n)).all()):
+            raise ValueError("checkpoint edge buffers must satisfy 0 <= _edge_idx_i < _edge_idx_j < n")
         if len(self._nodes) != self._linear.shape[0]:
             self._nodes = list(range(self._linear.shape[0]))
         self._graph_cache = None

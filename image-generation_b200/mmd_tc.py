@@ -1,8 +1,9 @@
-"""Host side of the tcgen05 MMD path (csrc/mmd_tc.cu): +-1 rows, int8 Gram on tensor cores.
+"""Host side of the tcgen05 MMD path (csrc/mmd_tc.cu, csrc/gemm_i8.cu, csrc/spin_extract.cu): +-1 rows, int8 Gram on
+tensor cores, Hamming-histogram epilogue, int8 fixed-point backward.
 
 Same block sums as :func:`image_generation_b200.mmd.mmd_block_sums` (reference call site
 src/model_wrapper.py:320); used for spin-valued inputs where the squared distance is the
-exact integer ``2 (D - a.b)``.
+exact integer ``4 * Hamming(a, b) = 2 (D - a.b)``.
 """
 from __future__ import annotations
 
@@ -10,7 +11,41 @@ import torch
 
 from . import _lib
 
-__all__ = ["pack_rows_i8", "pack_pair_i8", "mmd_block_sums_i8", "mmd_block_sums_bf16", "mmd_backward_bf16", "mmd_backward_i8", "gemm_bf16_tn"]
+__all__ = ["pack_rows_i8", "pack_pair_i8", "spin_extract", "PackedPair", "mmd_histograms_i8", "mmd_sums_from_histograms",
+           "mmd_block_sums_i8", "mmd_block_sums_bf16", "mmd_backward_bf16", "mmd_backward_i8", "gemm_bf16_tn",
+           "transpose_i8", "GRAD_PLANES"]
+
+
+def _d_pad(d: int) -> int:
+    # row pitch = a whole number of 128-byte lines: every 128 B TMA box row is then one aligned L2 line
+    # (a 16-byte-granular pitch makes each box row straddle two lines)
+    return (d + 127) // 128 * 128
+
+
+#: | |x| - 1 | beyond this marks a row as "not spin-valued" (straight-through residue is ~1e-7, src/utils/common.py:162-173)
+SPIN_TOL = 1e-4
+
+
+def spin_extract(src: torch.Tensor, rows_out: torch.Tensor = None, row_off: int = 0, zt: torch.Tensor = None,
+                 packed: torch.Tensor = None, pos: torch.Tensor = None, nonspin: torch.Tensor = None) -> None:
+    """One pass over ``src`` (rows of real-valued or int8 spins) writes, by sign, any of the layouts the hot path
+    consumes: the padded int8 Gram operand rows ``rows_out[row_off + r]``, their transpose ``zt[:, row_off + r]``
+    (B operand of the backward GEMM) and the bit-packed statistics words ``packed`` (visit-position order ``pos``).
+    ``nonspin`` (int32 device counter, accumulating) counts input tiles with an entry further than ``SPIN_TOL``
+    from +-1.  This is the spin extraction of src/model_wrapper.py:318 fused with every consumer's input layout."""
+    if not src.is_cuda:
+        raise RuntimeError("spin_extract runs on CUDA only (no CPU fallback)")
+    rows, d = src.shape
+    lib = _lib.load()
+    if src.dtype == torch.int8:
+        fn, s = lib.b200grbm_spin_extract_i8, src.contiguous()
+    else:
+        fn, s = lib.b200grbm_spin_extract_f32, src.detach().to(torch.float32).contiguous()
+    with torch.cuda.device(src.device):
+        _lib.check(fn(_lib.ptr(s), rows, d, _lib.ptr(rows_out), 0 if rows_out is None else rows_out.shape[1], int(row_off),
+                      _lib.ptr(zt), 0 if zt is None else zt.shape[1], _lib.ptr(packed), _lib.ptr(pos),
+                      0 if packed is None else packed.shape[1], _lib.ptr(nonspin), SPIN_TOL,
+                      _lib.current_stream(src.device)))
 
 
 def pack_rows_i8(z: torch.Tensor) -> tuple[torch.Tensor, int]:
@@ -19,45 +54,74 @@ def pack_rows_i8(z: torch.Tensor) -> tuple[torch.Tensor, int]:
     if not z.is_cuda:
         raise RuntimeError("the tcgen05 MMD path runs on CUDA only (no CPU fallback)")
     m, d = z.shape
-    # row pitch = a whole number of 128-byte lines: every 128 B TMA box row is then one aligned L2 line
-    # (a 16-byte-granular pitch makes each box row straddle two lines)
-    d_pad = (d + 127) // 128 * 128
-    if z.dtype == torch.int8:
-        if d_pad == d and z.is_contiguous() and z.data_ptr() % 16 == 0:
-            return z, d_pad
-        out = torch.zeros((m, d_pad), dtype=torch.int8, device=z.device)
-        out[:, :d] = z
-        return out, d_pad
-    z32 = z.detach().to(torch.float32).contiguous()
+    d_pad = _d_pad(d)
+    if z.dtype == torch.int8 and d_pad == d and z.is_contiguous() and z.data_ptr() % 16 == 0:
+        return z, d_pad
     out = torch.empty((m, d_pad), dtype=torch.int8, device=z.device)
-    lib = _lib.load()
-    with torch.cuda.device(z.device):
-        _lib.check(lib.b200grbm_mmd_pack_i8(_lib.ptr(z32), m, d, d_pad, _lib.ptr(out), _lib.current_stream(z.device)))
+    spin_extract(z, rows_out=out)
     return out, d_pad
 
 
-def pack_pair_i8(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+class PackedPair:
+    """``[x; y]`` in the layouts of the tcgen05 MMD kernels: ``rows`` int8 ``(m, d_pad)``; ``zt`` int8
+    ``(d, m_pad)`` (only when a gradient will be needed); ``stats`` the bit-packed statistics words of x."""
+
+    def __init__(self, rows, zt, m_x, d, stats=None):
+        self.rows, self.zt, self.m_x, self.d, self.stats = rows, zt, m_x, d, stats
+
+
+def pack_pair_i8(x: torch.Tensor, y: torch.Tensor, need_grad: bool = False, stats_pos: torch.Tensor = None,
+                 stats_n_pad: int = 0, nonspin: torch.Tensor = None) -> PackedPair:
     """Sign-pack ``x`` and ``y`` straight into one zero-padded int8 matrix ``[x; y]`` (no fp32 concatenation):
-    the spin extraction of the encoder output (src/model_wrapper.py:318) fused with the MMD input layout."""
+    the spin extraction of the encoder output (src/model_wrapper.py:318) fused with the MMD input layout --
+    and, when requested, with the transposed copy the backward GEMM reads and the bit-packed words of the
+    data-side edge statistics (``stats_pos`` = the sampler graph's visit position of every node)."""
     if not (x.is_cuda and y.is_cuda):
         raise RuntimeError("the tcgen05 MMD path runs on CUDA only (no CPU fallback)")
     (m_x, d), m_y = x.shape, y.shape[0]
-    d_pad = (d + 127) // 128 * 128
-    out = torch.empty((m_x + m_y, d_pad), dtype=torch.int8, device=x.device)
+    m = m_x + m_y
+    d_pad, m_pad = _d_pad(d), (m + 127) // 128 * 128
+    dev = x.device
+    rows = torch.empty((m, d_pad), dtype=torch.int8, device=dev)
+    zt = None
+    if need_grad:
+        zt = torch.empty((d, m_pad), dtype=torch.int8, device=dev)
+        if m_pad > m:
+            zt[:, m:].zero_()
+    stats = None
+    if stats_pos is not None:
+        stats = torch.zeros((-(-m_x // 32), stats_n_pad), dtype=torch.int32, device=dev)
+    spin_extract(x, rows, 0, zt, stats, stats_pos, nonspin)
+    spin_extract(y, rows, m_x, zt, nonspin=nonspin)
+    return PackedPair(rows, zt, m_x, d, stats)
+
+
+def mmd_histograms_i8(zi: torch.Tensor, m_x: int, d: int, shard: tuple = (0, 1), hist: torch.Tensor = None) -> torch.Tensor:
+    """Hamming-distance histograms ``(3, d + 1)`` int64 (xx, yy, xy ordered-pair counts) of the padded int8 rows
+    ``zi = [x; y]`` from ONE tcgen05 Gram pass.  ``shard = (rank, world)`` contracts only every ``world``-th tile:
+    the per-rank results sum to the full histogram exactly."""
+    m = zi.shape[0]
+    if hist is None:
+        hist = torch.zeros((3, d + 1), dtype=torch.int64, device=zi.device)
     lib = _lib.load()
-    with torch.cuda.device(x.device):
-        st = _lib.current_stream(x.device)
-        for src, row0 in ((x, 0), (y, m_x)):
-            rows = src.shape[0]
-            dst = out[row0:row0 + rows]
-            if src.dtype == torch.int8:
-                dst[:, :d] = src
-                if d_pad > d:
-                    dst[:, d:] = 0
-            else:
-                s32 = src.detach().to(torch.float32).contiguous()
-                _lib.check(lib.b200grbm_mmd_pack_i8(_lib.ptr(s32), rows, d, d_pad, dst.data_ptr(), st))
-    return out
+    with torch.cuda.device(zi.device):
+        _lib.check(lib.b200grbm_mmd_hist_i8(_lib.ptr(zi), m_x, m - m_x, d, zi.shape[1], int(shard[0]), int(shard[1]),
+                                            _lib.ptr(hist), _lib.current_stream(zi.device)))
+    return hist
+
+
+def mmd_sums_from_histograms(hist: torch.Tensor, m_x: int, m_y: int, kernel, sums: torch.Tensor = None) -> torch.Tensor:
+    """``[S_xx, S_yy, S_xy, sum_ab t_ab]`` (float64) from the Hamming histograms; the auto bandwidth comes from the
+    same histograms.  Fixed reduction order: identical bits wherever the histograms are identical."""
+    d = hist.shape[1] - 1
+    if sums is None:
+        sums = torch.empty(4, dtype=torch.float64, device=hist.device)
+    lib = _lib.load()
+    bw = -1.0 if kernel.bandwidth is None else kernel.bandwidth
+    with torch.cuda.device(hist.device):
+        _lib.check(lib.b200grbm_mmd_eval_hist(_lib.ptr(hist), m_x, m_y, d, kernel.n_kernels, kernel.mul_factor,
+                                              int(kernel.squared), bw, _lib.ptr(sums), _lib.current_stream(hist.device)))
+    return sums
 
 
 def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = None, d: int = None) -> torch.Tensor:
@@ -71,12 +135,12 @@ def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = No
         zi, d_pad = z, z.shape[1]
     if sums is None:
         sums = torch.empty(4, dtype=torch.float64, device=z.device)
-    lut = torch.empty(d + 1, dtype=torch.float32, device=z.device)
+    hist = torch.empty((3, d + 1), dtype=torch.int64, device=z.device)     # workspace, zeroed by the call
     lib = _lib.load()
     bw = -1.0 if kernel.bandwidth is None else kernel.bandwidth
     with torch.cuda.device(z.device):
         _lib.check(lib.b200grbm_mmd_forward_i8(_lib.ptr(zi), m_x, m - m_x, d, d_pad, kernel.n_kernels,
-                                               kernel.mul_factor, int(kernel.squared), bw, _lib.ptr(lut),
+                                               kernel.mul_factor, int(kernel.squared), bw, _lib.ptr(hist),
                                                _lib.ptr(sums), _lib.current_stream(z.device)))
     return sums
 
@@ -95,34 +159,55 @@ def gemm_bf16_tn(a_hi: torch.Tensor, a_lo, b: torch.Tensor, m_rows: int) -> torc
     return c[:, :n]
 
 
+#: fixed-point digits of the backward coefficients: 2 planes = 16 bits of the largest |A_ab| (the accuracy class of
+#: a bf16 hi/lo pair at half its tensor work), 3 planes = 24 bits (fp32 class)
+GRAD_PLANES = 2
+
+
+def transpose_i8(zi: torch.Tensor, d: int, m_pad: int) -> torch.Tensor:
+    """``ZT[d][m_pad]`` from the padded row-major int8 matrix (columns >= m zero)."""
+    m = zi.shape[0]
+    zt = torch.empty((d, m_pad), dtype=torch.int8, device=zi.device)
+    lib = _lib.load()
+    with torch.cuda.device(zi.device):
+        _lib.check(lib.b200grbm_transpose_i8(_lib.ptr(zi), m, d, zi.shape[1], _lib.ptr(zt), m_pad,
+                                             _lib.current_stream(zi.device)))
+    return zt
+
+
 def mmd_backward_i8(zi: torch.Tensor, d: int, m_x: int, kernel, sums: torch.Tensor, w_xx: float, w_xy: float,
-                    grad_out: torch.Tensor) -> torch.Tensor:
-    """d(MMD)/dx for +-1 rows on tensor cores: coefficient matrix from the int8 Gram (bf16 hi/lo
-    pair), then one bf16 GEMM against ``[Z^T; 1]`` -- the extra column is the row sum:
-    ``grad_x[a] = rowsum_a x_a - (A Z)_a``.  ``zi``: the packed int8 ``(m, d_pad)`` rows of the forward."""
+                    grad_out: torch.Tensor, zt: torch.Tensor = None, rows: tuple = None,
+                    n_planes: int = None) -> torch.Tensor:
+    """d(MMD)/dx for +-1 rows on int8 tensor cores: the coefficient matrix from a second int8 Gram as ``n_planes``
+    base-256 fixed-point digit planes plus exact integer row sums, then the int8 GEMM against ``Z^T``:
+    ``grad_x[a] = g (rowsum_a x_a - (A Z)_a)``.  ``zi``: the packed int8 ``(m, d_pad)`` rows of the forward;
+    ``zt``: their transpose if the forward kept it; ``rows = (row0, n_rows)``: gradient rows (default: all of x)."""
     m, d_pad = zi.shape
     dev = zi.device
-    m_pad = (m + 63) // 64 * 64
-    rows_alloc = (m_x + 127) // 128 * 128
-    a_hi = torch.empty((rows_alloc, m_pad), dtype=torch.bfloat16, device=dev)
-    a_lo = torch.empty((rows_alloc, m_pad), dtype=torch.bfloat16, device=dev)
-    if rows_alloc > m_x:           # rows the kernel never writes are still read by TMA: keep them finite
-        a_hi[m_x:].zero_()
-        a_lo[m_x:].zero_()
+    n_planes = GRAD_PLANES if n_planes is None else int(n_planes)
+    row0, n_rows = (0, m_x) if rows is None else rows
+    m_pad = (m + 127) // 128 * 128
+    rows_alloc = (n_rows + 127) // 128 * 128
+    if zt is None:
+        zt = transpose_i8(zi, d, m_pad)
+    planes = torch.empty((n_planes, rows_alloc, m_pad), dtype=torch.int8, device=dev)
+    rowsum = torch.empty(n_rows, dtype=torch.int64, device=dev)
+    scale = torch.empty(1, dtype=torch.float64, device=dev)
     lut = torch.empty(d + 1, dtype=torch.float32, device=dev)
+    grad_x = torch.empty((n_rows, d), dtype=torch.float32, device=dev)
+    g = grad_out.detach().reshape(1).to(torch.float32).contiguous()
     lib = _lib.load()
     bw = -1.0 if kernel.bandwidth is None else kernel.bandwidth
     with torch.cuda.device(dev):
-        _lib.check(lib.b200grbm_mmd_coef_i8(_lib.ptr(zi), m_x, m - m_x, d, d_pad, kernel.n_kernels, kernel.mul_factor,
-                                            int(kernel.squared), bw, _lib.ptr(sums), w_xx, w_xy, _lib.ptr(lut),
-                                            _lib.ptr(a_hi), _lib.ptr(a_lo), m_pad, _lib.current_stream(dev)))
-    # B = [Z^T; 1] as bf16 (N = d + 1 rows, K = m_pad): layout preparation only
-    b = torch.zeros((d + 1, m_pad), dtype=torch.bfloat16, device=dev)
-    b[:d, :m] = zi[:, :d].t()
-    b[d, :m] = 1
-    c = gemm_bf16_tn(a_hi, a_lo, b, m_x)                       # (m_x, d + 1)
-    x = zi[:m_x, :d].to(torch.float32)
-    return grad_out.to(torch.float32) * (c[:, d:d + 1] * x - c[:, :d])
+        st = _lib.current_stream(dev)
+        _lib.check(lib.b200grbm_mmd_coef_i8(_lib.ptr(zi), m_x, m - m_x, d, d_pad, int(row0), int(n_rows), kernel.n_kernels,
+                                            kernel.mul_factor, int(kernel.squared), bw, _lib.ptr(sums), w_xx, w_xy,
+                                            _lib.ptr(lut), _lib.ptr(planes), n_planes, rows_alloc, m_pad, _lib.ptr(rowsum),
+                                            _lib.ptr(scale), st))
+        _lib.check(lib.b200grbm_mmd_grad_i8(_lib.ptr(planes), n_planes, int(n_rows), rows_alloc, m_pad, _lib.ptr(zt), d,
+                                            _lib.ptr(rowsum), _lib.ptr(scale), _lib.ptr(g), _lib.ptr(zi), int(row0), d_pad,
+                                            _lib.ptr(grad_x), st))
+    return grad_x
 
 
 def _split_bf16(z: torch.Tensor, split: bool):

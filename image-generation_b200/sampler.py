@@ -371,6 +371,7 @@ class BlockGibbsSampler:
         self._edge_index: Optional[dict] = None
         self._coef_cache: dict = {}
         self._staging = None
+        self._staging_event = None
         self._packed_scratch: dict = {}
         self._generation = 0
         self.last_launches = 0
@@ -466,10 +467,17 @@ class BlockGibbsSampler:
                              torch.empty(g.n, dtype=torch.float32, device=self.device),
                              torch.empty(g.n_edges, dtype=torch.float32, device=self.device))
         h_pin, j_pin, h_t, j_t = self._staging
+        # the H2D copies below are asynchronous: the previous call's copies must have left the pinned buffers
+        # before the host overwrites them (back-to-back calls with different problems)
+        if self._staging_event is not None:
+            self._staging_event.synchronize()
         h_pin.copy_(torch.from_numpy(hv))
         j_pin.copy_(torch.from_numpy(jv))
         h_t.copy_(h_pin, non_blocking=True)
         j_t.copy_(j_pin, non_blocking=True)
+        if self._staging_event is None:
+            self._staging_event = torch.cuda.Event()
+        self._staging_event.record(torch.cuda.current_stream(self.device))
         self.device_graph.set_weights(h_t, j_t)
         return self._run(num_reads, num_sweeps, beta_range, beta_schedule_type, beta_schedule, seed, initial_states,
                          uniforms)
@@ -609,6 +617,10 @@ class PersistentChains:
         """Run ``num_sweeps`` more sweeps under the sampler's current weights (set them with
         ``sampler.device_graph.set_weights`` or through ``grbm.sample``); returns the current states."""
         s = self.sampler
+        if beta_schedule is None:
+            # resumed chains stay at the model's own temperature; the sampler's annealing range (if any) is for
+            # fresh chains only -- re-annealing from hot would destroy the persistent state
+            beta_schedule = np.ones(int(num_sweeps), dtype=np.float64)
         ss = s._run(self.num_chains, num_sweeps, None, None, beta_schedule, self.seed, None, None, packed_io=self.packed,
                     want_int8=want_samples, sweep_offset=self.sweeps_done, plan=self.plan, resume=self._started)
         self._started = True

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B200GRBM_ABI_VERSION 2
+#define B200GRBM_ABI_VERSION 3
 
 #define B200GRBM_EINVAL (-1)   /* bad argument / shape */
 #define B200GRBM_EUNSUPPORTED (-2) /* configuration not compiled in (e.g. chains_per_lane) */
@@ -157,6 +157,11 @@ int32_t b200grbm_energy_forward(const float *x_dev, int32_t rows, int32_t n, int
 int32_t b200grbm_energy_backward(const float *x_dev, const float *grad_energy_dev, int32_t rows, int32_t n,
                                  int32_t n_edges, const int32_t *edge_i_dev, const int32_t *edge_j_dev,
                                  float *grad_linear_dev, float *grad_quadratic_dev, void *stream);
+/* gradient of the same energies wrt the input rows (the plugin's forward is an ordinary differentiable torch
+ * expression in x): grad_x[r][i] = g_r * (linear_i + sum_{e ni i} quadratic_e x_r,other(e)) */
+int32_t b200grbm_energy_grad_x(const float *x_dev, const float *grad_energy_dev, int32_t rows, int32_t n,
+                               int32_t n_edges, const int32_t *edge_i_dev, const int32_t *edge_j_dev,
+                               const float *linear_dev, const float *quadratic_dev, float *grad_x_dev, void *stream);
 /* int8 +-1 rows -> fp64 energies (dimod SampleSet.record.energy, src/utils/persistent_qpu_sampler.py:84-88) */
 int32_t b200grbm_energy_i8(const int8_t *s_dev, int32_t rows, int32_t n, int32_t n_edges,
                            const int32_t *edge_i_dev, const int32_t *edge_j_dev, const float *h_dev,
@@ -201,29 +206,75 @@ int32_t b200grbm_mmd_backward_f32(const float *z_dev, int32_t m_x, int32_t m_y, 
 
 /*
  * tcgen05 path for +-1 rows (same contract as b200grbm_mmd_forward_f32; BASELINE.json cfg3).
- * z_dev: int8 [m][d_pad] row-major, 16-byte aligned, d_pad a multiple of 16, columns >= d zero
- * (b200grbm_mmd_pack_i8 produces it from real-valued spins by sign).  lut_dev: workspace of
- * d + 1 floats.  ||a-b||^2 = 2 (d - a.b) exactly, from the int32 Gram accumulators.
+ * z_dev: int8 [m][d_pad] row-major, 16-byte aligned, d_pad a multiple of 16 (128 for full TMA efficiency),
+ * columns >= d zero (b200grbm_spin_extract_* / b200grbm_mmd_pack_i8 produce it from real-valued spins by sign).
+ * ||a-b||^2 = 4 Hamming(a, b) = 2 (d - a.b) exactly, from the int32 Gram accumulators.
+ *
+ * b200grbm_mmd_hist_i8: ONE Gram pass over the upper triangle of 128 x 256 tiles; the epilogue counts the entries per
+ * Hamming distance into hist_dev[3][d + 1] (uint64, ACCUMULATING; [0] ordered pairs inside x incl. the diagonal,
+ * [1] inside y, [2] x-y pairs).  shard_rank / shard_world deal the tiles round-robin over ranks that each hold the
+ * whole z: the per-rank histograms add up (int64 all-reduce) to the single-GPU histogram exactly -- this is the
+ * "MMD partial sums combined by all-reduce" of the multi-GPU path.
+ * b200grbm_mmd_eval_hist: sums_dev[4] (same contract as b200grbm_mmd_forward_f32) from the histograms, float64,
+ * fixed reduction order; the data-dependent bandwidth comes from the same histograms, so the auto-bandwidth
+ * forward needs one Gram pass, not two.
+ * b200grbm_mmd_forward_i8 = memset + hist (all tiles) + eval; hist_dev is a workspace of 3 (d + 1) uint64.
  */
 int32_t b200grbm_mmd_pack_i8(const float *z_dev, int32_t m, int32_t d, int32_t d_pad, int8_t *out_dev, void *stream);
+int32_t b200grbm_mmd_hist_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad, int32_t shard_rank,
+                             int32_t shard_world, uint64_t *hist_dev, void *stream);
+int32_t b200grbm_mmd_eval_hist(const uint64_t *hist_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t n_kernels,
+                               float mul_factor, int32_t squared, float bandwidth, double *sums_dev, void *stream);
 int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,
-                                int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth, float *lut_dev,
+                                int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth, uint64_t *hist_dev,
                                 double *sums_dev, void *stream);
 
 /*
- * Backward of the +-1 MMD on tensor cores (dvae_loss.backward() through the MMD term,
- * src/model_wrapper.py:320-326):  grad_x[a] = rowsum_a(A) x_a - (A Z)_a.
- * b200grbm_mmd_coef_i8 re-runs the int8 Gram over (x rows) x (all rows) and writes
- * A_ab = w * (dk/dt)(dt/d||.||)/||.|| (w = w_xx for x-x pairs, w_xy for x-y pairs, 0 on the
- * diagonal and on padding) as a bf16 (hi, lo) pair, row pitch m_pad (multiple of 64, >= m);
- * both buffers hold at least ceil(m_x / 128) * 128 rows.  sums_dev[3] is the forward's distance sum.
- * b200grbm_gemm_bf16_tn: C[M][ldc] (fp32) = (A_hi + A_lo)[M][K] * B[N][K]^T with bf16 operands
- * (tcgen05.mma.kind::f16); a_lo_dev may be NULL; a_rows_alloc = rows allocated in the A buffers.
+ * Fused spin extraction (src/model_wrapper.py:318: `spins.reshape(-1, n)` feeds the MMD at :320 and, detached, the
+ * NLL at :332-342): one pass over real-valued (f32) or int8 rows writes, by sign, any of
+ *   rows_dev   int8 [row_off + r][d_pad]     Gram operand (padding columns zeroed)
+ *   zt_dev     int8 [i][row_off + r]         transposed copy, pitch zt_pitch (multiple of 16): B operand of the
+ *                                            backward GEMM; columns >= the last row written are the caller's to zero
+ *   packed_dev u32  [r / 32][pos[i]]         bit-packed words (32 rows per word, visit-position order) for
+ *                                            b200grbm_edge_stats; positions >= d are the caller's to zero
+ * NULL skips an output.  nonspin_dev (optional, accumulating int32): number of 128 x 64 input tiles holding an entry
+ * with | |x| - 1 | > tol -- lets the caller verify that sign-packing loses nothing before taking the int8 path.
  */
-int32_t b200grbm_mmd_coef_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad, int32_t n_kernels,
-                             float mul_factor, int32_t squared, float bandwidth, const double *sums_dev, float w_xx,
-                             float w_xy, float *lut_dev, void *coef_hi_dev, void *coef_lo_dev, int32_t m_pad,
+int32_t b200grbm_spin_extract_f32(const float *x_dev, int32_t rows, int32_t d, int8_t *rows_dev, int32_t d_pad,
+                                  int32_t row_off, int8_t *zt_dev, int32_t zt_pitch, uint32_t *packed_dev,
+                                  const int32_t *pos_dev, int32_t n_pad, int32_t *nonspin_dev, float tol, void *stream);
+int32_t b200grbm_spin_extract_i8(const int8_t *x_dev, int32_t rows, int32_t d, int8_t *rows_dev, int32_t d_pad,
+                                 int32_t row_off, int8_t *zt_dev, int32_t zt_pitch, uint32_t *packed_dev,
+                                 const int32_t *pos_dev, int32_t n_pad, int32_t *nonspin_dev, float tol, void *stream);
+/* out[c][r] = in[r][c] (int8), out pitch out_pitch >= rows, columns r >= rows zero-filled */
+int32_t b200grbm_transpose_i8(const int8_t *in_dev, int32_t rows, int32_t cols, int32_t in_pitch, int8_t *out_dev,
+                              int32_t out_pitch, void *stream);
+
+/*
+ * Backward of the +-1 MMD on int8 tensor cores (dvae_loss.backward() through the MMD term,
+ * src/model_wrapper.py:320-326):  grad_x[a] = g (rowsum_a(A) x_a - (A Z)_a),  A_ab = w (dk/dt)(dt/d||.||)/||.||
+ * (w = w_xx for x-x pairs, w_xy for x-y pairs, both including the factor 2 of the symmetric sum; 0 on the diagonal).
+ * b200grbm_mmd_coef_i8 re-runs the int8 Gram over rows [row0, row0 + n_rows) of the x block against every column and
+ * writes A as n_planes (2 or 3) signed base-256 digit planes of a fixed-point number -- planes_dev
+ * [n_planes][rows_alloc][m_pad] int8, most significant plane first, m_pad a multiple of 128 >= m, padding columns
+ * zero -- plus the exact integer row sums (rowsum_dev [n_rows]) and the value of one fixed-point unit (scale_dev,
+ * device scalar).  lut_dev: workspace of d + 1 floats.  sums_dev[3] is the forward's distance sum.
+ * b200grbm_mmd_grad_i8 contracts the planes with zt_dev (Z transposed, [d][m_pad] int8) on tcgen05.mma.kind::i8 and
+ * writes grad_x_dev [n_rows][d] = grad_out * scale * (rowsum_a z_ai - sum_b q_ab z_bi); z_dev row z_row0 + a is x_a.
+ */
+int32_t b200grbm_mmd_coef_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad, int32_t row0,
+                             int32_t n_rows, int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth,
+                             const double *sums_dev, float w_xx, float w_xy, float *lut_dev, int8_t *planes_dev,
+                             int32_t n_planes, int32_t rows_alloc, int32_t m_pad, int64_t *rowsum_dev, double *scale_dev,
                              void *stream);
+int32_t b200grbm_mmd_grad_i8(const int8_t *planes_dev, int32_t n_planes, int32_t n_rows, int32_t rows_alloc, int32_t m_pad,
+                             const int8_t *zt_dev, int32_t d, const int64_t *rowsum_dev, const double *scale_dev,
+                             const float *grad_out_dev, const int8_t *z_dev, int32_t z_row0, int32_t d_pad,
+                             float *grad_x_dev, void *stream);
+/*
+ * C[M][ldc] (fp32) = (A_hi + A_lo)[M][K] * B[N][K]^T with bf16 operands (tcgen05.mma.kind::f16); a_lo_dev may be
+ * NULL; a_rows_alloc = rows allocated in the A buffers.  Used by the backward of the continuous (bf16) MMD path.
+ */
 int32_t b200grbm_gemm_bf16_tn(const void *a_hi_dev, const void *a_lo_dev, int32_t M, int32_t K, int32_t a_rows_alloc,
                               const void *b_dev, int32_t N, float *c_dev, int32_t ldc, void *stream);
 

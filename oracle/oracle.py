@@ -278,3 +278,48 @@ def mmd(x: np.ndarray, y: np.ndarray, n_kernels: int = 7, mul_factor: float = 2.
     a[np.arange(mx), np.arange(mx)] = 0.0
     grad = a.sum(1)[:, None] * x - a @ z
     return val, grad
+
+
+# ---------------------------------------------------------------------------- MMD through Hamming histograms
+
+def hamming_histograms(z: np.ndarray, m_x: int, shard: tuple = (0, 1)) -> np.ndarray:
+    """``(3, d + 1)`` int64 counts of ORDERED row pairs per Hamming distance for +-1 rows ``z = [x; y]``:
+    [0] pairs inside x (diagonal included), [1] inside y, [2] x-y pairs -- the integer form of the kernel matrix
+    ``maximum_mean_discrepancy_loss`` builds (src/model_wrapper.py:320), since ``||a - b||^2 = 4 Hamming(a, b)``.
+    ``shard = (r, w)`` keeps only the unordered pairs {a <= b} with ``(a + b) % w == r`` (any partition of the pairs
+    sums to the full histogram; the CUDA kernel partitions by Gram tile)."""
+    z = np.asarray(z, dtype=np.int64)
+    m, d = z.shape
+    gram = z @ z.T
+    h = (d - gram) // 2
+    a, b = np.triu_indices(m)
+    r, w = shard
+    keep = ((a + b) % w) == r
+    a, b = a[keep], b[keep]
+    hv = h[a, b]
+    out = np.zeros((3, d + 1), dtype=np.int64)
+    xx = b < m_x
+    yy = a >= m_x
+    xy = ~xx & ~yy
+    wt = np.where(a == b, 1, 2)
+    np.add.at(out[0], hv[xx], wt[xx])
+    np.add.at(out[1], hv[yy], wt[yy])
+    np.add.at(out[2], hv[xy], 1)
+    return out
+
+
+def mmd_sums_from_histograms(hist: np.ndarray, m: int, n_kernels: int = 7, mul_factor: float = 2.0,
+                             bandwidth: Optional[float] = None, squared: bool = False) -> np.ndarray:
+    """``[S_xx, S_yy, S_xy, sum_ab t_ab]`` (float64) from the histograms, same formulas as
+    :func:`gaussian_kernel_matrix` evaluated once per distinct distance."""
+    hist = np.asarray(hist, dtype=np.float64)
+    d = hist.shape[1] - 1
+    hh = np.arange(d + 1, dtype=np.float64)
+    t = 4.0 * hh if squared else 2.0 * np.sqrt(hh)
+    dist = float((t * (hist[0] + hist[1] + 2.0 * hist[2])).sum())
+    bw = dist / (m * m - m) if bandwidth is None else float(bandwidth)
+    mult = mul_factor ** (np.arange(n_kernels) - n_kernels // 2)
+    k = np.zeros(d + 1)
+    for u in range(n_kernels):
+        k += np.exp(-t / (bw * mult[u]))
+    return np.array([(k * hist[0]).sum(), (k * hist[1]).sum(), (k * hist[2]).sum(), dist])

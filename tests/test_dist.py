@@ -67,3 +67,71 @@ def test_allreduce_is_identity_without_process_group():
     t = [torch.arange(5), torch.ones(3, dtype=torch.int64)]
     got = allreduce_statistics(t)
     assert all(torch.equal(a, b) for a, b in zip(got, t))
+
+
+# ------------------------------------------------------------------ cross-rank MMD
+
+class _NumpyOps:
+    """CPU stand-in for the sm_100a kernels behind ``sharded_mmd_loss``: the oracle's histograms and float64
+    evaluation.  Exercises the exchange (two int8 all-gathers, one int64 all-reduce, row offsets of the local
+    gradient) on the gloo backend."""
+
+    @staticmethod
+    def pack(rows):
+        return torch.sign(rows).to(torch.int8)
+
+    @staticmethod
+    def histograms(z, m_x, d, shard):
+        from oracle import oracle as O
+        return torch.from_numpy(O.hamming_histograms(z.numpy(), m_x, shard))
+
+    @staticmethod
+    def sums(hist, m_x, m_y, kernel):
+        from oracle import oracle as O
+        return torch.from_numpy(O.mmd_sums_from_histograms(hist.numpy(), m_x + m_y, kernel.n_kernels, kernel.mul_factor,
+                                                           kernel.bandwidth, kernel.squared))
+
+    @staticmethod
+    def backward(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out, rows):
+        from oracle import oracle as O
+        zz = z.numpy().astype(np.float64)
+        m = zz.shape[0]
+        bw = float(sums[3]) / (m * m - m) if kernel.bandwidth is None else kernel.bandwidth
+        _, grad = O.mmd(zz[:m_x], zz[m_x:], n_kernels=kernel.n_kernels, bandwidth=bw, return_grad=True)
+        r0, n = rows
+        return torch.from_numpy(grad[r0:r0 + n] * float(grad_out)).float()
+
+
+def _mmd_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import image_generation_b200 as B
+        from image_generation_b200.dist import sharded_mmd_loss
+        from oracle import oracle as O
+        rng = np.random.default_rng(5)
+        mx, my, d = 12, 10, 24                       # per rank
+        x_all = rng.choice([-1.0, 1.0], size=(world * mx, d)).astype(np.float32)
+        y_all = rng.choice([-1.0, 1.0], size=(world * my, d)).astype(np.float32)
+        y_all[:, :6] = 1.0
+        x = torch.from_numpy(x_all[rank * mx:(rank + 1) * mx]).requires_grad_(True)
+        y = torch.from_numpy(y_all[rank * my:(rank + 1) * my])
+        kern = B.GaussianKernel(7)
+        val = sharded_mmd_loss(x, y, kern, _ops=_NumpyOps)
+        val.backward()
+        bw = O.gaussian_kernel_matrix(np.concatenate([x_all, y_all]).astype(np.float64))[1]
+        want, grad = O.mmd(x_all, y_all, bandwidth=bw, return_grad=True)
+        ok = abs(float(val) - want) < 1e-6 and np.allclose(x.grad.numpy(), grad[rank * mx:(rank + 1) * mx], rtol=1e-5, atol=1e-9)
+        vals = [torch.zeros(1, dtype=torch.float32) for _ in range(world)]
+        dist.all_gather(vals, val.detach().reshape(1))
+        out[rank] = bool(ok and all(torch.equal(v, vals[0]) for v in vals))     # bit-identical on every rank
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_mmd_exchange_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_mmd_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}

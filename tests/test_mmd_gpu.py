@@ -140,7 +140,7 @@ def test_tensor_core_path_agrees_with_cuda_core_path_and_loss(cuda_device):
     b = float(B.maximum_mean_discrepancy_loss(xt, yt, kern, path="i8"))
     want, scale = _terms(x, y)
     assert abs(a - want) <= 1e-5 * scale and abs(b - want) <= 1e-5 * scale
-    # gradients: tensor-core backward (int8 Gram -> bf16 hi/lo coefficients -> bf16 GEMM) vs CUDA-core backward
+    # gradients: tensor-core backward (int8 Gram -> fixed-point digit planes -> int8 GEMM) vs CUDA-core backward
     xg = xt.clone().requires_grad_(True)
     B.maximum_mean_discrepancy_loss(xg, yt, kern, path="i8").backward()
     xf = xt.clone().requires_grad_(True)
@@ -165,7 +165,7 @@ def test_tensor_core_backward_matches_oracle(cuda_device, m_x, m_y, d, squared, 
     want_val, grad = O.mmd(x, y, squared=squared, estimator=estimator, bandwidth=bw, return_grad=True)
     got = xt.grad.cpu().numpy() / 2.0
     assert got.shape == grad.shape
-    # bf16 (hi, lo) coefficients carry 2^-16 relative error each; sums of ~m terms
+    # two base-256 digit planes carry 2^-16 of the largest coefficient each; sums of ~m terms
     np.testing.assert_allclose(got, grad, rtol=2e-3, atol=5e-5 * np.abs(grad).max())
     rel = np.linalg.norm(got - grad) / np.linalg.norm(grad)
     assert rel < 2e-4, rel
@@ -250,29 +250,99 @@ def test_cta_pair_kernel_matches_single_cta_kernel(cuda_device, monkeypatch):
     np.testing.assert_allclose(got["1"], got["2"], rtol=1e-9)
 
 
-def test_full_size_cfg3_tensor_core_vs_cuda_core(cuda_device):
-    """BASELINE.json cfg3 at full size (8192 + 8192 rows, D = 5640): the tcgen05 int8 path against the independent
-    CUDA-core fp32 path (directly accumulated differences), plus size-independent properties."""
+def _cfg3(cuda_device):
     g = torch.Generator().manual_seed(3)
     m, d = 8192, 5640
     z = torch.randint(0, 2, (2 * m, d), generator=g, dtype=torch.int8) * 2 - 1
     z[m:, :700] = 1
-    z = z.to(cuda_device)
+    return z.to(cuda_device), m, d
+
+
+def test_full_size_cfg3_histograms_exact_and_float64_oracle(cuda_device):
+    """BASELINE.json cfg3 at full size (8192 + 8192 rows, D = 5640).  The tcgen05 kernel's Hamming histograms must equal,
+    count for count, the histograms of an independent Gram (cuBLAS fp32 on +-1 rows: exact integers below 2^24); the
+    block sums must equal the float64 oracle's evaluation of those histograms; plus size-independent properties."""
+    from image_generation_b200.mmd_tc import mmd_histograms_i8, pack_rows_i8
+    z, m, d = _cfg3(cuda_device)
     kern = B.GaussianKernel(7).to(cuda_device)
+    zi, _ = pack_rows_i8(z)
+    hist = mmd_histograms_i8(zi, m, d).cpu().numpy()
+    # independent route: fp32 Gram in row blocks -> Hamming distance -> bincount (upper triangle weighted like the kernel)
+    zf = z.float()
+    ref = np.zeros((3, d + 1), dtype=np.int64)
+    for r0 in range(0, 2 * m, 2048):
+        gram = zf[r0:r0 + 2048] @ zf.t()
+        h = ((d - gram) * 0.5).round().to(torch.int64)
+        for blk, (c0, c1) in enumerate(((0, m), (m, 2 * m))):
+            t = 0 if (r0 < m and blk == 0) else (1 if (r0 >= m and blk == 1) else 2)
+            if r0 >= m and blk == 0:
+                continue                                        # y rows against x columns: counted from the x side
+            ref[t] += torch.bincount(h[:, c0:c1].reshape(-1), minlength=d + 1).cpu().numpy()
+    assert np.array_equal(hist, ref)
     s_tc = mmd_block_sums(z, m, kern, path="i8").cpu().numpy()
-    s_cc = mmd_block_sums(z.float(), m, kern, path="f32").cpu().numpy()
-    np.testing.assert_allclose(s_tc, s_cc, rtol=3e-6)
-    # diagonal blocks contain m entries equal to n_kernels, and every entry lies in (0, n_kernels]
-    assert s_tc[0] > 7 * m and s_tc[0] <= 7.0 * m * m and s_tc[2] <= 7.0 * m * m
-    # swapping the roles of x and y swaps S_xx and S_yy and keeps S_xy and the distance sum
+    want = O.mmd_sums_from_histograms(ref, 2 * m)
+    np.testing.assert_allclose(s_tc, want, rtol=1e-12)
+    # the two-CTA (cta_group::2) kernel and a 3-way tile sharding give the same counts
+    import os
+    os.environ["B200GRBM_MMD_TILE"] = "2"
+    try:
+        assert np.array_equal(mmd_histograms_i8(zi, m, d).cpu().numpy(), ref)
+    finally:
+        del os.environ["B200GRBM_MMD_TILE"]
+    parts = sum(mmd_histograms_i8(zi, m, d, shard=(r, 3)).cpu().numpy() for r in range(3))
+    assert np.array_equal(parts, ref)
+    # swapping the roles of x and y swaps S_xx and S_yy and keeps S_xy and the distance sum -- bit for bit
     zs = torch.cat([z[m:], z[:m]], 0).contiguous()
     s_sw = mmd_block_sums(zs, m, kern, path="i8").cpu().numpy()
-    np.testing.assert_allclose(s_sw[[1, 0, 2, 3]], s_tc, rtol=1e-9)
-    # identical clouds: the biased estimate vanishes
+    assert np.array_equal(s_sw[[1, 0, 2, 3]], s_tc)
+    # identical clouds: the biased estimate vanishes exactly (integer counts, fixed evaluation order)
     x = z[:m].float()
     val = B.maximum_mean_discrepancy_loss(x, x.clone(), kern, estimator="biased", path="i8")
-    assert abs(float(val)) < 1e-6          # block sums agree to fp32 partial-sum rounding (~1e-8 relative)
+    assert float(val) == 0.0
 
+
+def test_full_size_cfg3_coefficient_tiles_vs_float64_oracle(cuda_device):
+    """cfg3 at full size, entry by entry: 64 sampled 128 x 256 tiles of the backward coefficient matrix (incl. tiles on
+    the diagonal and on the x/y boundary) against the float64 oracle's A_ab = w (dk/dt) / t, and the integer row sums."""
+    from image_generation_b200 import _lib
+    from image_generation_b200.mmd_tc import pack_rows_i8
+    z, m, d = _cfg3(cuda_device)
+    kern = B.GaussianKernel(7).to(cuda_device)
+    sums = mmd_block_sums(z, m, kern, path="i8")
+    zi, d_pad = pack_rows_i8(z)
+    w_xx, w_xy = 2.0 / (m * (m - 1)), -2.0 / (m * m)
+    n_planes, m_pad = 3, 2 * m
+    planes = torch.empty((n_planes, m, m_pad), dtype=torch.int8, device=cuda_device)
+    rowsum = torch.empty(m, dtype=torch.int64, device=cuda_device)
+    scale = torch.empty(1, dtype=torch.float64, device=cuda_device)
+    lut = torch.empty(d + 1, dtype=torch.float32, device=cuda_device)
+    lib = _lib.load()
+    _lib.check(lib.b200grbm_mmd_coef_i8(_lib.ptr(zi), m, m, d, d_pad, 0, m, 7, 2.0, 0, -1.0, _lib.ptr(sums), w_xx, w_xy,
+                                        _lib.ptr(lut), _lib.ptr(planes), n_planes, m, m_pad, _lib.ptr(rowsum), _lib.ptr(scale),
+                                        _lib.current_stream(cuda_device)))
+    q = (planes[0].to(torch.int32) * 65536 + planes[1].to(torch.int32) * 256 + planes[2].to(torch.int32))
+    assert torch.equal(q.sum(1, dtype=torch.int64), rowsum)
+    unit = float(scale)
+    bw = float(sums[3]) / ((2.0 * m) ** 2 - 2.0 * m)
+    zc = z.cpu().numpy().astype(np.float64)
+    mult = 2.0 ** (np.arange(7) - 3)
+    rng = np.random.default_rng(0)
+    tiles = [(i, i // 2) for i in (0, 1, 30, 63)] + [(31, 31), (31, 32), (63, 32), (0, 63)]      # diagonal / boundary tiles
+    tiles += [(int(rng.integers(64)), int(rng.integers(64))) for _ in range(56)]
+    worst = 0.0
+    for ti, tj in tiles:
+        a, b = zc[128 * ti:128 * ti + 128], zc[256 * tj:256 * tj + 256]
+        dist = np.sqrt(np.maximum(2.0 * (d - a @ b.T), 0.0))
+        dk = sum(-np.exp(-dist / (bw * mu)) / (bw * mu) for mu in mult)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            coef = np.where(dist > 0, dk / dist, 0.0)
+        coef *= np.where(np.arange(256 * tj, 256 * tj + 256)[None, :] < m, w_xx, w_xy)
+        rows, cols = np.arange(128 * ti, 128 * ti + 128), np.arange(256 * tj, 256 * tj + 256)
+        coef[rows[:, None] == cols[None, :]] = 0.0
+        got = q[128 * ti:128 * ti + 128, 256 * tj:256 * tj + 256].cpu().numpy() * unit
+        worst = max(worst, np.abs(got - coef).max())
+    cmax = unit * 8355711.0
+    assert worst <= 2.0 ** -22 * cmax, (worst, cmax)       # 24-bit fixed point of the largest coefficient (+ fp32 LUT rounding)
 
 def test_tensor_core_super_block_tile_order_ragged(cuda_device):
     """m > 4096 switches the forward to L2-sized super-blocks of the tile triangle; ragged sizes make the last
@@ -286,3 +356,112 @@ def test_tensor_core_super_block_tile_order_ragged(cuda_device):
     k, bw, dist = O.gaussian_kernel_matrix(z.astype(np.float64))
     want = [k[:m_x, :m_x].sum(), k[m_x:, m_x:].sum(), k[:m_x, m_x:].sum(), dist.sum()]
     np.testing.assert_allclose(got, want, rtol=2e-6)
+
+
+@pytest.mark.parametrize("m_x,m_y,d", [(256, 256, 128), (300, 215, 333), (70, 45, 100), (1024, 256, 256)])
+def test_hamming_histograms_exact_and_shards_add_up(cuda_device, m_x, m_y, d):
+    """One tcgen05 Gram pass -> integer Hamming histograms: equal to the oracle's count for count (ragged sizes put
+    tiles on the diagonal, the x/y boundary and the matrix edge), and any tile sharding sums to the whole."""
+    from image_generation_b200.mmd_tc import mmd_histograms_i8, mmd_sums_from_histograms, pack_rows_i8
+    rng = np.random.default_rng(m_x + d)
+    z = rng.choice([-1, 1], size=(m_x + m_y, d)).astype(np.int8)
+    z[m_x:, : d // 5] = 1
+    zi, _ = pack_rows_i8(torch.from_numpy(z).to(cuda_device))
+    want = O.hamming_histograms(z, m_x)
+    got = mmd_histograms_i8(zi, m_x, d).cpu().numpy()
+    assert np.array_equal(got, want)
+    for world in (2, 5):
+        parts = sum(mmd_histograms_i8(zi, m_x, d, shard=(r, world)).cpu().numpy() for r in range(world))
+        assert np.array_equal(parts, want)
+    kern = B.GaussianKernel(7).to(cuda_device)
+    sums = mmd_sums_from_histograms(torch.from_numpy(want).to(cuda_device), m_x, m_y, kern).cpu().numpy()
+    np.testing.assert_allclose(sums, O.mmd_sums_from_histograms(want, m_x + m_y), rtol=1e-12)
+
+
+@pytest.mark.parametrize("m_x,m_y,d", [(1024, 256, 256), (8192, 8192, 5640)])
+def test_reference_call_without_extra_arguments_reaches_tensor_cores(cuda_device, m_x, m_y, d):
+    """``maximum_mean_discrepancy_loss(x=spins, y=samples, kernel=kernel)`` exactly as src/model_wrapper.py:320 writes
+    it (cfg1 and cfg3 shapes): the default path must be the tcgen05 int8 kernels, inside the oracle tolerance; inputs
+    that are not spin-valued go to the tcgen05 bf16 kernels instead."""
+    from image_generation_b200 import mmd as M
+    g = torch.Generator().manual_seed(d)
+    x = (torch.randint(0, 2, (m_x, d), generator=g) * 2 - 1).float()
+    x = (x + 1e-7 * torch.randn(x.shape, generator=g)).to(cuda_device).requires_grad_(True)    # straight-through residue
+    y = (torch.randint(0, 2, (m_y, d), generator=g) * 2 - 1).float()
+    y[:, : d // 8] = 1
+    y = y.to(cuda_device)
+    kernel = B.GaussianKernel(n_kernels=7).to(cuda_device)
+    M.last_path = None
+    val = B.maximum_mean_discrepancy_loss(x=x, y=y, kernel=kernel)
+    assert M.last_path == "i8"
+    val.backward()
+    assert x.grad.shape == x.shape and torch.isfinite(x.grad).all()
+    if m_x <= 1024:
+        want, scale = _terms(torch.sign(x.detach()).cpu().numpy(), y.cpu().numpy())
+        assert abs(float(val) - want) <= 1e-5 * scale
+    else:           # full cfg3: the oracle evaluates the kernel's (exact, separately verified) histograms in float64
+        from image_generation_b200.mmd_tc import mmd_histograms_i8, pack_pair_i8
+        hist = mmd_histograms_i8(pack_pair_i8(x, y).rows, m_x, d).cpu().numpy()
+        s = O.mmd_sums_from_histograms(hist, m_x + m_y)
+        want = (s[0] - 7.0 * m_x) / (m_x * (m_x - 1)) + (s[1] - 7.0 * m_y) / (m_y * (m_y - 1)) - 2.0 * s[2] / (m_x * m_y)
+        assert abs(float(val) - want) <= 1e-5 * (s[0] / m_x ** 2 + s[1] / m_y ** 2 + 2 * s[2] / (m_x * m_y))
+    M.last_path = None
+    xc = torch.randn((256, 64), generator=g).to(cuda_device).requires_grad_(True)
+    B.maximum_mean_discrepancy_loss(x=xc, y=y[:256, :64].contiguous(), kernel=kernel).backward()
+    assert M.last_path == "bf16x3" and torch.isfinite(xc.grad).all()
+
+
+@pytest.mark.parametrize("n_planes,tol", [(2, 2e-4), (3, 2e-6)])
+def test_fixed_point_backward_accuracy_by_digit_planes(cuda_device, n_planes, tol):
+    """d(MMD)/dx through the int8 GEMM: 2 digit planes (16-bit fixed point, the default) and 3 planes (24 bits)."""
+    from image_generation_b200.mmd_tc import mmd_backward_i8, pack_pair_i8
+    rng = np.random.default_rng(9)
+    m_x, m_y, d = 384, 300, 200
+    x, y = _spins(rng, m_x, d), _spins(rng, m_y, d)
+    y[:, :50] = 1.0
+    kern = B.GaussianKernel(7).to(cuda_device)
+    pair = pack_pair_i8(torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device), need_grad=True)
+    sums = mmd_block_sums(pair.rows[:, :d].contiguous(), m_x, kern, path="i8")
+    w_xx, w_xy = 2.0 / (m_x * (m_x - 1)), -2.0 / (m_x * m_y)
+    one = torch.ones((), device=cuda_device)
+    got = mmd_backward_i8(pair.rows, d, m_x, kern, sums, w_xx, w_xy, one, zt=pair.zt, n_planes=n_planes).cpu().numpy()
+    bw = O.gaussian_kernel_matrix(np.concatenate([x, y]).astype(np.float64))[1]
+    _, grad = O.mmd(x, y, bandwidth=bw, return_grad=True)
+    rel = np.linalg.norm(got - grad) / np.linalg.norm(grad)
+    assert rel < tol, rel
+    # a row range (what a rank of the sharded MMD asks for) and the transpose built on demand agree bit for bit
+    part = mmd_backward_i8(pair.rows, d, m_x, kern, sums, w_xx, w_xy, one, rows=(128, 200), n_planes=n_planes).cpu().numpy()
+    assert np.array_equal(part, got[128:328])
+
+
+def test_spin_extract_layouts(cuda_device):
+    """The fused extraction kernel: padded int8 rows, their transpose and the bit-packed statistics words from one pass,
+    for aligned and ragged row offsets, float and int8 input; and the non-spin detector."""
+    from image_generation_b200.mmd_tc import pack_pair_i8
+    from image_generation_b200.stats import edge_statistics, pack_spins
+    rng = np.random.default_rng(4)
+    g = B.IsingGraph.pegasus(2)
+    for m_x, m_y in ((256, 128), (70, 45), (129, 300)):
+        x = _spins(rng, m_x, g.n, residue=1e-7)
+        y = rng.choice([-1, 1], size=(m_y, g.n)).astype(np.int8)
+        sampler = B.BlockGibbsSampler(g, device=cuda_device)
+        dg = sampler.device_graph
+        flag = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+        pair = pack_pair_i8(torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device), need_grad=True,
+                            stats_pos=dg.pos, stats_n_pad=g.n_pad, nonspin=flag)
+        z = np.concatenate([np.sign(x).astype(np.int8), y])
+        rows = pair.rows.cpu().numpy()
+        assert np.array_equal(rows[:, :g.n], z) and not rows[:, g.n:].any()
+        zt = pair.zt.cpu().numpy()
+        assert np.array_equal(zt[:, :m_x + m_y], z.T) and not zt[:, m_x + m_y:].any()
+        assert int(flag) == 0
+        want = pack_spins(torch.from_numpy(x).to(cuda_device), dg)
+        assert torch.equal(pair.stats, want)
+        s1, s2 = edge_statistics(pair.stats, m_x, dg)
+        o1, o2 = O.edge_stats(g.n, g.edge_i, g.edge_j, np.sign(x).astype(np.int8))
+        assert np.array_equal(s1.cpu().numpy(), o1) and np.array_equal(s2.cpu().numpy()[: g.n_edges], o2)
+    bad = torch.from_numpy(x).to(cuda_device).clone()
+    bad[3, 5] = 0.5
+    flag = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    pack_pair_i8(bad, torch.from_numpy(y).to(cuda_device), nonspin=flag)
+    assert int(flag) == 1

@@ -204,3 +204,23 @@ def test_mmd_oracle_gradient_matches_finite_differences():
                     num[i, k] = (O.mmd(xp, y, squared=squared, estimator=est, bandwidth=bwfix)
                                  - O.mmd(xm, y, squared=squared, estimator=est, bandwidth=bwfix)) / 2e-6
             np.testing.assert_allclose(grad, num, rtol=2e-5, atol=1e-9)
+
+
+def test_hamming_histogram_form_of_the_mmd_matches_the_dense_oracle():
+    """The integer restatement the tcgen05 kernels compute (ordered-pair counts per Hamming distance, evaluated in
+    float64) is the dense kernel-matrix oracle, for every switch; shards of the pair set add up exactly."""
+    rng = np.random.default_rng(8)
+    z = rng.choice([-1, 1], size=(57, 40)).astype(np.int8)
+    z[30:, :9] = 1
+    m_x = 30
+    hist = O.hamming_histograms(z, m_x)
+    assert hist[0].sum() == m_x * m_x and hist[1].sum() == 27 * 27 and hist[2].sum() == m_x * 27
+    assert hist[0][0] >= m_x                                    # the diagonal sits at distance 0
+    parts = sum(O.hamming_histograms(z, m_x, (r, 4)) for r in range(4))
+    assert np.array_equal(parts, hist)
+    for squared in (False, True):
+        for bw in (None, 3.5):
+            got = O.mmd_sums_from_histograms(hist, 57, bandwidth=bw, squared=squared)
+            k, _, dist = O.gaussian_kernel_matrix(z.astype(np.float64), bandwidth=bw, squared=squared)
+            want = [k[:m_x, :m_x].sum(), k[m_x:, m_x:].sum(), k[:m_x, m_x:].sum(), dist.sum()]
+            np.testing.assert_allclose(got, want, rtol=1e-12)
