@@ -69,6 +69,7 @@ SIGNATURES = {
     "b200grbm_sweep_state_offset": ([_i32], _i32),
     "b200grbm_gibbs_sweeps": ([C.POINTER(SweepArgs), _vp], _i32),
     "b200grbm_last_launch_count": ([], _i32),
+    "b200grbm_last_sweep_kernel": ([], _i32),
     "b200grbm_ex2_probe": ([_f32, _f32, C.c_int64, C.POINTER(C.c_double), _vp], _i32),
     "b200grbm_pack_f32": ([_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp], _i32),
     "b200grbm_pack_i8": ([_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp], _i32),
@@ -86,7 +87,7 @@ SIGNATURES = {
     "b200grbm_spin_extract_f32": ([_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _f32, _vp], _i32),
     "b200grbm_spin_extract_i8": ([_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _f32, _vp], _i32),
     "b200grbm_transpose_i8": ([_vp, _i32, _i32, _i32, _vp, _i32, _vp], _i32),
-    "b200grbm_mmd_coef_i8": ([_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _f32, _f32, _vp, _vp,
+    "b200grbm_mmd_coef_i8": ([_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _vp, _f32, _f32, _vp, _vp,
                               _i32, _i32, _i32, _vp, _vp, _vp], _i32),
     "b200grbm_mmd_grad_i8": ([_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp], _i32),
     "b200grbm_gemm_bf16_tn": ([_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp], _i32),

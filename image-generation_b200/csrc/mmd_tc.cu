@@ -62,6 +62,7 @@ struct TcParams {
     int row0, n_rows, tiles_rows;       // row tiles covering the requested rows
     int m_pad, rows_alloc, n_planes;    // plane p = planes + p * rows_alloc * m_pad, row pitch m_pad
     float r_xx, r_xy;                   // w_xx / max(|w_xx|, |w_xy|), w_xy / max(...)
+    float q_max;                        // largest digit-plane magnitude (clamp for distances the scale did not see)
     int8_t *planes;
     long long *rowsum;                  // [n_rows] integer row sums of the quantised coefficients (accumulating)
     // L2-sized super-blocks of the tile triangle (forward pass): 4096 x 4096 entries = 32 x 16 tiles per
@@ -251,7 +252,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
                         const int col = col0 + cbase + c;
                         int q = 0;
                         if (col < p.m && col != row)
-                            q = __float2int_rn(lut[hamming_index(two_d, (int)v[c], p.d)] * (col < p.m_x ? p.r_xx : p.r_xy));
+                            q = __float2int_rn(fminf(fmaxf(lut[hamming_index(two_d, (int)v[c], p.d)], -p.q_max), p.q_max) *
+                                               (col < p.m_x ? p.r_xx : p.r_xy));
                         part += q;
                         // signed base-256 digits, least significant first: q = d0 + 256 d1 + 65536 d2
                         const int d0 = (q << 24) >> 24, q1 = (q - d0) >> 8;
@@ -354,8 +356,8 @@ __global__ void __launch_bounds__(1024) mmd_eval_hist_kernel(const unsigned long
 // n_planes base-256 digits represent.  scale_out[0] = max|c| * max(|w_xx|, |w_xy|) / Q  undoes it after the GEMM.
 __global__ void __launch_bounds__(1024) mmd_coef_lut_kernel(int d, int m, int n_kernels, float mul_factor, int squared,
                                                             float bandwidth, const double *__restrict__ sums, float w_xx,
-                                                            float w_xy, int n_planes, float *__restrict__ lut,
-                                                            double *__restrict__ scale_out)
+                                                            float w_xy, int n_planes, const unsigned long long *__restrict__ hist,
+                                                            float *__restrict__ lut, double *__restrict__ scale_out)
 {
     __shared__ double scratch[32];
     const double mm = (double)m;
@@ -372,7 +374,9 @@ __global__ void __launch_bounds__(1024) mmd_coef_lut_kernel(int d, int m, int n_
             }
             c = squared ? 2.0 * dk : dk / t;
         }
-        cmax = fmax(cmax, fabs(c));
+        // with the forward's histograms at hand the fixed-point range covers only distances that occur among the
+        // x-x and x-y pairs (|c| grows steeply towards h = 1, which real data rarely reaches: ~7 bits regained)
+        if (hist == nullptr || (hist[h] | hist[2 * ((size_t)d + 1) + h]) != 0ull) cmax = fmax(cmax, fabs(c));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
@@ -596,9 +600,9 @@ extern "C" int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int
 
 extern "C" int32_t b200grbm_mmd_coef_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,
                                         int32_t row0, int32_t n_rows, int32_t n_kernels, float mul_factor, int32_t squared,
-                                        float bandwidth, const double *sums_dev, float w_xx, float w_xy, float *lut_dev,
-                                        int8_t *planes_dev, int32_t n_planes, int32_t rows_alloc, int32_t m_pad,
-                                        int64_t *rowsum_dev, double *scale_dev, void *stream)
+                                        float bandwidth, const double *sums_dev, const uint64_t *hist_dev, float w_xx,
+                                        float w_xy, float *lut_dev, int8_t *planes_dev, int32_t n_planes, int32_t rows_alloc,
+                                        int32_t m_pad, int64_t *rowsum_dev, double *scale_dev, void *stream)
 {
     if (m_x <= 0 || m_y <= 0 || d <= 0 || d_pad < d || d_pad % 16 != 0)
         return fail(B200GRBM_EINVAL, "mmd_coef_i8: m_x=%d m_y=%d d=%d d_pad=%d", m_x, m_y, d, d_pad);
@@ -637,6 +641,7 @@ extern "C" int32_t b200grbm_mmd_coef_i8(const int8_t *z_dev, int32_t m_x, int32_
     p.m_pad = m_pad; p.rows_alloc = rows_alloc; p.n_planes = n_planes;
     p.r_xx = wmax > 0.f ? w_xx / wmax : 0.f;
     p.r_xy = wmax > 0.f ? w_xy / wmax : 0.f;
+    p.q_max = n_planes >= 3 ? 8355711.0f : 32639.0f;
     p.planes = planes_dev;
     p.rowsum = reinterpret_cast<long long *>(rowsum_dev);
     B200_CUDA(cudaFuncSetAttribute(mmd_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -644,7 +649,7 @@ extern "C" int32_t b200grbm_mmd_coef_i8(const int8_t *z_dev, int32_t m_x, int32_
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     B200_CUDA(cudaMemsetAsync(rowsum_dev, 0, (size_t)n_rows * sizeof(int64_t), st));
     mmd_coef_lut_kernel<<<1, 1024, 0, st>>>(d, m, n_kernels, mul_factor, squared, bandwidth, sums_dev, w_xx, w_xy, n_planes,
-                                            lut_dev, scale_dev);
+                                            reinterpret_cast<const unsigned long long *>(hist_dev), lut_dev, scale_dev);
     B200_CUDA(cudaGetLastError());
     mmd_gram_i8_kernel<<<grid, TC_THREADS, smem, st>>>(tmap, p);
     B200_CUDA(cudaGetLastError());

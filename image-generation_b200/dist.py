@@ -93,7 +93,7 @@ class _ShardedMMD(torch.autograd.Function):
     def backward(ctx, grad_out):
         z, sums = ctx.saved_tensors
         kernel, w_xx, w_xy, m_x, d, row0, n_rows, ops = ctx.meta
-        grad = ops.backward(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out.detach().reshape(()), (row0, n_rows))
+        grad = ops.backward(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out.detach().reshape(()), (row0, n_rows), ctx.hist)
         return grad, None, None, None, None, None
 
 
@@ -117,9 +117,9 @@ class _DeviceOps:
         return mmd_sums_from_histograms(hist, m_x, m_y, kernel)
 
     @staticmethod
-    def backward(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out, rows):
+    def backward(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out, rows, hist):
         from .mmd_tc import mmd_backward_i8
-        return mmd_backward_i8(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out, rows=rows)
+        return mmd_backward_i8(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out, rows=rows, hist=hist)
 
 
 def sharded_mmd_loss(x_local: torch.Tensor, y_local: torch.Tensor, kernel, *, estimator: str = "unbiased",

@@ -135,7 +135,7 @@ class _MMDFunction(torch.autograd.Function):
             from .mmd_tc import mmd_block_sums_i8, pack_pair_i8
             # sign-packed, zero-padded int8 rows (+ their transpose when a gradient will be asked for), kept for backward
             pair = packed if packed is not None else pack_pair_i8(x, y, need_grad=ctx.needs_input_grad[0])
-            sums = mmd_block_sums_i8(pair.rows, m_x, kernel, d=d)
+            sums, hist = mmd_block_sums_i8(pair.rows, m_x, kernel, d=d, return_hist=True)
         elif path in ("bf16", "bf16x3"):
             from .mmd_tc import mmd_block_sums_bf16
             z = torch.cat([x.detach().to(torch.float32), y.detach().to(torch.float32)], 0).contiguous()
@@ -148,7 +148,7 @@ class _MMDFunction(torch.autograd.Function):
         val, w_xx, w_xy = _estimate(sums, m_x, m_y, kernel, estimator)
         if pair is not None:
             ctx.save_for_backward(pair.rows, sums)
-            ctx.zt = pair.zt
+            ctx.zt, ctx.hist = pair.zt, hist
         else:
             ctx.save_for_backward(z, sums)
         ctx.meta = (m_x, m_y, kernel, w_xx, w_xy, path, d)
@@ -160,7 +160,8 @@ class _MMDFunction(torch.autograd.Function):
         m_x, m_y, kernel, w_xx, w_xy, path, d = ctx.meta
         if path == "i8":
             from .mmd_tc import mmd_backward_i8
-            return (mmd_backward_i8(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out.detach().reshape(()), zt=ctx.zt),
+            return (mmd_backward_i8(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out.detach().reshape(()), zt=ctx.zt,
+                                    hist=ctx.hist),
                     None, None, None, None, None)
         if path in ("bf16", "bf16x3"):
             from .mmd_tc import mmd_backward_bf16

@@ -124,9 +124,11 @@ def mmd_sums_from_histograms(hist: torch.Tensor, m_x: int, m_y: int, kernel, sum
     return sums
 
 
-def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = None, d: int = None) -> torch.Tensor:
+def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = None, d: int = None,
+                      return_hist: bool = False):
     """``[S_xx, S_yy, S_xy, sum_ab t_ab]`` (float64) for +-1 rows ``z = [x; y]`` on tensor cores.
-    ``d``: true feature count when ``z`` is already the zero-padded int8 matrix of :func:`pack_rows_i8`."""
+    ``d``: true feature count when ``z`` is already the zero-padded int8 matrix of :func:`pack_rows_i8`.
+    ``return_hist``: also return the ``(3, d + 1)`` Hamming histograms the sums were evaluated from."""
     m = z.shape[0]
     if d is None:
         d = z.shape[1]
@@ -142,7 +144,7 @@ def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = No
         _lib.check(lib.b200grbm_mmd_forward_i8(_lib.ptr(zi), m_x, m - m_x, d, d_pad, kernel.n_kernels,
                                                kernel.mul_factor, int(kernel.squared), bw, _lib.ptr(hist),
                                                _lib.ptr(sums), _lib.current_stream(z.device)))
-    return sums
+    return (sums, hist) if return_hist else sums
 
 
 def gemm_bf16_tn(a_hi: torch.Tensor, a_lo, b: torch.Tensor, m_rows: int) -> torch.Tensor:
@@ -177,11 +179,12 @@ def transpose_i8(zi: torch.Tensor, d: int, m_pad: int) -> torch.Tensor:
 
 def mmd_backward_i8(zi: torch.Tensor, d: int, m_x: int, kernel, sums: torch.Tensor, w_xx: float, w_xy: float,
                     grad_out: torch.Tensor, zt: torch.Tensor = None, rows: tuple = None,
-                    n_planes: int = None) -> torch.Tensor:
+                    n_planes: int = None, hist: torch.Tensor = None) -> torch.Tensor:
     """d(MMD)/dx for +-1 rows on int8 tensor cores: the coefficient matrix from a second int8 Gram as ``n_planes``
     base-256 fixed-point digit planes plus exact integer row sums, then the int8 GEMM against ``Z^T``:
     ``grad_x[a] = g (rowsum_a x_a - (A Z)_a)``.  ``zi``: the packed int8 ``(m, d_pad)`` rows of the forward;
-    ``zt``: their transpose if the forward kept it; ``rows = (row0, n_rows)``: gradient rows (default: all of x)."""
+    ``zt``: their transpose if the forward kept it; ``rows = (row0, n_rows)``: gradient rows (default: all of x);
+    ``hist``: the forward's Hamming histograms (the fixed-point range then covers only distances that occur)."""
     m, d_pad = zi.shape
     dev = zi.device
     n_planes = GRAD_PLANES if n_planes is None else int(n_planes)
@@ -201,8 +204,8 @@ def mmd_backward_i8(zi: torch.Tensor, d: int, m_x: int, kernel, sums: torch.Tens
     with torch.cuda.device(dev):
         st = _lib.current_stream(dev)
         _lib.check(lib.b200grbm_mmd_coef_i8(_lib.ptr(zi), m_x, m - m_x, d, d_pad, int(row0), int(n_rows), kernel.n_kernels,
-                                            kernel.mul_factor, int(kernel.squared), bw, _lib.ptr(sums), w_xx, w_xy,
-                                            _lib.ptr(lut), _lib.ptr(planes), n_planes, rows_alloc, m_pad, _lib.ptr(rowsum),
+                                            kernel.mul_factor, int(kernel.squared), bw, _lib.ptr(sums), _lib.ptr(hist), w_xx,
+                                            w_xy, _lib.ptr(lut), _lib.ptr(planes), n_planes, rows_alloc, m_pad, _lib.ptr(rowsum),
                                             _lib.ptr(scale), st))
         _lib.check(lib.b200grbm_mmd_grad_i8(_lib.ptr(planes), n_planes, int(n_rows), rows_alloc, m_pad, _lib.ptr(zt), d,
                                             _lib.ptr(rowsum), _lib.ptr(scale), _lib.ptr(g), _lib.ptr(zi), int(row0), d_pad,

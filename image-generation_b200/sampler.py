@@ -375,6 +375,7 @@ class BlockGibbsSampler:
         self._packed_scratch: dict = {}
         self._generation = 0
         self.last_launches = 0
+        self.last_kernel = "packed"
         self.last_plan: tuple[int, int] = (0, 0)
 
     # ------------------------------------------------------------------ plumbing
@@ -571,6 +572,7 @@ class BlockGibbsSampler:
         with torch.cuda.device(dev):
             _lib.check(lib.b200grbm_gibbs_sweeps(C.byref(a), _lib.current_stream(dev)))
             self.last_launches = lib.b200grbm_last_launch_count()
+            self.last_kernel = "small" if lib.b200grbm_last_sweep_kernel() == 1 else "packed"
             energies = None
             if samples is not None:
                 energies = out[1] if out is not None else torch.empty(num_reads, dtype=torch.float64, device=dev)
@@ -583,7 +585,7 @@ class BlockGibbsSampler:
         gen = self._generation
         return SampleSet(self.variables, samples, energies,
                          info={"seed": int(seed), "chains_per_lane": cpl, "threads": threads,
-                               "num_sweeps": num_sweeps, "accept": self.accept},
+                               "num_sweeps": num_sweeps, "accept": self.accept, "kernel": self.last_kernel},
                          packed=packed, packed_is_current=lambda: self._generation == gen)
 
 

@@ -123,6 +123,10 @@ int32_t b200grbm_ex2_probe(float x_lo, float x_hi, int64_t n, double *max_rel_er
 
 /* number of kernel launches the last b200grbm_gibbs_sweeps call on this thread enqueued */
 int32_t b200grbm_last_launch_count(void);
+/* which sweep kernel that call chose: 0 = chains bit-packed per lane (throughput), 1 = one chain per lane column with
+ * every round's table in registers (small problems: chains_per_lane == 4, <= 5 colour rounds of <= 256 spins,
+ * degree <= 20, few enough chains for all CTAs to be resident at once) */
+int32_t b200grbm_last_sweep_kernel(void);
 
 /*
  * Sign-pack rows of real-valued spins (encoder output, src/model_wrapper.py:297,318) or int8
@@ -258,15 +262,17 @@ int32_t b200grbm_transpose_i8(const int8_t *in_dev, int32_t rows, int32_t cols, 
  * writes A as n_planes (2 or 3) signed base-256 digit planes of a fixed-point number -- planes_dev
  * [n_planes][rows_alloc][m_pad] int8, most significant plane first, m_pad a multiple of 128 >= m, padding columns
  * zero -- plus the exact integer row sums (rowsum_dev [n_rows]) and the value of one fixed-point unit (scale_dev,
- * device scalar).  lut_dev: workspace of d + 1 floats.  sums_dev[3] is the forward's distance sum.
+ * device scalar).  lut_dev: workspace of d + 1 floats.  sums_dev[3] is the forward's distance sum.  hist_dev
+ * (optional): the forward's histograms -- the fixed-point range then spans only the distances that occur (coefficients
+ * of other distances, if any, saturate).
  * b200grbm_mmd_grad_i8 contracts the planes with zt_dev (Z transposed, [d][m_pad] int8) on tcgen05.mma.kind::i8 and
  * writes grad_x_dev [n_rows][d] = grad_out * scale * (rowsum_a z_ai - sum_b q_ab z_bi); z_dev row z_row0 + a is x_a.
  */
 int32_t b200grbm_mmd_coef_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad, int32_t row0,
                              int32_t n_rows, int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth,
-                             const double *sums_dev, float w_xx, float w_xy, float *lut_dev, int8_t *planes_dev,
-                             int32_t n_planes, int32_t rows_alloc, int32_t m_pad, int64_t *rowsum_dev, double *scale_dev,
-                             void *stream);
+                             const double *sums_dev, const uint64_t *hist_dev, float w_xx, float w_xy, float *lut_dev,
+                             int8_t *planes_dev, int32_t n_planes, int32_t rows_alloc, int32_t m_pad, int64_t *rowsum_dev,
+                             double *scale_dev, void *stream);
 int32_t b200grbm_mmd_grad_i8(const int8_t *planes_dev, int32_t n_planes, int32_t n_rows, int32_t rows_alloc, int32_t m_pad,
                              const int8_t *zt_dev, int32_t d, const int64_t *rowsum_dev, const double *scale_dev,
                              const float *grad_out_dev, const int8_t *z_dev, int32_t z_row0, int32_t d_pad,

@@ -92,7 +92,7 @@ class _NumpyOps:
                                                            kernel.bandwidth, kernel.squared))
 
     @staticmethod
-    def backward(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out, rows):
+    def backward(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out, rows, hist):
         from oracle import oracle as O
         zz = z.numpy().astype(np.float64)
         m = zz.shape[0]

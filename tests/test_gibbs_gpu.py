@@ -411,3 +411,65 @@ def test_full_size_cfg4_shard_properties(cuda_device):
         xs = sh.sample_ising(h, J, num_reads=cnt, num_sweeps=sweeps, seed=seed).samples_tensor
         parts.append(edge_statistics(pack_spins(xs, sh.device_graph), cnt, sh.device_graph))
     assert torch.equal(parts[0][0] + parts[1][0], s1) and torch.equal(parts[0][1] + parts[1][1], s2)
+
+
+# ------------------------------------------------------------------ one-chain-per-lane kernel (small problems)
+
+@pytest.mark.parametrize("graph,chains", [("ckpt", 256), ("p3", 70), ("p4", 37), ("z2", 9)])
+def test_small_problem_kernel_bit_exact_all_modes(cuda_device, golden, monkeypatch, graph, chains):
+    """The reference's default call (256 reads on a 256-spin sub-graph) runs on gibbs_small_kernel: one (spin, chain)
+    pair per thread, tables in registers.  Same contract: supplied uniforms and native Philox (exact) equal the oracle
+    bit for bit for 4 / 2 / 1 chains per CTA and ragged chain counts, and equal the throughput kernel's output."""
+    if graph == "ckpt":
+        z, _ = golden
+        name = "Advantage2_system1_10_epochs"
+        g = B.IsingGraph.build(256, z[name + "/edge_i"], z[name + "/edge_j"])
+    else:
+        g = {"p3": B.IsingGraph.pegasus(3), "p4": B.IsingGraph.pegasus(4), "z2": B.IsingGraph.zephyr(2)}[graph]
+    h, J = _problem(g, 31, h_scale=0.4, j_scale=0.8)
+    csr = _oracle_csr(g)
+    sweeps, seed, off = 7, 0x5EED5, 12
+    beta = np.geomspace(0.2, 4.0, sweeps)
+    s = B.BlockGibbsSampler(g, device=cuda_device, chain_offset=off)
+    s.device_graph.set_weights(torch.from_numpy(h), torch.from_numpy(J))
+    threads = s.device_graph.default_threads
+    want = O.gibbs(csr, h, J, O.init_state(csr, chains, seed, chain_offset=off), beta, seed=seed, chain_offset=off)
+    ss = s._run(chains, None, None, None, beta, seed, None, None, plan=(4, threads))
+    assert ss.info["kernel"] == "small"
+    assert np.array_equal(ss.record.sample, want)
+    np.testing.assert_allclose(ss.record.energy, O.energies(g.n, g.edge_i, g.edge_j, h, J, want), rtol=1e-12, atol=1e-9)
+    packed_small = ss.packed[:, : g.n].clone()          # positions beyond n are padding
+    # supplied uniforms + initial states
+    rng = np.random.default_rng(6)
+    U = rng.uniform(1e-6, 1 - 1e-6, size=(sweeps, chains, g.n)).astype(np.float32)
+    init = rng.choice([-1, 1], size=(chains, g.n)).astype(np.int8)
+    want_u = O.gibbs(csr, h, J, init, beta, uniforms=U)
+    got_u = s._run(chains, None, None, None, beta, 0, init, torch.from_numpy(U), plan=(4, threads))
+    assert got_u.info["kernel"] == "small" and np.array_equal(got_u.record.sample, want_u)
+    # the throughput kernel (4 chains bit-packed per lane) on the same call: identical samples and packed words
+    monkeypatch.setenv("B200GRBM_SMALL", "0")
+    ref = s._run(chains, None, None, None, beta, seed, None, None, plan=(4, threads))
+    assert ref.info["kernel"] == "packed"
+    assert np.array_equal(ref.record.sample, want) and torch.equal(ref.packed[:, : g.n], packed_small)
+
+
+def test_small_problem_kernel_persistent_chains_resume(cuda_device, golden):
+    """advance(a); advance(b) == advance(a + b) through the small kernel (packed state read and rewritten in place)."""
+    z, _ = golden
+    name = "Advantage2_system1_10_epochs"
+    g = B.IsingGraph.build(256, z[name + "/edge_i"], z[name + "/edge_j"])
+    h, J = _problem(g, 5)
+    outs = []
+    for split in ((9,), (4, 5)):
+        s = B.BlockGibbsSampler(g, device=cuda_device, seed=3)
+        s.device_graph.set_weights(torch.from_numpy(h), torch.from_numpy(J))
+        pc = B.PersistentChains(s, 130)
+        for k in split:
+            ss = pc.advance(k)
+        assert ss.info["kernel"] == "small"
+        outs.append(ss.record.sample.copy())
+    assert np.array_equal(outs[0], outs[1])
+    csr = _oracle_csr(g)
+    seed = pc.seed
+    want = O.gibbs(csr, h, J, O.init_state(csr, 130, seed), [1.0] * 9, seed=seed)
+    assert np.array_equal(outs[0], want)

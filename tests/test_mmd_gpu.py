@@ -317,7 +317,7 @@ def test_full_size_cfg3_coefficient_tiles_vs_float64_oracle(cuda_device):
     scale = torch.empty(1, dtype=torch.float64, device=cuda_device)
     lut = torch.empty(d + 1, dtype=torch.float32, device=cuda_device)
     lib = _lib.load()
-    _lib.check(lib.b200grbm_mmd_coef_i8(_lib.ptr(zi), m, m, d, d_pad, 0, m, 7, 2.0, 0, -1.0, _lib.ptr(sums), w_xx, w_xy,
+    _lib.check(lib.b200grbm_mmd_coef_i8(_lib.ptr(zi), m, m, d, d_pad, 0, m, 7, 2.0, 0, -1.0, _lib.ptr(sums), None, w_xx, w_xy,
                                         _lib.ptr(lut), _lib.ptr(planes), n_planes, m, m_pad, _lib.ptr(rowsum), _lib.ptr(scale),
                                         _lib.current_stream(cuda_device)))
     q = (planes[0].to(torch.int32) * 65536 + planes[1].to(torch.int32) * 256 + planes[2].to(torch.int32))

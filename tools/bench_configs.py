@@ -46,5 +46,5 @@ for a, b in ev:
 torch.cuda.synchronize()
 ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
 print(json.dumps({"graph": args.graph, "n": g.n, "edges": g.n_edges, "chains": args.chains, "sweeps": args.sweeps,
-                  "anneal": args.anneal, "accept": args.accept, "lib": os.path.basename(args.lib), "plan": s.last_plan, "ms": ms,
+                  "anneal": args.anneal, "accept": args.accept, "lib": os.path.basename(args.lib), "plan": s.last_plan, "kernel": s.last_kernel, "ms": ms,
                   "spin_updates_per_s": args.chains * args.sweeps * g.n / ms * 1e3}))
