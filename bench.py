@@ -8,7 +8,7 @@ Workload (config.workload): BASELINE.json configs[1] -- block-Gibbs sampling on 
 P16 fabric graph (5 640 spins, 40 484 couplers), 4 096 chains x 1 000 sweeps at beta = 1 per
 GPU, synthetic h ~ U(-0.05, 0.05) * prefactor, J ~ U(-5, 5) * prefactor, prefactor 0.05
 (SURVEY.md section 8d cfg2).  A *step* is one pass of the hot path over one batch of chains:
-sampler.sample (sweeps + sample energies) followed by the integer edge statistics of the
+sampler.sample_grbm (sweeps + sample energies) followed by the integer edge statistics of the
 samples; at N > 1 each rank owns 4 096 chains of the global chain-id space (weak scaling, no
 data-path collective) and the step ends with the path's one exchange, an NCCL all-reduce of
 the N + E int64 counters.
@@ -19,7 +19,16 @@ the N + E int64 counters.
 `roofline`: dominant kernel b200grbm::gibbs_kernel.  SURVEY.md section 8(d): the sweep is not HBM bound (one
            state read + write per launch); algorithmic bytes are (mean degree + 1) per update against the
            shared-memory roof n_SM x 128 B/clk x f_SM; the HBM view is reported next to it.
-`cpu_baseline`: the oracle port's textbook double-precision sequential heat bath on the box's host cores.
+`cpu_baseline`: the oracle port's textbook double-precision sequential heat bath on the box's host cores (N = 1 only).
+
+Blocks next to the headline, measured at EVERY N (they are what SCALE_rNN.json carries for BASELINE.json's other
+multi-GPU configurations):
+`cfg4`       : configs[3] -- Zephyr Z15, 262 144 chains split over the N ranks (STRONG scaling), 100 sweeps, integer
+               statistics + the NCCL int64 all-reduce per step; at N > 1 rank 0 also runs the whole job alone, in the
+               same process, for `strong_scaling_vs_n1`.
+`mmd_sharded`: configs[2] with the 8 192 + 8 192 rows sharded over the ranks: int8 all-gather, each rank contracts
+               its share of the Gram tiles, one int64 all-reduce of the Hamming histograms; checked equal, count for
+               count and bit for bit, to the single-GPU result.
 """
 import argparse
 import json
@@ -36,6 +45,8 @@ import numpy as np  # noqa: E402
 
 P16_MEAN_DEGREE = 2 * 40484 / 5640.0
 CFG = dict(pegasus_m=16, chains=4096, sweeps=1000, prefactor=0.05, beta=1.0, seed=775321899904)
+WORKLOAD = ("GRBM block-Gibbs, Pegasus P16 (5640 spins, 40484 couplers), 4096 chains x 1000 sweeps per GPU, beta=1, "
+            "prefactor 0.05 (BASELINE.json configs[1])")
 
 
 def make_problem(cfg):
@@ -109,7 +120,8 @@ def cpu_port_rate(g, h, J, beta, target_seconds, threads=None):
     t = time.perf_counter()
     O.gibbs(csr, h, J, st, [beta] * sweeps, seed=2, f64=True)
     dt = time.perf_counter() - t
-    return chains * sweeps * g.n / dt, cores, f"Pegasus P16, {chains} chains x {sweeps} sweeps ({dt:.1f} s), oracle_gibbs_f64"
+    return (chains * sweeps * g.n / dt, cores, f"Pegasus P16, {chains} chains x {sweeps} sweeps ({dt:.1f} s), oracle_gibbs_f64",
+            {"chains": chains, "sweeps": sweeps, "seconds": dt})
 
 
 def run_reference(args):
@@ -117,19 +129,26 @@ def run_reference(args):
     if rank != 0:
         return
     g, h, J = make_problem(CFG)
-    rates, sample, cores = [], "", 1
+    rates, sample, cores, last = [], "", 1, {}
     per_step = max(1.0, min(15.0, 120.0 / max(1, args.steps + args.warmup)))
     for k in range(args.warmup + args.steps):
-        r, cores, sample = cpu_port_rate(g, h, J, CFG["beta"], per_step)
+        r, cores, sample, last = cpu_port_rate(g, h, J, CFG["beta"], per_step)
         if k >= args.warmup:
             rates.append(r)
     val = float(np.mean(rates))
+    full_updates = CFG["chains"] * CFG["sweeps"] * g.n
     line = {
         "impl": "reference", "metric": "grbm_spin_updates_per_s", "value": val, "unit": "spin-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * CFG["chains"] * CFG["sweeps"] * g.n / val, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * full_updates / val, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "GRBM block-Gibbs, Pegasus P16 (5640 spins, 40484 couplers), 4096 chains x 1000 sweeps, beta=1"},
+        "config": {"workload": WORKLOAD},
+        # every step times a BOUNDED sample of the workload; ms_per_step is what the full 4096 x 1000 step would take
+        # at the measured rate -- an extrapolation, not a measured full step
+        "extrapolated_from": {"sample_chains": last.get("chains"), "sample_sweeps": last.get("sweeps"),
+                              "sample_seconds": last.get("seconds"), "sample_updates": last.get("chains", 0) * last.get("sweeps", 0) * g.n,
+                              "full_step_updates": full_updates,
+                              "note": "ms_per_step = full_step_updates / measured rate; the timed region per step is the sample"},
         "cpu_baseline": {"value": val, "unit": "spin-updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "spin-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -137,6 +156,21 @@ def run_reference(args):
                 "of the reference-style sequential heat bath on all host threads, each step a bounded sample",
     }
     print(json.dumps(line))
+
+
+def _load_profile_metrics():
+    """ncu-derived constants of the dominant kernel, written by tools/ncu_summary.py --json from the committed capture
+    (never literals in this file)."""
+    for name in ("r2_gibbs_ncu_metrics.json", "r1_gibbs_v5_ncu_metrics.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            try:
+                d = json.load(open(path))
+                d["file"] = "profiles/" + name
+                return d
+            except (OSError, ValueError):
+                pass
+    return None
 
 
 def run_b200(args):
@@ -163,28 +197,25 @@ def run_b200(args):
                                   chain_offset=rank * chains)
     dg = sampler.device_graph
     h_d, J_d = torch.from_numpy(h).to(dev), torch.from_numpy(J).to(dev)
-    dg.set_weights(h_d, J_d)
     sum_s = torch.zeros(g.n, dtype=torch.int64, device=dev)
     sum_ss = torch.zeros(g.n_edges, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    plan = (args.cpl, args.threads) if args.cpl and args.threads else None
     launches = {"n": 0}
 
     # caller-owned output buffers: the steady state allocates nothing (a cudaMalloc between the
     # start event and the launch would be charged to the kernel)
     out_bufs = (torch.empty((chains, g.n), dtype=torch.int8, device=dev), torch.empty(chains, dtype=torch.float64, device=dev))
 
-    def step_device():
-        ss = sampler._run(chains, sweeps, None, None, None, None, None, None, plan=plan, out=out_bufs)
-        n_l = sampler.last_launches
+    def sample():
+        # the public device-resident call (what GraphRestrictedBoltzmannMachine.sample makes): h, J already in HBM
+        return sampler.sample_grbm(h_d, J_d, 1.0, num_reads=chains, num_sweeps=sweeps, out=out_bufs)
+
+    def finish_step(ss):
         sum_s.zero_(); sum_ss.zero_()
         sample_statistics(ss, dg, out=(sum_s, sum_ss))
-        n_l += 2                                    # edge + node statistics kernels (on the sampler's packed state)
         if world > 1:
             a, b = allreduce_statistics([sum_s, sum_ss])
             sum_s.copy_(a); sum_ss.copy_(b)
-        launches["n"] += n_l
-        return ss
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -196,9 +227,8 @@ def run_b200(args):
     if not args.no_clocks:
         clocks.start()                              # started before warm-up so the GPU never idles before step 0
     for _ in range(args.warmup):
-        step_device()
+        finish_step(sample())
     sync_all()
-    launches["n"] = 0
     t_wall0 = time.time()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -208,16 +238,12 @@ def run_b200(args):
         sync_all()
         ev[k][0].record()
         kev[k][0].record()                          # the dominant kernel alone, on the stream it is launched on
-        ss = sampler._run(chains, sweeps, None, None, None, None, None, None, plan=plan, out=out_bufs)
+        ss = sample()
         kev[k][1].record()
-        n_l = sampler.last_launches
-        sum_s.zero_(); sum_ss.zero_()
-        sample_statistics(ss, dg, out=(sum_s, sum_ss))
-        if world > 1:
-            a, b = allreduce_statistics([sum_s, sum_ss])
-            sum_s.copy_(a); sum_ss.copy_(b)
+        n_l = 2 + sampler.last_launches             # set_weights (edge + node kernels) + sweeps + sample energies
+        finish_step(ss)
         ev[k][1].record()
-        launches["n"] += n_l + 2
+        launches["n"] += n_l + 2                    # edge + node statistics kernels (on the sampler's packed state)
     sync_all()
     t_wall1 = time.time()
     clk = clocks.stop(t_wall0, t_wall1)
@@ -256,6 +282,14 @@ def run_b200(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = updates_per_step * e2e_steps / float(e2e_s)
 
+    # ---- BASELINE.json configs[3] and the cross-rank MMD: every rank takes part
+    del out_bufs, flush
+    torch.cuda.empty_cache()
+    cfg4 = mmd_sh = None
+    if not args.skip_extra:
+        cfg4 = bench_cfg4(dev, rank, world)
+        mmd_sh = bench_mmd_sharded(dev, rank, world)
+
     # every rank leaves the process group here, together; the CPU baseline and the side metrics
     # below are rank-0-only work with no collective in them
     if world > 1:
@@ -264,7 +298,7 @@ def run_b200(args):
     if rank != 0:
         return
 
-    kernel_s = float(kern_ms.mean()) / 1e3            # gibbs_kernel + the small energy kernel behind it
+    kernel_s = float(kern_ms.mean()) / 1e3            # set_weights + gibbs_kernel + the small energy kernel behind it
     upd_per_launch = chains * sweeps * g.n
     alg_bytes = (P16_MEAN_DEGREE + 1.0) * upd_per_launch
     peaks = {}
@@ -278,43 +312,49 @@ def run_b200(args):
     smem_peak = sms * 128 * f_sm / 1e9
     achieved = alg_bytes / kernel_s / 1e9
     hbm_bytes = 2.0 * chains * g.n                      # int8 state written once (+ read when resuming chains)
+    prof = _load_profile_metrics()
     roofline = {
         "bound": "smem", "kernel": "b200grbm::gibbs_kernel", "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
         "frac": achieved / smem_peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one gibbs_kernel launch in the committed ncu --set full capture
-        # (profiles/r1_gibbs_v5_ncu_summary.txt; 20-sweep launch, part of the final state write still sits in L2)
-        "traffic": 14288640 + 13467904, "traffic_note": "ncu capture of a 20-sweep launch; algorithmic HBM bytes per launch = state write 23.1 MB",
-        "algorithmic_bytes_per_update": P16_MEAN_DEGREE + 1.0, "updates_per_launch": upd_per_launch,
+        "traffic": None, "algorithmic_bytes_per_update": P16_MEAN_DEGREE + 1.0, "updates_per_launch": upd_per_launch,
         "kernel_ms": kernel_s * 1e3,
         "peak_source": f"SURVEY.md 8(d): n_SM({sms}) x 128 B/clk x SM clock sampled under load ({f_sm / 1e6:.0f} MHz)",
         "hbm": {"achieved": hbm_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": hbm_bytes / kernel_s / 1e9 / hbm_peak,
+                "frac": hbm_bytes / kernel_s / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": hbm_bytes,
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
-        # the binding resource: warp-instruction issue.  40.5 warp instructions per 32 spin-updates is the count ncu
-        # reports for this kernel (smsp__inst_executed.sum / updates, profiles/r1_gibbs_v5_ncu_summary.txt;
-        # 56.6 before the lazy-acceptance kernel)
-        "issue": {"warp_instr_per_32_updates": 40.5, "peak_updates_per_s": sms * 4 * 32 / 40.5 * f_sm,
-                  "frac": (upd_per_launch / kernel_s) / (sms * 4 * 32 / 40.5 * f_sm),
-                  "ncu_issue_active_frac": 0.764},
         "note": "state is bit-packed (28 chains per word) so the kernel is issue-bound, not byte-bound; see DESIGN.md 5.1",
     }
-    cpu_rate, cores, sample = cpu_port_rate(g, h, J, CFG["beta"], args.cpu_seconds)
+    if prof:
+        # read from the committed ncu capture (tools/ncu_summary.py --json): DRAM traffic of one launch and the warp
+        # instructions per 32 spin-updates that set the issue roof
+        roofline["traffic"] = prof.get("dram_bytes_per_launch")
+        roofline["traffic_source"] = prof.get("file")
+        wi = prof.get("warp_instr_per_32_updates")
+        if wi:
+            roofline["issue"] = {"warp_instr_per_32_updates": wi, "peak_updates_per_s": sms * 4 * 32 / wi * f_sm,
+                                 "frac": (upd_per_launch / kernel_s) / (sms * 4 * 32 / wi * f_sm),
+                                 "ncu_issue_active_frac": prof.get("issue_active_frac"), "source": prof.get("file")}
     line = {
         "metric": "grbm_spin_updates_per_s", "value": value, "unit": "spin-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"GRBM block-Gibbs, Pegasus P16 ({g.n} spins, {g.n_edges} couplers), {chains} chains x "
-                               f"{sweeps} sweeps per GPU, beta=1, prefactor 0.05 (BASELINE.json configs[1])",
+        "config": {"workload": WORKLOAD,
                    "chains_per_gpu": chains, "sweeps": sweeps, "accept": args.accept,
                    "chains_per_lane": timed_plan[0], "threads": timed_plan[1],
                    "l2": "256 MB buffer written between timed steps", "parallelism": f"chains sharded x{world}",
-                   "exchange": "int64 all-reduce of N+E counters per step" if world > 1 else "none"},
+                   "exchange": "int64 all-reduce of N+E counters per step" if world > 1 else "none",
+                   "api": "BlockGibbsSampler.sample_grbm (device-resident h, J) + stats.sample_statistics"},
         "e2e": {"value": e2e_val, "unit": "spin-updates/s", "h2d_bytes_per_step": int(4 * (g.n + g.n_edges)),
                 "d2h_bytes_per_step": int(chains * g.n + 8 * chains), "steps": e2e_steps},
         "gpu_launches": launches["n"], "clocks": clk, "roofline": roofline,
         "step_ms": [round(float(v), 3) for v in step_ms.tolist()],
-        "cpu_baseline": {"value": cpu_rate, "unit": "spin-updates/s", "cores": cores, "kind": "port", "sample": sample},
     }
+    if world == 1:
+        cpu_rate, cores, sample_txt, _ = cpu_port_rate(g, h, J, CFG["beta"], args.cpu_seconds)
+        line["cpu_baseline"] = {"value": cpu_rate, "unit": "spin-updates/s", "cores": cores, "kind": "port", "sample": sample_txt}
+    if cfg4 is not None:
+        line["cfg4"] = cfg4
+        line["mmd_sharded"] = mmd_sh
     if not args.skip_extra:
         line["sweep_variants"] = bench_sweep_variants(dev, g, h, J)
         line["mmd"] = bench_mmd(dev, peaks)
@@ -322,34 +362,178 @@ def run_b200(args):
     print(json.dumps(line))
 
 
+def bench_cfg4(dev, rank, world, total_chains=262144, sweeps=100, steps=4, warmup=2):
+    """BASELINE.json configs[3]: Zephyr Z15 (7 440 spins, 71 736 couplers), 262 144 chains split by global chain id over
+    the ranks (strong scaling), 100 sweeps, the integer sufficient statistics of all chains and the NCCL all-reduce of
+    the N + E int64 counters -- the h/J gradient exchange -- inside every timed step."""
+    import torch
+    import torch.distributed as dist
+
+    import image_generation_b200 as B
+    from image_generation_b200.dist import allreduce_statistics, shard_chains
+    from image_generation_b200.stats import sample_statistics
+
+    z = B.IsingGraph.zephyr(15)
+    rng = np.random.default_rng(15)
+    hz = torch.from_numpy((CFG["prefactor"] * rng.uniform(-0.05, 0.05, z.n)).astype(np.float32)).to(dev)
+    Jz = torch.from_numpy((CFG["prefactor"] * rng.uniform(-5.0, 5.0, z.n_edges)).astype(np.float32)).to(dev)
+
+    def run(off, cnt, reduce_over_ranks, n_steps):
+        s = B.BlockGibbsSampler(z, device=dev, num_sweeps=sweeps, seed=CFG["seed"], chain_offset=off)
+        out = (torch.empty((cnt, z.n), dtype=torch.int8, device=dev), torch.empty(cnt, dtype=torch.float64, device=dev))
+        bufs = (torch.zeros(z.n, dtype=torch.int64, device=dev), torch.zeros(z.n_edges, dtype=torch.int64, device=dev))
+        ex_ms = []
+
+        def step(seed, timed):
+            ss = s.sample_grbm(hz, Jz, 1.0, num_reads=cnt, num_sweeps=sweeps, seed=seed, out=out)
+            bufs[0].zero_(); bufs[1].zero_()
+            sample_statistics(ss, s.device_graph, out=bufs)
+            if reduce_over_ranks:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                a, b = allreduce_statistics([bufs[0], bufs[1]])
+                bufs[0].copy_(a); bufs[1].copy_(b)
+                e1.record()
+                if timed:
+                    ex_ms.append((e0, e1))
+        for k in range(warmup):
+            step(100 + k, False)
+        torch.cuda.synchronize(dev)
+        if reduce_over_ranks:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        for k, (a, b) in enumerate(ev):
+            a.record()
+            step(200 + k, True)
+            b.record()
+        torch.cuda.synchronize(dev)
+        ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        ex = float(np.mean([a.elapsed_time(b) for a, b in ex_ms])) if ex_ms else 0.0
+        step(999, False)                                   # identity check: fixed seed, whatever the sharding
+        torch.cuda.synchronize(dev)
+        stats_sum = int((bufs[1] * torch.arange(1, z.n_edges + 1, device=dev)).sum().item())   # weighted checksum of sum s_i s_j
+        return ms, ex, s.last_plan, stats_sum
+
+    off, cnt = shard_chains(total_chains, rank, world)
+    ms, ex, plan, checksum = run(off, cnt, world > 1, steps)
+    t = torch.tensor([ms, ex], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, ex_max = float(t[0]), float(t[1])
+    out = {"workload": f"Zephyr Z15 ({z.n} spins, {z.n_edges} couplers), {total_chains} chains over {world} GPU(s), {sweeps} sweeps, "
+                       "integer statistics + int64 all-reduce per step (BASELINE.json configs[3])",
+           "scaling": "strong", "chains_total": total_chains, "chains_per_gpu": cnt, "sweeps": sweeps, "steps": steps,
+           "ms_per_step": ms_max, "spin_updates_per_s": total_chains * sweeps * z.n / ms_max * 1e3,
+           "exchange_ms": ex_max, "exchange_bytes": 8 * (z.n + z.n_edges), "plan": list(plan),
+           "statistics_checksum": checksum}
+    if world > 1:
+        # the whole job on ONE GPU, same process, same seeds: the strong-scaling denominator and an identity check
+        # (integer statistics of the same global chains must be equal whatever the sharding)
+        if rank == 0:
+            ms1, _, _, checksum1 = run(0, total_chains, False, 2)
+            out["n1_ms_per_step_same_run"] = ms1
+            out["strong_scaling_vs_n1"] = ms1 / ms_max
+            out["statistics_equal_to_n1"] = bool(checksum1 == checksum)
+            rest = ms_max - ms1 / world
+            out["limiter"] = (f"per-GPU sweep launch of {cnt} chains ({ms_max - ex_max:.2f} ms incl. statistics) + exchange {ex_max:.2f} ms; "
+                              f"ideal {ms1 / world:.2f} ms, lost {rest:.2f} ms to wave quantisation of "
+                              f"{-(-cnt // plan[0])} chain groups over the SMs, the fixed per-launch work and the all-reduce")
+        dist.barrier()
+    else:
+        out["strong_scaling_vs_n1"] = 1.0
+    return out
+
+
+def bench_mmd_sharded(dev, rank, world, m_each=8192, d=5640, iters=3):
+    """BASELINE.json configs[2] with its rows sharded over the ranks (m_each / N encoder rows and as many samples per
+    rank): dist.sharded_mmd_loss = int8 all-gather of both blocks, every rank contracts its share of the Gram tiles into
+    Hamming histograms, one int64 all-reduce, float64 evaluation; backward for the rank's own rows."""
+    import torch
+    import torch.distributed as dist
+
+    import image_generation_b200 as B
+    from image_generation_b200.dist import sharded_mmd_loss
+    from image_generation_b200.mmd_tc import mmd_block_sums_i8, pack_rows_i8
+
+    gen = torch.Generator(device=dev).manual_seed(11)                  # same seed on every rank: same global matrix
+    z = torch.randint(0, 2, (2 * m_each, d), generator=gen, dtype=torch.int8, device=dev) * 2 - 1
+    z[m_each:, : d // 8] = 1
+    mx = m_each // world
+    x_loc = z[rank * mx:(rank + 1) * mx].float().requires_grad_(True)
+    y_loc = z[m_each + rank * mx: m_each + (rank + 1) * mx].contiguous()
+    kern = B.GaussianKernel(7).to(dev)
+
+    def call():
+        x_loc.grad = None
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        val = sharded_mmd_loss(x_loc, y_loc, kern)
+        e1.record()
+        val.backward()
+        e2.record()
+        return val, e0, e1, e2
+
+    for _ in range(2):
+        call()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    fw, bw = [], []
+    for _ in range(iters):
+        val, e0, e1, e2 = call()
+        torch.cuda.synchronize(dev)
+        fw.append(e0.elapsed_time(e1)); bw.append(e1.elapsed_time(e2))
+    t = torch.tensor([float(np.mean(fw)), float(np.mean(bw))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # single-GPU truth on this rank: the same global matrix in one piece
+    x_all, y_all = z[: mx * world], z[m_each: m_each + mx * world]
+    zi, _ = pack_rows_i8(torch.cat([x_all, y_all], 0))
+    sums1 = mmd_block_sums_i8(zi, mx * world, kern, d=d)
+    m_x = m_y = mx * world
+    from image_generation_b200.mmd import _estimate
+    val1 = _estimate(sums1, m_x, m_y, kern, "unbiased")[0].to(torch.float32)
+    same = torch.tensor([int(torch.equal(val.detach().reshape(()), val1.reshape(())))], device=dev)
+    if world > 1:
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    return {"workload": f"MMD {m_x} x {m_y} rows, D = {d}, 7 kernels, rows sharded over {world} GPU(s) (BASELINE.json configs[2])",
+            "forward_ms": float(t[0]), "backward_ms": float(t[1]), "rows_per_gpu": mx,
+            "exchange": {"allgather_int8_bytes": int(2 * m_x * zi.shape[1]), "allreduce_int64_bytes": int(3 * (d + 1) * 8)} if world > 1
+            else {"allgather_int8_bytes": 0, "allreduce_int64_bytes": 0},
+            "value": float(val.detach()), "bit_identical_to_single_gpu_on_every_rank": bool(int(same.item()) == 1)}
+
+
 def bench_sweep_variants(dev, g, h, J, iters=3):
-    """The sweep kernel off the headline configuration: fast (MUFU, 16-bit uniform) acceptance, an annealed
-    schedule on the same P16 problem, and the per-GPU shard of BASELINE.json configs[3] (Zephyr Z15, 32 768
-    chains, 100 sweeps).  Device-resident, CUDA events, no L2 flush (state and tables live in shared memory)."""
+    """The sweep kernels off the headline configuration: fast (MUFU, 16-bit uniform) acceptance, an annealed schedule on
+    the same P16 problem, the per-GPU shard of BASELINE.json configs[3] at 8 GPUs (Zephyr Z15, 32 768 chains, 100 sweeps),
+    and the reference's own default call (256 reads on the 256-spin Advantage2 sub-graph, configs[0]).  Device-resident,
+    CUDA events, no L2 flush (state and tables live in shared memory / registers)."""
     import torch
 
     import image_generation_b200 as B
 
     def timed(graph, hh, JJ, chains, sweeps, stats=False, **kw):
         s = B.BlockGibbsSampler(graph, device=dev, **kw)
-        s.device_graph.set_weights(torch.from_numpy(hh).to(dev), torch.from_numpy(JJ).to(dev))
+        hd, Jd = torch.from_numpy(hh).to(dev), torch.from_numpy(JJ).to(dev)
         out = (torch.empty((chains, graph.n), dtype=torch.int8, device=dev),
                torch.empty(chains, dtype=torch.float64, device=dev))
-        s._run(chains, sweeps, None, None, None, None, None, None, out=out)
+        run = lambda n_sweeps=sweeps: s.sample_grbm(hd, Jd, 1.0, num_reads=chains, num_sweeps=n_sweeps, out=out)
+        run()
         torch.cuda.synchronize(dev)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
         for a, b in ev:
             a.record()
-            s._run(chains, sweeps, None, None, None, None, None, None, out=out)
+            run()
             b.record()
         torch.cuda.synchronize(dev)
         ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
         res = {"ms": ms, "spin_updates_per_s": chains * sweeps * graph.n / ms * 1e3, "chains": chains,
-               "sweeps": sweeps, "plan": list(s.last_plan)}
+               "sweeps": sweeps, "plan": list(s.last_plan), "kernel": s.last_kernel}
         if stats:
             # integer statistics (sum s_i, sum s_i s_j) straight from the sampler's packed final state
             from image_generation_b200.stats import sample_statistics
-            ss = s._run(chains, 1, None, None, None, None, None, None, out=out)
+            ss = run(1)
             bufs = (torch.zeros(graph.n, dtype=torch.int64, device=dev),
                     torch.zeros(graph.n_edges, dtype=torch.int64, device=dev))
             sample_statistics(ss, s.device_graph, out=bufs)
@@ -367,6 +551,17 @@ def bench_sweep_variants(dev, g, h, J, iters=3):
                                  "packed_GBps": packed_bytes / st_ms / 1e6,
                                  "note": "edge + node statistics kernels over the bit-packed state (N/8 bytes per "
                                          "chain instead of the N bytes of SURVEY 8(d)'s stand-alone int8 form)"}
+            # a short launch: the int8 write-back (coalesced through shared memory) is most of its HBM traffic
+            short = 5
+            run(short)
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                run(short)
+            b.record()
+            torch.cuda.synchronize(dev)
+            res["short_launch_5_sweeps_ms"] = a.elapsed_time(b) / 3
         return res
 
     out = {"p16_fast_acceptance": timed(g, h, J, CFG["chains"], CFG["sweeps"], accept="fast"),
@@ -376,16 +571,23 @@ def bench_sweep_variants(dev, g, h, J, iters=3):
     hz = (CFG["prefactor"] * rng.uniform(-0.05, 0.05, z.n)).astype(np.float32)
     Jz = (CFG["prefactor"] * rng.uniform(-5.0, 5.0, z.n_edges)).astype(np.float32)
     out["z15_shard_32768_chains"] = timed(z, hz, Jz, 32768, 100, stats=True)
+    ck = np.load(os.path.join(ROOT, "tests", "golden", "grbm_checkpoints.npz"))
+    name = "Advantage2_system1_10_epochs"
+    gc = B.IsingGraph.build(256, ck[name + "/edge_i"], ck[name + "/edge_j"])
+    hc = np.clip(np.float32(0.05) * ck[name + "/linear"], -4, 4).astype(np.float32)
+    Jc = np.clip(np.float32(0.05) * ck[name + "/quadratic"], -1, 1).astype(np.float32)
+    out["cfg1_256_reads_256_spins"] = timed(gc, hc, Jc, 256, 1000)
     return out
 
 
 def bench_mmd(dev, peaks, m_each=8192, d=5640, iters=5):
     """BASELINE.json configs[2]: fused mixture-of-RBF MMD, 8192 encoder latents vs 8192 GRBM samples,
-    latent dim = P16 graph size, +-1 rows on the tcgen05 int8 path (auto bandwidth = two Gram passes)."""
+    latent dim = P16 graph size, +-1 rows on the tcgen05 int8 path (auto bandwidth from ONE Gram pass)."""
     import torch
 
     import image_generation_b200 as B
     from image_generation_b200 import _lib as L
+    from image_generation_b200 import mmd as M
 
     # int8 tcgen05 peak of THIS device (MEASURED_PEAKS.json has none): back-to-back kind::i8 MMAs from resident
     # zero operands -- an upper bound real data cannot reach under the power cap; 2 x the cuBLAS bf16 burst beside it
@@ -408,38 +610,39 @@ def bench_mmd(dev, peaks, m_each=8192, d=5640, iters=5):
             b.record()
         torch.cuda.synchronize(dev)
         ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-        passes = 2 if bw is None else 1
         m = 2 * m_each
         tiles = (m // 256) * (m // 256 + 1)                     # upper triangle of 128 x 256 tiles
-        executed = 2.0 * tiles * 128 * 256 * (-(-d // 128) * 128) * passes
+        executed = 2.0 * tiles * 128 * 256 * (-(-d // 128) * 128)
         i8_2x = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
         out[label] = {
-            "ms": ms, "gram_passes": passes, "input_GBps": m * d / ms / 1e6,
-            "tflops_as_reference_computes_it": 2.0 * m * m * d * passes / ms / 1e9,
+            "ms": ms, "gram_passes": 1, "input_GBps": m * d / ms / 1e6,
+            "tflops_as_reference_computes_it": 2.0 * m * m * d / ms / 1e9,
             "roofline": {"bound": "tensor", "achieved": executed / ms / 1e9, "peak": i8_probe, "unit": "TOP/s",
                          "frac": executed / ms / 1e9 / i8_probe, "traffic": None,
                          "peak_source": "int8 tcgen05 probe on this device (b200grbm_tensor_peak, resident zero operands)",
                          "frac_of_2x_bf16_burst": executed / ms / 1e9 / i8_2x, "peak_2x_bf16_burst": i8_2x,
-                         "executed_ops": executed, "note": "symmetric: only the upper triangle of tiles is contracted"}}
-    # value + gradient wrt x through the public call (what ModelWrapper.step does at src/model_wrapper.py:320-326)
+                         "executed_ops": executed, "note": "symmetric: only the upper triangle of tiles is contracted; the "
+                                                           "epilogue counts Hamming distances (integer histograms), one pass"}}
+    # value + gradient wrt x through the reference's own call, no extra arguments (src/model_wrapper.py:320-326)
     x = z[:m_each].float().requires_grad_(True)
     y = z[m_each:].float()
     kern = B.GaussianKernel(7).to(dev)
     for _ in range(2):
         x.grad = None
-        B.maximum_mean_discrepancy_loss(x, y, kern, path="i8").backward()
+        B.maximum_mean_discrepancy_loss(x=x, y=y, kernel=kern).backward()
     torch.cuda.synchronize(dev)
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     x.grad = None
     e0.record()
-    val = B.maximum_mean_discrepancy_loss(x, y, kern, path="i8")
+    val = B.maximum_mean_discrepancy_loss(x=x, y=y, kernel=kern)
     e1.record()
     val.backward()
     e2.record()
     torch.cuda.synchronize(dev)
-    out["loss_call"] = {"forward_ms": e0.elapsed_time(e1), "backward_ms": e1.elapsed_time(e2),
-                        "note": "maximum_mean_discrepancy_loss(x, y, GaussianKernel(7), path='i8') from fp32 inputs: cat + sign-pack + "
-                                "2 Gram passes; backward = int8 Gram coefficient pass (bf16 hi/lo) + tcgen05 bf16 GEMM"}
+    out["loss_call"] = {"forward_ms": e0.elapsed_time(e1), "backward_ms": e1.elapsed_time(e2), "dispatched_to": M.last_path,
+                        "note": "maximum_mean_discrepancy_loss(x=, y=, kernel=GaussianKernel(7)) from fp32 inputs, default path: fused spin "
+                                "extraction (rows + transpose) + spin check + 1 Gram pass; backward = int8 Gram coefficient pass "
+                                "(2 fixed-point digit planes) + tcgen05 int8 GEMM"}
     out["workload"] = f"MMD {m_each} x {m_each} rows, D = {d}, 7 kernels, int8 +-1 rows (BASELINE.json configs[2])"
     return out
 
@@ -454,23 +657,31 @@ def bench_dvae_step(dev, steps=20, warmup=5):
     z = np.load(os.path.join(ROOT, "tests", "golden", "grbm_checkpoints.npz"))
     name = "Advantage2_system1_10_epochs"
     edges = list(zip(z[name + "/edge_i"].tolist(), z[name + "/edge_j"].tolist()))
-    model = HybridDVAE(range(256), edges, device=dev)
-    model.setup()
-    model.train_init(n_epochs=1, n_batches=steps + warmup)
-    batches = [(synthetic_batch(128, seed=k, device=dev), None) for k in range(4)]
-    for k in range(warmup):
-        model.step(batches[k % 4], epoch=0, record_losses=False)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for k in range(steps):
-        model.step(batches[k % 4], epoch=0, record_losses=False)
-    torch.cuda.synchronize(dev)
-    ms = 1e3 * (time.perf_counter() - t0) / steps
+
+    def run(**kw):
+        model = HybridDVAE(range(256), edges, device=dev, **kw)
+        model.setup()
+        model.train_init(n_epochs=1, n_batches=steps + warmup)
+        batches = [(synthetic_batch(128, seed=k, device=dev), None) for k in range(4)]
+        for k in range(warmup):
+            model.step(batches[k % 4], epoch=0, record_losses=False)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            model.step(batches[k % 4], epoch=0, record_losses=False)
+        torch.cuda.synchronize(dev)
+        return 1e3 * (time.perf_counter() - t0) / steps
+
+    ms = run()
     out = {"ms_per_step": ms, "steps": steps, "workload": "DVAE+GRBM step, B=128, R=8, n_latents=256, 256 reads x 1000 sweeps, "
            "MMD on tcgen05 int8 path, NLL via packed statistics every 10th step (BASELINE.json configs[0], GPU path)"}
     try:
+        out["persistent_chains_20_sweeps_ms_per_step"] = run(persistent=20)
+    except Exception as exc:  # a side metric must never take the bench line down
+        out["persistent_chains_error"] = repr(exc)
+    try:
         out["cpu_baseline"] = cpu_dvae_step(z, name, edges)
-    except Exception as exc:  # the side metric must never take the bench line down
+    except Exception as exc:
         out["cpu_baseline"] = {"error": repr(exc)}
     return out
 
@@ -528,12 +739,10 @@ def main():
     ap.add_argument("--accept", default="exact", choices=["exact", "fast"])
     ap.add_argument("--chains", type=int, default=0)
     ap.add_argument("--sweeps", type=int, default=0)
-    ap.add_argument("--cpl", type=int, default=0)
-    ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample nvidia-smi during the timed region")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic: skip the L2 flush between timed steps")
-    ap.add_argument("--skip-extra", action="store_true", help="skip the MMD (configs[2]) and DVAE-step (configs[0]) side metrics")
+    ap.add_argument("--skip-extra", action="store_true", help="headline only: skip cfg4 / mmd_sharded / mmd / dvae_step / sweep_variants")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

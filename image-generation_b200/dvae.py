@@ -145,7 +145,8 @@ class HybridDVAE:
     :355-381), with a :class:`BlockGibbsSampler` where the reference builds a QPU composite."""
 
     def __init__(self, nodes, edges, n_latents: Optional[int] = None, device=None, parameters: Optional[dict] = None,
-                 sampler_kwargs: Optional[dict] = None, mmd_path: str = "i8", packed_nll: bool = True):
+                 sampler_kwargs: Optional[dict] = None, mmd_path: str = "i8", packed_nll: bool = True,
+                 persistent: int = 0):
         self.params = dict(DEFAULT_PARAMETERS)
         self.params.update(parameters or {})
         self.nodes, self.edges = list(nodes), list(edges)
@@ -156,6 +157,12 @@ class HybridDVAE:
         self.linear_range, self.quadratic_range = (-4.0, 4.0), (-1.0, 1.0)   # Advantage h_range / j_range
         self._sampler_kwargs_extra = sampler_kwargs or {}
         self.mmd_path, self.packed_nll = mmd_path, packed_nll
+        # persistent > 0: persistent contrastive divergence -- NUM_READS chains stay resident on the device and advance
+        # by `persistent` sweeps per sampler call under the current parameters (the intent of the reference's
+        # PersistentQPUSampleHelper, src/utils/persistent_qpu_sampler.py:41-49, :79-103) instead of restarting from
+        # random spins and running the sampler's full schedule every step
+        self.persistent = int(persistent)
+        self._chains = None
         self.losses = {"mse_losses": [], "dvae_losses": []}
         self.overlap_sampling = True
         self._side_stream = None
@@ -179,6 +186,7 @@ class HybridDVAE:
         self._dvae = DiscreteVariationalAutoencoder(Encoder(self.n_latents), Decoder(self.n_latents), l2d).to(self.device)
         self._grbm = GraphRestrictedBoltzmannMachine(self.nodes, self.edges).to(self.device)
         self.sampler = self._grbm.make_sampler(self.device, seed=self.RANDOM_SEED, **self._sampler_kwargs_extra)
+        self._chains = None
         # kwargs of src/utils/common.py:130-138 (QPU-only ones are ignored by the sampler)
         self.sampler_kwargs = dict(num_reads=self.NUM_READS, answer_mode="raw", auto_scale=False,
                                    annealing_time=self.ANNEALING_TIME, label="Examples - ML MNIST Image Gen")
@@ -195,8 +203,12 @@ class HybridDVAE:
         if self._dvae is None or self._grbm is None:
             self.setup()
         total = n_epochs * n_batches
+        if self.persistent > 0 and self._chains is None:
+            from .sampler import PersistentChains
+            self._chains = PersistentChains(self.sampler, self.NUM_READS)
         self._tpar = dict(
-            persistent_qpu_sample_helper=PersistentQPUSampleHelper(self.MAX_DEQUE_SIZE, self.ITERATIONS_BEFORE_RESAMPLING),
+            persistent_qpu_sample_helper=PersistentQPUSampleHelper(self.MAX_DEQUE_SIZE, self.ITERATIONS_BEFORE_RESAMPLING,
+                                                                   persistent_chains=self._chains, sweeps_per_call=self.persistent),
             dvae_lr_schedule=np.geomspace(self.AUTOENCODER_INITIAL_LR, self.AUTOENCODER_FINAL_LR, total + 1),
             grbm_lr_schedule=np.geomspace(self.BM_INITIAL_LR, self.BM_FINAL_LR, total + 1),
             opt_step=0, kernel=GaussianKernel(n_kernels=7).to(self.device), sample_set=None, init_done=True)
@@ -234,9 +246,18 @@ class HybridDVAE:
             with torch.no_grad():
                 samples = self._sample_prior()
         spins = spins.reshape(-1, spins.shape[-1])
-        mmd = maximum_mean_discrepancy_loss(x=spins, y=samples, kernel=self._tpar["kernel"], path=self.mmd_path)
-        dvae_loss = mse + mmd
         will_train_grbm = train_grbm(self._tpar["opt_step"], epoch)
+        pair = None
+        if self.mmd_path == "i8":
+            # ONE pass over the encoder spins writes the int8 Gram rows, their transpose for the backward GEMM and -- on
+            # the steps that update the GRBM -- the bit-packed words of the data-side edge statistics (csrc/spin_extract.cu)
+            from .mmd_tc import pack_pair_i8
+            dg = self.sampler.device_graph
+            want_stats = will_train_grbm and self.packed_nll
+            pair = pack_pair_i8(spins, samples, need_grad=True, stats_pos=dg.pos if want_stats else None,
+                                stats_n_pad=dg.graph.n_pad)
+        mmd = maximum_mean_discrepancy_loss(x=spins, y=samples, kernel=self._tpar["kernel"], path=self.mmd_path, packed=pair)
+        dvae_loss = mse + mmd
         if overlap and not will_train_grbm:
             self._launch_prefetch(main)          # GRBM parameters stay as they are: next step's samples, now
         if record_losses:     # the reference logs .item() every step (:306,:324) -- a host sync
@@ -251,7 +272,8 @@ class HybridDVAE:
                 spins=spins.detach(), grbm=self._grbm, sampler=self.sampler, sampler_kwargs=self.sampler_kwargs,
                 linear_range=self.linear_range, quadratic_range=self.quadratic_range, prefactor=self.PREFACTOR,
                 persistent_qpu_sample_helper=self._tpar["persistent_qpu_sample_helper"],
-                sample_set=self._tpar["sample_set"], packed_statistics=self.packed_nll, process_group=False)
+                sample_set=self._tpar["sample_set"], packed_statistics=self.packed_nll, process_group=False,
+                data_packed=None if pair is None else pair.stats)
             grbm_loss.backward()
             self._grbm_optimizer.step()
 
@@ -270,6 +292,10 @@ class HybridDVAE:
             self._prefetched = self._sample_prior()
 
     def _sample_prior(self) -> torch.Tensor:
+        if self._chains is not None:           # persistent chains: a few more sweeps under the current parameters
+            self.sampler.device_graph.set_weights(self._grbm.linear, self._grbm.quadratic, self.PREFACTOR,
+                                                  self.linear_range, self.quadratic_range)
+            return self._grbm.sampleset_to_tensor(self._chains.advance(self.persistent), device=self.device)
         return self._grbm.sample(self.sampler, prefactor=self.PREFACTOR, linear_range=self.linear_range,
                                  quadratic_range=self.quadratic_range, device=self.device,
                                  sample_params=self.sampler_kwargs)
@@ -301,6 +327,7 @@ class HybridDVAE:
         self._dvae.load_state_dict(torch.load(os.path.join(file_path, "dvae.pth"), map_location=self.device, weights_only=True))
         self._grbm.load_state_dict(torch.load(os.path.join(file_path, "grbm.pth"), map_location=self.device, weights_only=True))
         self.sampler = self._grbm.make_sampler(self.device, seed=self.RANDOM_SEED, **self._sampler_kwargs_extra)
+        self._chains = None
         # a checkpoint with another edge count replaces the parameter objects: rebind the optimizer to them
         self._grbm_optimizer = torch.optim.Adam(self._grbm.parameters(), lr=self.BM_INITIAL_LR,
                                                 weight_decay=self.BM_WEIGHT_DECAY)

@@ -181,7 +181,7 @@ class _MMDFunction(torch.autograd.Function):
 
 
 def maximum_mean_discrepancy_loss(x: torch.Tensor, y: torch.Tensor, kernel: GaussianKernel, *,
-                                  estimator: str = "unbiased", path: str = "auto") -> torch.Tensor:
+                                  estimator: str = "unbiased", path: str = "auto", packed=None) -> torch.Tensor:
     """MMD^2 estimate between the rows of ``x`` (gradient flows here) and ``y``.
 
     ``path="auto"`` (the default, i.e. what the reference's unmodified call
@@ -195,6 +195,10 @@ def maximum_mean_discrepancy_loss(x: torch.Tensor, y: torch.Tensor, kernel: Gaus
     real inputs; ``"bf16"`` / ``"bf16x3"`` run the Gram of real-valued rows on the tcgen05 bf16
     kernel, forward and backward.  The backward pass of the ``"i8"`` path also runs on int8 tensor cores
     (coefficients as fixed-point digit planes, csrc/gemm_i8.cu); the gradient is evaluated at the sign-packed points.
+
+    ``packed``: a :class:`mmd_tc.PackedPair` of ``(x, y)`` made by the caller with ``pack_pair_i8`` (a training step
+    that also wants the bit-packed statistics words of ``x`` extracts everything in one pass and hands the pair in);
+    implies ``path="i8"``.
     """
     if estimator not in ("unbiased", "biased"):
         raise ValueError("estimator must be 'unbiased' or 'biased'")
@@ -204,8 +208,13 @@ def maximum_mean_discrepancy_loss(x: torch.Tensor, y: torch.Tensor, kernel: Gaus
         raise ValueError(f"x and y must be (rows, features) with equal features, got {tuple(x.shape)} and {tuple(y.shape)}")
     if not isinstance(kernel, GaussianKernel):
         raise TypeError("kernel must be a GaussianKernel")
-    packed = None
-    if path == "auto":
+    if packed is not None:
+        if packed.m_x != x.shape[0] or packed.rows.shape[0] != x.shape[0] + y.shape[0] or packed.d != x.shape[1]:
+            raise ValueError("packed does not match the shapes of x and y")
+        if x.requires_grad and torch.is_grad_enabled() and packed.zt is None:
+            raise ValueError("packed was made without need_grad=True but x requires a gradient")
+        path = "i8"
+    elif path == "auto":
         if not (x.is_cuda and y.is_cuda):
             raise RuntimeError("MMD kernels run on CUDA only (no CPU fallback)")
         from .mmd_tc import pack_pair_i8

@@ -451,10 +451,13 @@ class BlockGibbsSampler:
                      beta_range: Optional[Sequence[float]] = None, beta_schedule_type: Optional[str] = None,
                      beta_schedule: Optional[Sequence[float]] = None, seed: Optional[int] = None,
                      initial_states: Optional[Union[np.ndarray, torch.Tensor]] = None,
-                     uniforms: Optional[torch.Tensor] = None, **kwargs) -> SampleSet:
+                     uniforms: Optional[torch.Tensor] = None,
+                     out: Optional[tuple[torch.Tensor, torch.Tensor]] = None, **kwargs) -> SampleSet:
         """Draw ``num_reads`` spin configurations ~ exp(-beta E) for the Ising problem
         ``(h, J)`` given as dicts keyed by node / edge (dimod style) or as arrays in the
-        graph's node / edge order.  QPU-only keyword arguments are accepted and ignored."""
+        graph's node / edge order.  QPU-only keyword arguments are accepted and ignored.
+        ``out = (samples int8 (reads, n), energies float64 (reads,))``: caller-owned device buffers to fill
+        (a steady-state training loop then allocates nothing per call)."""
         unknown = set(kwargs) - _IGNORED_QPU_KWARGS
         if unknown:
             raise TypeError(f"sample_ising() got unexpected keyword arguments {sorted(unknown)}")
@@ -481,21 +484,21 @@ class BlockGibbsSampler:
         self._staging_event.record(torch.cuda.current_stream(self.device))
         self.device_graph.set_weights(h_t, j_t)
         return self._run(num_reads, num_sweeps, beta_range, beta_schedule_type, beta_schedule, seed, initial_states,
-                         uniforms)
+                         uniforms, out=out)
 
     def sample_grbm(self, linear: torch.Tensor, quadratic: torch.Tensor, prefactor: float,
                     linear_range=None, quadratic_range=None, num_reads: int = 1, **kwargs) -> SampleSet:
         """Device-resident variant used by ``GraphRestrictedBoltzmannMachine.sample``: scales and
         clips the parameters on the GPU (no Python dict round trip) and samples."""
         run_kw = {k: kwargs.pop(k) for k in ("num_sweeps", "beta_range", "beta_schedule_type", "beta_schedule",
-                                             "seed", "initial_states", "uniforms") if k in kwargs}
+                                             "seed", "initial_states", "uniforms", "out") if k in kwargs}
         unknown = set(kwargs) - _IGNORED_QPU_KWARGS
         if unknown:
             raise TypeError(f"sample_grbm() got unexpected keyword arguments {sorted(unknown)}")
         self.device_graph.set_weights(linear, quadratic, prefactor, linear_range, quadratic_range)
         return self._run(num_reads, run_kw.get("num_sweeps"), run_kw.get("beta_range"),
                          run_kw.get("beta_schedule_type"), run_kw.get("beta_schedule"), run_kw.get("seed"),
-                         run_kw.get("initial_states"), run_kw.get("uniforms"))
+                         run_kw.get("initial_states"), run_kw.get("uniforms"), out=run_kw.get("out"))
 
     def _run(self, num_reads, num_sweeps, beta_range, beta_schedule_type, beta_sched, seed, initial_states,
              uniforms, packed_io: Optional[torch.Tensor] = None, want_int8: bool = True,

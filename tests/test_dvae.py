@@ -186,3 +186,42 @@ def test_integration_recipe_of_the_reference_setup(cuda_device):
     model = torch.from_numpy(sample_set.record.sample).float().to(cuda_device)
     want = flat.detach().mean(0) - model.mean(0)
     torch.testing.assert_close(grbm._linear.grad, want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_persistent_chains_in_the_training_step(cuda_device, golden):
+    """HybridDVAE(persistent=k): the negative phase comes from resident chains advanced by k sweeps per sampler call under
+    the current parameters (the reference helper's stated intent, src/utils/persistent_qpu_sampler.py:41-49), for the MMD
+    samples and for the NLL statistics alike; the chains' sweep counter runs on across steps, and the first sample set is
+    the oracle's k sweeps from the Philox initial state."""
+    from oracle import oracle as O
+    z, _ = golden
+    name = "Advantage2_system1_10_epochs"
+    edges = list(zip(z[name + "/edge_i"].tolist(), z[name + "/edge_j"].tolist()))
+    k = 7
+    model = HybridDVAE(range(256), edges, device=cuda_device, persistent=k)
+    model.overlap_sampling = False
+    model.setup()
+    model.train_init(n_epochs=1, n_batches=12)
+    pc = model._chains
+    assert pc is not None and pc.num_chains == 256 and pc.sweeps_done == 0
+    lin, quad = model._grbm.linear.detach().cpu().numpy(), model._grbm.quadratic.detach().cpu().numpy()
+    model.step((synthetic_batch(128, seed=0), None), epoch=0)
+    assert pc.sweeps_done == 2 * k                        # one call for the MMD samples, one for the NLL at opt_step 0
+    model.step((synthetic_batch(128, seed=1), None), epoch=0)
+    assert pc.sweeps_done == 3 * k
+    g = model.sampler.graph
+    # replay the first call on the oracle: k sweeps at beta = 1 from the Philox initial state under the initial parameters
+    model2 = HybridDVAE(range(256), edges, device=cuda_device, persistent=k)
+    model2.setup()
+    model2._grbm.load_state_dict(model._grbm.state_dict())
+    with torch.no_grad():
+        model2._grbm._linear.copy_(torch.from_numpy(lin)); model2._grbm._quadratic.copy_(torch.from_numpy(quad))
+    model2.train_init(n_epochs=1, n_batches=2)
+    got = model2._sample_prior().cpu().numpy().astype(np.int8)
+    h = np.clip(np.float32(0.05) * lin, -4, 4).astype(np.float32)
+    J = np.clip(np.float32(0.05) * quad, -1, 1).astype(np.float32)
+    csr = O.PositionCSR(g.n, g.edge_i, g.edge_j, g.order)
+    seed = model2._chains.seed
+    want = O.gibbs(csr, h, J, O.init_state(csr, 256, seed), [1.0] * k, seed=seed)
+    assert np.array_equal(got, want)

@@ -1,7 +1,13 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (ncu --set full) into a small text file for profiles/.
 
-    python tools/ncu_summary.py gpurun_out/x.ncu-rep profiles/x_summary.txt [kernel-regex]
+    python tools/ncu_summary.py gpurun_out/x.ncu-rep profiles/x_summary.txt
+    python tools/ncu_summary.py gpurun_out/x.ncu-rep profiles/x_summary.txt --json profiles/x_metrics.json --updates N
+
+--json also writes the handful of numbers bench.py quotes next to its live measurements (DRAM bytes of one launch of
+the dominant kernel, warp instructions per 32 spin-updates, issue-slot utilisation), so that they are read from the
+committed capture instead of being literals in bench.py.  --updates = spin-updates of the captured launch
+(chains x sweeps x spins of the command that was profiled).
 """
 import csv
 import io
@@ -24,6 +30,8 @@ KEEP = [
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
+    json_out = sys.argv[sys.argv.index("--json") + 1] if "--json" in sys.argv else None
+    updates = float(sys.argv[sys.argv.index("--updates") + 1]) if "--updates" in sys.argv else None
     text = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(text)))
     hdr, units = rows[0], rows[1]
@@ -36,6 +44,22 @@ def main():
                 if any(re.search(p, h) for p in KEEP):
                     f.write(f"{h:95s} {units[i]:12s} {r[i]}\n")
     print("wrote", out)
+    if json_out:
+        import json
+        r = rows[2]
+        get = lambda name: float(r[hdr.index(name)].replace(",", "")) if name in hdr else None
+        unit = lambda name: units[hdr.index(name)] if name in hdr else ""
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd = get("dram__bytes_read.sum") * scale.get(unit("dram__bytes_read.sum"), 1.0)
+        wr = get("dram__bytes_write.sum") * scale.get(unit("dram__bytes_write.sum"), 1.0)
+        inst = get("smsp__inst_executed.sum")
+        d = {"kernel": r[name_col][:120], "capture": rep, "dram_bytes_read": rd, "dram_bytes_write": wr,
+             "dram_bytes_per_launch": rd + wr, "warp_instructions": inst,
+             "issue_active_frac": (get("smsp__issue_active.avg.pct_of_peak_sustained_active") or 0.0) / 100.0,
+             "gpu_time_us": get("gpu__time_duration.sum"), "updates_in_capture": updates,
+             "warp_instr_per_32_updates": (inst * 32.0 / updates) if (inst and updates) else None}
+        json.dump(d, open(json_out, "w"), indent=1)
+        print("wrote", json_out)
 
 
 if __name__ == "__main__":
