@@ -317,22 +317,31 @@ __device__ double block_reduce_sum(double v, double *scratch)
     return t;
 }
 
-// Histograms -> sums[4] = { sum_{a,b in x} k, sum_{a,b in y} k, sum_{a in x, b in y} k, sum_ab t_ab } in float64.
-// One block; the reductions run in a fixed order, so the result is bit-reproducible.
-__global__ void __launch_bounds__(1024) mmd_eval_hist_kernel(const unsigned long long *__restrict__ hist, int d, int m,
+// 1 / (bw * mul_factor^(u - n_kernels/2)) for the kernels of the mixture, computed once per block
+__device__ void inverse_bandwidths(double bw, int n_kernels, float mul_factor, double *inv_b /* shared, [16] */)
+{
+    if ((int)threadIdx.x < n_kernels)
+        inv_b[threadIdx.x] = 1.0 / (bw * pow((double)mul_factor, (double)((int)threadIdx.x - n_kernels / 2)));
+    __syncthreads();
+}
+
+// Histograms -> sums[5] = { sum_{a,b in x} k, sum_{a,b in y} k, sum_{a in x, b in y} k, sum_ab t_ab, MMD^2 estimate }
+// in float64.  One block; the reductions run in a fixed order, so the result is bit-reproducible.  The estimate
+// (sums[4]) is  scale * (xx + yy - 2 xy)  with the block means of the unbiased (diagonal dropped) or biased form.
+__global__ void __launch_bounds__(1024) mmd_eval_hist_kernel(const unsigned long long *__restrict__ hist, int d, int m_x, int m_y,
                                                              int n_kernels, float mul_factor, int squared, float bandwidth,
-                                                             double *__restrict__ sums)
+                                                             int unbiased, double scale, double *__restrict__ sums)
 {
     __shared__ double scratch[32];
+    __shared__ double inv_b[16];
     const size_t stride = (size_t)d + 1;
     double dist = 0.0;
     for (int h = threadIdx.x; h <= d; h += blockDim.x)
         dist += hamming_to_t(h, squared) * ((double)hist[h] + (double)hist[stride + h] + 2.0 * (double)hist[2 * stride + h]);
     dist = block_reduce_sum(dist, scratch);
-    const double mm = (double)m;
+    const double mm = (double)(m_x + m_y);
     const double bw = bandwidth > 0.f ? (double)bandwidth : dist / (mm * mm - mm);
-    double inv_b[16];
-    for (int u = 0; u < n_kernels; ++u) inv_b[u] = 1.0 / (bw * pow((double)mul_factor, (double)(u - n_kernels / 2)));
+    inverse_bandwidths(bw, n_kernels, mul_factor, inv_b);
     double s[3] = {0.0, 0.0, 0.0};
     for (int h = threadIdx.x; h <= d; h += blockDim.x) {
         const unsigned long long c0 = hist[h], c1 = hist[stride + h], c2 = hist[2 * stride + h];
@@ -344,36 +353,46 @@ __global__ void __launch_bounds__(1024) mmd_eval_hist_kernel(const unsigned long
         s[1] += k * (double)c1;
         s[2] += k * (double)c2;
     }
-    for (int b = 0; b < 3; ++b) {
-        const double tot = block_reduce_sum(s[b], scratch);
-        if (threadIdx.x == 0) sums[b] = tot;
+    double tot[3];
+    for (int b = 0; b < 3; ++b) tot[b] = block_reduce_sum(s[b], scratch);
+    if (threadIdx.x == 0) {
+        sums[0] = tot[0]; sums[1] = tot[1]; sums[2] = tot[2]; sums[3] = dist;
+        const double nx = (double)m_x, ny = (double)m_y, diag = (double)n_kernels;       // k(a, a) = n_kernels * exp(0)
+        const double xx = unbiased ? (tot[0] - diag * nx) / (nx * (nx - 1.0)) : tot[0] / (nx * nx);
+        const double yy = unbiased ? (tot[1] - diag * ny) / (ny * (ny - 1.0)) : tot[1] / (ny * ny);
+        sums[4] = scale * (xx + yy - 2.0 * (tot[2] / (nx * ny)));
     }
-    if (threadIdx.x == 0) sums[3] = dist;
 }
 
 // Backward coefficient table over the Hamming distance:  c(h) = (dk/dt)(dt/d||.||)/||.||  (multiplies x_a - z_b;
 // zero where the rows coincide), normalised to  lut[h] = c(h) / max|c| * Q  with Q the largest magnitude the
 // n_planes base-256 digits represent.  scale_out[0] = max|c| * max(|w_xx|, |w_xy|) / Q  undoes it after the GEMM.
+// One block; c(h) is evaluated once (float64) and parked in the output table's own storage as its float32 value
+// until the maximum is known.
 __global__ void __launch_bounds__(1024) mmd_coef_lut_kernel(int d, int m, int n_kernels, float mul_factor, int squared,
                                                             float bandwidth, const double *__restrict__ sums, float w_xx,
                                                             float w_xy, int n_planes, const unsigned long long *__restrict__ hist,
                                                             float *__restrict__ lut, double *__restrict__ scale_out)
 {
     __shared__ double scratch[32];
+    __shared__ double inv_b[16];
     const double mm = (double)m;
     const double bw = bandwidth > 0.f ? (double)bandwidth : sums[3] / (mm * mm - mm);
+    inverse_bandwidths(bw, n_kernels, mul_factor, inv_b);
+    constexpr int PER_THREAD = 8;                   // d + 1 <= 8192 bins are kept in registers, more are recomputed
+    double cval[PER_THREAD];
+    const auto coef_at = [&](int h) {
+        if (h == 0) return 0.0;
+        const double t = hamming_to_t(h, squared);
+        double dk = 0.0;
+        for (int u = 0; u < n_kernels; ++u) dk -= exp(-t * inv_b[u]) * inv_b[u];
+        return squared ? 2.0 * dk : dk / t;
+    };
     double cmax = 0.0;
-    for (int h = threadIdx.x; h <= d; h += blockDim.x) {
-        double c = 0.0;
-        if (h > 0) {
-            const double t = hamming_to_t(h, squared);
-            double dk = 0.0;
-            for (int u = 0; u < n_kernels; ++u) {
-                const double b = bw * pow((double)mul_factor, (double)(u - n_kernels / 2));
-                dk -= exp(-t / b) / b;
-            }
-            c = squared ? 2.0 * dk : dk / t;
-        }
+    int j = 0;
+    for (int h = threadIdx.x; h <= d; h += blockDim.x, ++j) {
+        const double c = coef_at(h);
+        if (j < PER_THREAD) cval[j] = c;
         // with the forward's histograms at hand the fixed-point range covers only distances that occur among the
         // x-x and x-y pairs (|c| grows steeply towards h = 1, which real data rarely reaches: ~7 bits regained)
         if (hist == nullptr || (hist[h] | hist[2 * ((size_t)d + 1) + h]) != 0ull) cmax = fmax(cmax, fabs(c));
@@ -386,19 +405,8 @@ __global__ void __launch_bounds__(1024) mmd_coef_lut_kernel(int d, int m, int n_
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) cmax = fmax(cmax, scratch[w]);
     const double Q = n_planes >= 3 ? 8355711.0 : 32639.0;        // 127 * (65536 + 256 + 1) / 127 * (256 + 1)
     const double norm = cmax > 0.0 ? Q / cmax : 0.0;
-    for (int h = threadIdx.x; h <= d; h += blockDim.x) {
-        double c = 0.0;
-        if (h > 0) {
-            const double t = hamming_to_t(h, squared);
-            double dk = 0.0;
-            for (int u = 0; u < n_kernels; ++u) {
-                const double b = bw * pow((double)mul_factor, (double)(u - n_kernels / 2));
-                dk -= exp(-t / b) / b;
-            }
-            c = squared ? 2.0 * dk : dk / t;
-        }
-        lut[h] = (float)(c * norm);
-    }
+    j = 0;
+    for (int h = threadIdx.x; h <= d; h += blockDim.x, ++j) lut[h] = (float)((j < PER_THREAD ? cval[j] : coef_at(h)) * norm);
     if (threadIdx.x == 0) scale_out[0] = cmax * fmax(fabs((double)w_xx), fabs((double)w_xy)) / Q;
 }
 
@@ -571,22 +579,26 @@ extern "C" int32_t b200grbm_mmd_hist_i8(const int8_t *z_dev, int32_t m_x, int32_
 }
 
 extern "C" int32_t b200grbm_mmd_eval_hist(const uint64_t *hist_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t n_kernels,
-                                          float mul_factor, int32_t squared, float bandwidth, double *sums_dev, void *stream)
+                                          float mul_factor, int32_t squared, float bandwidth, int32_t unbiased, double scale,
+                                          double *sums_dev, void *stream)
 {
     if (m_x <= 0 || m_y <= 0 || d <= 0) return fail(B200GRBM_EINVAL, "mmd_eval_hist: m_x=%d m_y=%d d=%d", m_x, m_y, d);
     if (n_kernels < 1 || n_kernels > 16 || !(mul_factor > 0.f))
         return fail(B200GRBM_EINVAL, "mmd_eval_hist: n_kernels=%d mul_factor=%g", n_kernels, mul_factor);
     if (!hist_dev || !sums_dev) return fail(B200GRBM_EINVAL, "mmd_eval_hist: NULL pointer argument");
     B200_TRY(require_device());
-    mmd_eval_hist_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long *>(hist_dev), d,
-                                                              m_x + m_y, n_kernels, mul_factor, squared, bandwidth, sums_dev);
+    if (unbiased && (m_x < 2 || m_y < 2))
+        return fail(B200GRBM_EINVAL, "mmd_eval_hist: the unbiased estimator needs at least two rows in x and in y");
+    mmd_eval_hist_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long *>(hist_dev), d, m_x,
+                                                              m_y, n_kernels, mul_factor, squared, bandwidth, unbiased, scale,
+                                                              sums_dev);
     B200_CUDA(cudaGetLastError());
     return 0;
 }
 
 extern "C" int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,
                                            int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth,
-                                           uint64_t *hist_dev, double *sums_dev, void *stream)
+                                           int32_t unbiased, double scale, uint64_t *hist_dev, double *sums_dev, void *stream)
 {
     if (n_kernels < 1 || n_kernels > 16 || !(mul_factor > 0.f))
         return fail(B200GRBM_EINVAL, "mmd_forward_i8: n_kernels=%d mul_factor=%g", n_kernels, mul_factor);
@@ -595,7 +607,8 @@ extern "C" int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int
     B200_TRY(require_device());
     B200_CUDA(cudaMemsetAsync(hist_dev, 0, 3 * ((size_t)d + 1) * sizeof(uint64_t), (cudaStream_t)stream));
     B200_TRY(b200grbm_mmd_hist_i8(z_dev, m_x, m_y, d, d_pad, 0, 1, hist_dev, stream));
-    return b200grbm_mmd_eval_hist(hist_dev, m_x, m_y, d, n_kernels, mul_factor, squared, bandwidth, sums_dev, stream);
+    return b200grbm_mmd_eval_hist(hist_dev, m_x, m_y, d, n_kernels, mul_factor, squared, bandwidth, unbiased, scale, sums_dev,
+                                  stream);
 }
 
 extern "C" int32_t b200grbm_mmd_coef_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,

@@ -50,6 +50,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         : "memory");
 }
 
+// pull one box of a tiled tensor into L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int x, int y)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
+
 // K-major operand, 128-byte swizzle: rows are 128 B apart, 8-row groups 1024 B apart (SBO),
 // descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.  (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)

@@ -82,7 +82,7 @@ class _ShardedMMD(torch.autograd.Function):
         hist = ops.histograms(z, m_x, d, (rank, world))     # this rank's share of the Gram tiles
         if world > 1:
             dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)     # exact: int64 counters
-        sums = ops.sums(hist, m_x, m_y, kernel)
+        sums = ops.sums(hist, m_x, m_y, kernel, estimator)
         val, w_xx, w_xy = _estimate(sums, m_x, m_y, kernel, estimator)
         ctx.save_for_backward(z, sums)
         ctx.meta = (kernel, w_xx, w_xy, m_x, d, rank * mx_loc, mx_loc, ops)
@@ -112,9 +112,9 @@ class _DeviceOps:
         return mmd_histograms_i8(z, m_x, d, shard)
 
     @staticmethod
-    def sums(hist, m_x, m_y, kernel):
+    def sums(hist, m_x, m_y, kernel, estimator="unbiased"):
         from .mmd_tc import mmd_sums_from_histograms
-        return mmd_sums_from_histograms(hist, m_x, m_y, kernel)
+        return mmd_sums_from_histograms(hist, m_x, m_y, kernel, estimator=estimator)
 
     @staticmethod
     def backward(z, d, m_x, kernel, sums, w_xx, w_xy, grad_out, rows, hist):

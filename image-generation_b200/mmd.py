@@ -91,7 +91,7 @@ def mmd_block_sums(z: torch.Tensor, m_x: int, kernel: GaussianKernel, path: str 
         st = _lib.current_stream(z.device)
         if path == "i8":
             from .mmd_tc import mmd_block_sums_i8
-            return mmd_block_sums_i8(z, m_x, kernel, sums)
+            return mmd_block_sums_i8(z, m_x, kernel)[:4]
         if path in ("bf16", "bf16x3"):
             from .mmd_tc import mmd_block_sums_bf16
             return mmd_block_sums_bf16(z, m_x, kernel, split=(path == "bf16x3"), sums=sums)
@@ -120,6 +120,8 @@ def _estimate(sums, m_x: int, m_y: int, kernel: GaussianKernel, estimator: str):
         xx = sums[0] / (m_x * m_x)
         yy = sums[1] / (m_y * m_y)
         w_xx = 2.0 / (m_x * m_x)
+    if sums.numel() >= 5:       # the histogram evaluation kernel already formed the estimate (same formula, float64)
+        return sums[4], scale * w_xx, -2.0 * scale / (m_x * m_y)
     xy = sums[2] / (m_x * m_y)
     return scale * (xx + yy - 2.0 * xy), scale * w_xx, -2.0 * scale / (m_x * m_y)
 
@@ -135,7 +137,9 @@ class _MMDFunction(torch.autograd.Function):
             from .mmd_tc import mmd_block_sums_i8, pack_pair_i8
             # sign-packed, zero-padded int8 rows (+ their transpose when a gradient will be asked for), kept for backward
             pair = packed if packed is not None else pack_pair_i8(x, y, need_grad=ctx.needs_input_grad[0])
-            sums, hist = mmd_block_sums_i8(pair.rows, m_x, kernel, d=d, return_hist=True)
+            if estimator == "unbiased" and (m_x < 2 or m_y < 2):
+                raise ValueError("the unbiased MMD estimator needs at least two rows in x and in y")
+            sums, hist = mmd_block_sums_i8(pair.rows, m_x, kernel, d=d, return_hist=True, estimator=estimator)
         elif path in ("bf16", "bf16x3"):
             from .mmd_tc import mmd_block_sums_bf16
             z = torch.cat([x.detach().to(torch.float32), y.detach().to(torch.float32)], 0).contiguous()

@@ -110,23 +110,34 @@ def mmd_histograms_i8(zi: torch.Tensor, m_x: int, d: int, shard: tuple = (0, 1),
     return hist
 
 
-def mmd_sums_from_histograms(hist: torch.Tensor, m_x: int, m_y: int, kernel, sums: torch.Tensor = None) -> torch.Tensor:
-    """``[S_xx, S_yy, S_xy, sum_ab t_ab]`` (float64) from the Hamming histograms; the auto bandwidth comes from the
-    same histograms.  Fixed reduction order: identical bits wherever the histograms are identical."""
+def _estimator_args(kernel, estimator: str, m_x: int, m_y: int) -> tuple:
+    if estimator not in ("unbiased", "biased"):
+        raise ValueError("estimator must be 'unbiased' or 'biased'")
+    if estimator == "unbiased" and (m_x < 2 or m_y < 2):
+        raise ValueError("the unbiased MMD estimator needs at least two rows in x and in y")
+    return int(estimator == "unbiased"), (1.0 / kernel.n_kernels if kernel.reduce == "mean" else 1.0)
+
+
+def mmd_sums_from_histograms(hist: torch.Tensor, m_x: int, m_y: int, kernel, sums: torch.Tensor = None,
+                             estimator: str = "unbiased") -> torch.Tensor:
+    """``[S_xx, S_yy, S_xy, sum_ab t_ab, MMD^2 estimate]`` (float64) from the Hamming histograms; the auto bandwidth
+    comes from the same histograms.  Fixed reduction order: identical bits wherever the histograms are identical."""
     d = hist.shape[1] - 1
+    unbiased, scale = _estimator_args(kernel, estimator, m_x, m_y)
     if sums is None:
-        sums = torch.empty(4, dtype=torch.float64, device=hist.device)
+        sums = torch.empty(5, dtype=torch.float64, device=hist.device)
     lib = _lib.load()
     bw = -1.0 if kernel.bandwidth is None else kernel.bandwidth
     with torch.cuda.device(hist.device):
         _lib.check(lib.b200grbm_mmd_eval_hist(_lib.ptr(hist), m_x, m_y, d, kernel.n_kernels, kernel.mul_factor,
-                                              int(kernel.squared), bw, _lib.ptr(sums), _lib.current_stream(hist.device)))
+                                              int(kernel.squared), bw, unbiased, scale, _lib.ptr(sums),
+                                              _lib.current_stream(hist.device)))
     return sums
 
 
 def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = None, d: int = None,
-                      return_hist: bool = False):
-    """``[S_xx, S_yy, S_xy, sum_ab t_ab]`` (float64) for +-1 rows ``z = [x; y]`` on tensor cores.
+                      return_hist: bool = False, estimator: str = "unbiased"):
+    """``[S_xx, S_yy, S_xy, sum_ab t_ab, MMD^2 estimate]`` (float64) for +-1 rows ``z = [x; y]`` on tensor cores.
     ``d``: true feature count when ``z`` is already the zero-padded int8 matrix of :func:`pack_rows_i8`.
     ``return_hist``: also return the ``(3, d + 1)`` Hamming histograms the sums were evaluated from."""
     m = z.shape[0]
@@ -135,14 +146,15 @@ def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = No
         zi, d_pad = pack_rows_i8(z)
     else:
         zi, d_pad = z, z.shape[1]
+    unbiased, scale = _estimator_args(kernel, estimator if (m_x >= 2 and m - m_x >= 2) else "biased", m_x, m - m_x)
     if sums is None:
-        sums = torch.empty(4, dtype=torch.float64, device=z.device)
+        sums = torch.empty(5, dtype=torch.float64, device=z.device)
     hist = torch.empty((3, d + 1), dtype=torch.int64, device=z.device)     # workspace, zeroed by the call
     lib = _lib.load()
     bw = -1.0 if kernel.bandwidth is None else kernel.bandwidth
     with torch.cuda.device(z.device):
         _lib.check(lib.b200grbm_mmd_forward_i8(_lib.ptr(zi), m_x, m - m_x, d, d_pad, kernel.n_kernels,
-                                               kernel.mul_factor, int(kernel.squared), bw, _lib.ptr(hist),
+                                               kernel.mul_factor, int(kernel.squared), bw, unbiased, scale, _lib.ptr(hist),
                                                _lib.ptr(sums), _lib.current_stream(z.device)))
     return (sums, hist) if return_hist else sums
 

@@ -219,19 +219,22 @@ int32_t b200grbm_mmd_backward_f32(const float *z_dev, int32_t m_x, int32_t m_y, 
  * [1] inside y, [2] x-y pairs).  shard_rank / shard_world deal the tiles round-robin over ranks that each hold the
  * whole z: the per-rank histograms add up (int64 all-reduce) to the single-GPU histogram exactly -- this is the
  * "MMD partial sums combined by all-reduce" of the multi-GPU path.
- * b200grbm_mmd_eval_hist: sums_dev[4] (same contract as b200grbm_mmd_forward_f32) from the histograms, float64,
- * fixed reduction order; the data-dependent bandwidth comes from the same histograms, so the auto-bandwidth
- * forward needs one Gram pass, not two.
+ * b200grbm_mmd_eval_hist: sums_dev[5] from the histograms, float64, fixed reduction order: [0..3] as
+ * b200grbm_mmd_forward_f32, [4] = scale * (E k(x,x') + E k(y,y') - 2 E k(x,y)) with the unbiased (diagonal dropped,
+ * unbiased != 0) or biased block means -- the value maximum_mean_discrepancy_loss returns (scale = 1, or 1 / n_kernels
+ * for the mean-of-kernels variant).  The data-dependent bandwidth comes from the same histograms, so the
+ * auto-bandwidth forward needs one Gram pass, not two.
  * b200grbm_mmd_forward_i8 = memset + hist (all tiles) + eval; hist_dev is a workspace of 3 (d + 1) uint64.
  */
 int32_t b200grbm_mmd_pack_i8(const float *z_dev, int32_t m, int32_t d, int32_t d_pad, int8_t *out_dev, void *stream);
 int32_t b200grbm_mmd_hist_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad, int32_t shard_rank,
                              int32_t shard_world, uint64_t *hist_dev, void *stream);
 int32_t b200grbm_mmd_eval_hist(const uint64_t *hist_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t n_kernels,
-                               float mul_factor, int32_t squared, float bandwidth, double *sums_dev, void *stream);
+                               float mul_factor, int32_t squared, float bandwidth, int32_t unbiased, double scale,
+                               double *sums_dev, void *stream);
 int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,
-                                int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth, uint64_t *hist_dev,
-                                double *sums_dev, void *stream);
+                                int32_t n_kernels, float mul_factor, int32_t squared, float bandwidth, int32_t unbiased,
+                                double scale, uint64_t *hist_dev, double *sums_dev, void *stream);
 
 /*
  * Fused spin extraction (src/model_wrapper.py:318: `spins.reshape(-1, n)` feeds the MMD at :320 and, detached, the

@@ -86,7 +86,7 @@ class _NumpyOps:
         return torch.from_numpy(O.hamming_histograms(z.numpy(), m_x, shard))
 
     @staticmethod
-    def sums(hist, m_x, m_y, kernel):
+    def sums(hist, m_x, m_y, kernel, estimator="unbiased"):
         from oracle import oracle as O
         return torch.from_numpy(O.mmd_sums_from_histograms(hist.numpy(), m_x + m_y, kernel.n_kernels, kernel.mul_factor,
                                                            kernel.bandwidth, kernel.squared))
