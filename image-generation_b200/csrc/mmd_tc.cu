@@ -458,17 +458,31 @@ int32_t make_tensor_map_2d(CUtensorMap *map, const void *base, CUtensorMapDataTy
 int32_t launch_gram_i8_2cta(const CUtensorMap &tmap, int m_x, int m, int d, int d_pad, unsigned long long *hist,
                             int shard_rank, int shard_world, cudaStream_t st);
 
-// Forward tile shape.  Measured on B200 (8192 + 8192 rows): while the sample matrix fits in L2 the single-CTA
-// kernel and the CTA-pair kernel run at the same k-block rate (742 vs 750 clk per 128-byte k-block at
-// D = 5632); once it does not (D = 11264, 185 MB) the pair kernel's 33 % smaller operand traffic wins
-// (1.04 vs 1.16 ms).  B200GRBM_MMD_TILE=1|2 forces one of them (A/B measurements, parity tests of both).
+// Forward tile shape.  The single-CTA kernel reads 48 KB of operands per k-block from shared memory and receives as
+// many from TMA: against the 128 B/clk of shared-memory bandwidth that alone caps it near 70 % of the tensor rate
+// (742 clk per k-block measured, 512 ideal), and every shared-memory access of the counting epilogue comes on top.
+// The CTA-pair kernel (mmd_tc2.cu) stages 32 KB per k-block and CTA; with the counting epilogue it is the faster one
+// at every size that fills the machine (cfg3: 0.60 vs 0.69 ms), so it is the default from 74 pair-tiles up.
+// B200GRBM_MMD_TILE=1|2 forces one of them (A/B measurements, parity tests of both).
+//
+// Counting experiments (cfg3, B200), all exact, kept here because they explain the design:
+//   ATOMS per entry on a CTA histogram (this version)                         single 0.69 ms   pair 0.60 ms
+//   per-lane byte counters in shared memory (conflict-free, no atomics),
+//     windows of 224 / 288 distances, flushed per tile into the CTA histogram single 0.72 ms   pair 0.62 ms
+//   the same windows flushed straight to the global histogram                 single 1.43 ms   (8 M atomics on ~300
+//                                                                             hot addresses serialise in L2)
+//   epilogue that reads TMEM and counts nothing, 3 stages                     single 0.50 ms
+// ncu (source view) shows the epilogue warps WAITING for accumulators a third of the time in every variant: the
+// counting is not latency- or issue-bound, it takes shared-memory bandwidth from the MMA operand stream, and any
+// counter scheme with >= 2 shared-memory wavefronts per 32 entries costs about the same.
 static bool use_pair_kernel(int m, int d_pad)
 {
     const char *env = getenv("B200GRBM_MMD_TILE");
     if (env != nullptr && env[0] == '1') return false;
     if (env != nullptr && env[0] == '2') return true;
+    (void)d_pad;
     const int tiles = (m + 255) / 256;
-    return tiles * (tiles + 1) / 2 >= 74 && (size_t)m * (size_t)d_pad > (size_t)100 << 20;
+    return tiles * (tiles + 1) / 2 >= 74;
 }
 
 static int32_t gram_smem(int d, int *stages_out, size_t *smem_out, const char *who)
