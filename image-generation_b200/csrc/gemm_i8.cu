@@ -25,6 +25,8 @@
 // boxes evict Z^T lines the other CTAs of the wave are about to re-read.)
 #include "tc_common.cuh"
 
+#include <cstdlib>
+
 namespace b200grbm {
 
 constexpr int I_BM = 128, I_BN = 256, I_BK = 128;       // bytes = int8 elements per k-block: one 128-byte swizzle row
@@ -194,6 +196,162 @@ __global__ void __launch_bounds__(I_THREADS, 1) gemm_i8_planes_kernel(const __gr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair version (tcgen05 cta_group::2): two SMs of a TPC share one 256 x 256 output tile.  Each CTA stages its own
+// 128 rows of the digit plane and HALF of the Z^T rows per k-block -- 32 KB instead of 48 KB per 128 x 256 x 128 MACs.
+// The single-CTA kernel above moves 48 KB per k-block out of shared memory into the tensor core and as many in from
+// TMA; at 128 B/clk that alone caps it near 70 % of the tensor rate.  Same barrier scheme as mmd_tc2.cu: full[s] lives
+// in the leader (2 arrivals + both CTAs' transaction bytes), empty[s] / tmem_full[a] are arrived in both CTAs by the
+// multicast tcgen05.commit, tmem_empty[a] lives in the leader (2 x 8 epilogue warps).
+constexpr int I2_STAGE_BYTES = 2 * I_A_BYTES;        // 16 KB of A + 16 KB of B per CTA
+constexpr int I2_STAGES = 6;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I_THREADS, 1)
+    gemm_i8_planes_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                               const GemmI8Params p)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)I2_STAGES * I2_STAGE_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * I2_STAGES + 4);
+    const uint32_t full0 = smem_addr(bars), empty0 = full0 + 8u * I2_STAGES, tfull0 = empty0 + 8u * I2_STAGES,
+                   tempty0 = tfull0 + 16u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < I2_STAGES; ++s) { bar_init(full0 + 8u * s, 2); bar_init(empty0 + 8u * s, 1); }
+        for (int a = 0; a < 2; ++a) { bar_init(tfull0 + 8u * a, 1); bar_init(tempty0 + 8u * a, 2 * I_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1) tmem_alloc_2cta(smem_addr(tmem_slot), 512);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                      // the peer's barriers are initialised before anyone arrives remotely
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ---- TMA producer (both CTAs)
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = pair; t < p.total_tiles; t += n_pairs) {
+                int ti, tj;
+                gemm_i8_tile(p, t, ti, tj);
+                for (int pl = 0; pl < p.n_planes; ++pl) {
+                    const int a_row = pl * p.rows_alloc + ti * 256 + (int)rank * 128;
+                    const int b_row = tj * I_BN + (int)rank * 128;
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        bar_wait(empty0 + 8u * s, ph ^ 1u);
+                        const uint32_t lead_full = mapa_cluster(full0 + 8u * s, 0);
+                        const uint32_t dst = smem_addr(smem + (size_t)s * I2_STAGE_BYTES);
+                        if (leader) bar_expect_tx(full0 + 8u * s, 2 * I2_STAGE_BYTES);
+                        else bar_arrive_cluster(lead_full);
+                        tma_load_2d_2sm(dst, &map_a, kb * I_BK, a_row, lead_full);
+                        tma_load_2d_2sm(dst + I_A_BYTES, &map_b, kb * I_BK, b_row, lead_full);
+                        if (++s == I2_STAGES) { s = 0; ph ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {                         // ---- MMA issuer (leader CTA only)
+            const uint32_t idesc = umma_idesc_i8(256, 256);
+            int s = 0, unit = 0;
+            uint32_t ph = 0;
+            for (int t = pair; t < p.total_tiles; t += n_pairs) {
+                for (int pl = 0; pl < p.n_planes; ++pl, ++unit) {
+                    const uint32_t acc = (uint32_t)unit & 1u, acc_ph = ((uint32_t)unit >> 1) & 1u;
+                    bar_wait(tempty0 + 8u * acc, acc_ph ^ 1u);               // both epilogues drained this accumulator
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d_tmem = tmem_base + acc * I_BN;
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        bar_wait(full0 + 8u * s, ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_addr = smem_addr(smem + (size_t)s * I2_STAGE_BYTES);
+                        const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + I_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < I_BK / I_UMMA_K; ++k)
+                            umma_i8_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_2cta(empty0 + 8u * s);                   // frees the stage in both CTAs
+                        if (++s == I2_STAGES) { s = 0; ph ^= 1u; }
+                    }
+                    umma_commit_2cta(tfull0 + 8u * acc);                     // accumulator ready in both CTAs
+                }
+            }
+        }
+    } else {                                               // ---- epilogue (both CTAs)
+        const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+        const float gscale = (float)((double)__ldg(p.grad_out) * __ldg(p.scale));
+        const bool vec_ok = (p.d & 3) == 0;
+        const uint32_t lead_tempty0 = mapa_cluster(tempty0, 0);
+        int unit = 0;
+        for (int t = pair; t < p.total_tiles; t += n_pairs) {
+            int ti, tj;
+            gemm_i8_tile(p, t, ti, tj);
+            const int row = ti * 256 + (int)rank * 128 + quarter * 32 + lane;
+            float accum[128];
+            for (int pl = 0; pl < p.n_planes; ++pl, ++unit) {
+                const uint32_t acc = (uint32_t)unit & 1u, acc_ph = ((uint32_t)unit >> 1) & 1u;
+                bar_wait(tfull0 + 8u * acc, acc_ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int chunk = 0; chunk < 4; ++chunk) {
+                    uint32_t v[32];
+                    __syncwarp();
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * I_BN + (uint32_t)(half * 128 + chunk * 32), v);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float x = (float)(int)v[c];
+                        accum[chunk * 32 + c] = pl == 0 ? x : fmaf(accum[chunk * 32 + c], 256.0f, x);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) bar_arrive_cluster(lead_tempty0 + 8u * acc);
+            }
+            if (row < p.n_rows) {
+                const float rs = (float)__ldg(p.rowsum + row);
+                const int8_t *zrow = p.z + (size_t)(p.z_row0 + row) * p.d_pad;
+                float *out = p.grad_x + (size_t)row * p.d;
+#pragma unroll
+                for (int chunk = 0; chunk < 4; ++chunk) {
+                    const int col = tj * I_BN + half * 128 + chunk * 32;
+                    if (col >= p.d) continue;
+                    const uint4 za = *reinterpret_cast<const uint4 *>(zrow + col), zb = *reinterpret_cast<const uint4 *>(zrow + col + 16);
+                    const uint32_t zw[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+                    float r[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float zs = (float)(int8_t)((zw[c >> 2] >> (8 * (c & 3))) & 0xffu);
+                        r[c] = gscale * (rs * zs - accum[chunk * 32 + c]);
+                    }
+                    if (vec_ok && col + 32 <= p.d) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4 *>(out + col + 4 * q) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (col + c < p.d) out[col + c] = r[c];
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                      // neither CTA frees TMEM / exits while the peer may still touch it
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_dealloc_2cta(tmem_base, 512);
+    }
+}
+
 // int8 transpose with zero fill: out[c][r] = in[r][c] for r < rows, c < cols; out has `out_rows` = cols rows of pitch
 // out_pitch >= rows; columns r in [rows, out_pitch) are zeroed.  (ZT for callers that hold only the row-major matrix.)
 __global__ void transpose_i8_kernel(const int8_t *__restrict__ in, int rows, int cols, int in_pitch, int8_t *__restrict__ out,
@@ -267,9 +425,28 @@ extern "C" int32_t b200grbm_mmd_grad_i8(const int8_t *planes_dev, int32_t n_plan
     p.grad_out = grad_out_dev;
     p.z = z_dev; p.z_row0 = z_row0; p.d_pad = d_pad;
     p.grad_x = grad_x_dev;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    // CTA pairs (256-row tiles) once they fill the machine; B200GRBM_GEMM_TILE=1|2 forces a shape (A/B measurements, tests)
+    const int pair_tiles = ((n_rows + 255) / 256) * p.tiles_n;
+    const char *env = getenv("B200GRBM_GEMM_TILE");
+    const bool use_pair = env != nullptr && (env[0] == '1' || env[0] == '2') ? env[0] == '2' : pair_tiles >= sms / 2;
+    if (use_pair) {
+        p.tiles_m = (n_rows + 255) / 256;
+        p.total_tiles = pair_tiles;
+        int band2 = (int)(band_budget / (2 * per_row_tile));
+        if (band2 < 1) band2 = 1;
+        if (band2 > p.tiles_m) band2 = p.tiles_m;
+        p.band_rows = band2;
+        const size_t smem2 = (size_t)I2_STAGES * I2_STAGE_BYTES + (2 * I2_STAGES + 4) * 8 + 16 + 1024;
+        B200_CUDA(cudaFuncSetAttribute(gemm_i8_planes_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        int pairs = sms / 2;
+        if (pairs > p.total_tiles) pairs = p.total_tiles;
+        gemm_i8_planes_2cta_kernel<<<2 * pairs, I_THREADS, smem2, (cudaStream_t)stream>>>(ma, mb, p);     // __cluster_dims__(2,1,1)
+        B200_CUDA(cudaGetLastError());
+        return 0;
+    }
     const size_t smem = (size_t)I_STAGES * I_STAGE_BYTES + (2 * I_STAGES + 4) * 8 + 16 + 1024;
     B200_CUDA(cudaFuncSetAttribute(gemm_i8_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int sms = sm_count() > 0 ? sm_count() : 148;
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     gemm_i8_planes_kernel<<<grid, I_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, p);
     B200_CUDA(cudaGetLastError());

@@ -411,9 +411,13 @@ def test_reference_call_without_extra_arguments_reaches_tensor_cores(cuda_device
     assert M.last_path == "bf16x3" and torch.isfinite(xc.grad).all()
 
 
+@pytest.mark.parametrize("gemm_tile", ["1", "2"])
 @pytest.mark.parametrize("n_planes,tol", [(2, 2e-4), (3, 2e-6)])
-def test_fixed_point_backward_accuracy_by_digit_planes(cuda_device, n_planes, tol):
-    """d(MMD)/dx through the int8 GEMM: 2 digit planes (16-bit fixed point, the default) and 3 planes (24 bits)."""
+def test_fixed_point_backward_accuracy_by_digit_planes(cuda_device, monkeypatch, n_planes, tol, gemm_tile):
+    """d(MMD)/dx through the int8 GEMM: 2 digit planes (16-bit fixed point, the default) and 3 planes (24 bits), on the
+    single-CTA kernel and on the CTA-pair (cta_group::2, 256-row tiles) kernel -- integer arithmetic, so both must give
+    the same bits."""
+    monkeypatch.setenv("B200GRBM_GEMM_TILE", gemm_tile)
     from image_generation_b200.mmd_tc import mmd_backward_i8, pack_pair_i8
     rng = np.random.default_rng(9)
     m_x, m_y, d = 384, 300, 200
@@ -436,6 +440,9 @@ def test_fixed_point_backward_accuracy_by_digit_planes(cuda_device, n_planes, to
     # a row range (what a rank of the sharded MMD asks for) and the transpose built on demand agree bit for bit
     part = mmd_backward_i8(pair.rows, d, m_x, kern, sums, w_xx, w_xy, one, rows=(128, 200), n_planes=n_planes, hist=hist).cpu().numpy()
     assert np.array_equal(part, got[128:328])
+    monkeypatch.setenv("B200GRBM_GEMM_TILE", "1" if gemm_tile == "2" else "2")
+    other = mmd_backward_i8(pair.rows, d, m_x, kern, sums, w_xx, w_xy, one, zt=pair.zt, n_planes=n_planes, hist=hist).cpu().numpy()
+    assert np.array_equal(other, got)
 
 
 def test_spin_extract_layouts(cuda_device):
