@@ -56,6 +56,32 @@ __device__ __forceinline__ void gemm_i8_tile(const GemmI8Params &p, int t, int &
     ti = band * p.band_rows + r % rows_here;
 }
 
+// Output stage of both GEMM kernels: grad_x[row][col .. col + 128) = gscale * (rowsum * z - accum), four columns per step
+// so that no second 32-float array is alive next to the 128 accumulators.
+__device__ __forceinline__ void gemm_i8_store_row(const GemmI8Params &p, const float (&accum)[128], int row, int col0, float gscale)
+{
+    const float rs = (float)__ldg(p.rowsum + row);
+    const int8_t *zrow = p.z + (size_t)(p.z_row0 + row) * p.d_pad;
+    float *out = p.grad_x + (size_t)row * p.d;
+    const bool vec_ok = (p.d & 3) == 0;
+#pragma unroll
+    for (int g = 0; g < 32; ++g) {              // 32 groups of 4 columns
+        const int col = col0 + 4 * g;
+        if (col >= p.d) break;
+        const uint32_t zw = *reinterpret_cast<const uint32_t *>(zrow + col);    // d_pad is a multiple of 128; pad columns are zero
+        float r[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) r[c] = gscale * (rs * (float)(int8_t)((zw >> (8 * c)) & 0xffu) - accum[4 * g + c]);
+        if (vec_ok && col + 4 <= p.d) {
+            *reinterpret_cast<float4 *>(out + col) = make_float4(r[0], r[1], r[2], r[3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (col + c < p.d) out[col + c] = r[c];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(I_THREADS, 1) gemm_i8_planes_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                       const __grid_constant__ CUtensorMap map_b,
                                                                       const GemmI8Params p)
@@ -132,13 +158,14 @@ __global__ void __launch_bounds__(I_THREADS, 1) gemm_i8_planes_kernel(const __gr
     } else {                                               // ---- epilogue: TMEM planes -> fixed point -> gradient rows
         const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
         const float gscale = (float)((double)__ldg(p.grad_out) * __ldg(p.scale));
-        const bool vec_ok = (p.d & 3) == 0;
         int unit = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             int ti, tj;
             gemm_i8_tile(p, t, ti, tj);
             const int row = ti * I_BM + quarter * 32 + lane;
             float accum[128];
+#pragma unroll
+            for (int k = 0; k < 128; ++k) accum[k] = 0.f;
             for (int pl = 0; pl < p.n_planes; ++pl, ++unit) {
                 const uint32_t acc = (uint32_t)unit & 1u, acc_ph = ((uint32_t)unit >> 1) & 1u;
                 bar_wait(tfull0 + 8u * acc, acc_ph);
@@ -151,41 +178,14 @@ __global__ void __launch_bounds__(I_THREADS, 1) gemm_i8_planes_kernel(const __gr
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const float x = (float)(int)v[c];           // |x| <= 128 K < 2^24: exact
-                        accum[chunk * 32 + c] = pl == 0 ? x : fmaf(accum[chunk * 32 + c], 256.0f, x);
+                        accum[chunk * 32 + c] = fmaf(accum[chunk * 32 + c], 256.0f, x);      // in place: acc = 256 acc + digit
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) bar_arrive(tempty0 + 8u * acc);
             }
-            if (row < p.n_rows) {
-                const float rs = (float)__ldg(p.rowsum + row);
-                const int8_t *zrow = p.z + (size_t)(p.z_row0 + row) * p.d_pad;
-                float *out = p.grad_x + (size_t)row * p.d;
-#pragma unroll
-                for (int chunk = 0; chunk < 4; ++chunk) {
-                    const int col = tj * I_BN + half * 128 + chunk * 32;
-                    if (col >= p.d) continue;
-                    // 32 spins of this row: two aligned 16-byte loads (d_pad is a multiple of 128; pad columns are zero)
-                    const uint4 za = *reinterpret_cast<const uint4 *>(zrow + col), zb = *reinterpret_cast<const uint4 *>(zrow + col + 16);
-                    const uint32_t zw[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
-                    float r[32];
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float zs = (float)(int8_t)((zw[c >> 2] >> (8 * (c & 3))) & 0xffu);
-                        r[c] = gscale * (rs * zs - accum[chunk * 32 + c]);
-                    }
-                    if (vec_ok && col + 32 <= p.d) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *reinterpret_cast<float4 *>(out + col + 4 * q) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            if (col + c < p.d) out[col + c] = r[c];
-                    }
-                }
-            }
+            if (row < p.n_rows) gemm_i8_store_row(p, accum, row, tj * I_BN + half * 128, gscale);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -287,7 +287,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I_THREADS, 1)
     } else {                                               // ---- epilogue (both CTAs)
         const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
         const float gscale = (float)((double)__ldg(p.grad_out) * __ldg(p.scale));
-        const bool vec_ok = (p.d & 3) == 0;
         const uint32_t lead_tempty0 = mapa_cluster(tempty0, 0);
         int unit = 0;
         for (int t = pair; t < p.total_tiles; t += n_pairs) {
@@ -295,6 +294,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I_THREADS, 1)
             gemm_i8_tile(p, t, ti, tj);
             const int row = ti * 256 + (int)rank * 128 + quarter * 32 + lane;
             float accum[128];
+#pragma unroll
+            for (int k = 0; k < 128; ++k) accum[k] = 0.f;
             for (int pl = 0; pl < p.n_planes; ++pl, ++unit) {
                 const uint32_t acc = (uint32_t)unit & 1u, acc_ph = ((uint32_t)unit >> 1) & 1u;
                 bar_wait(tfull0 + 8u * acc, acc_ph);
@@ -307,40 +308,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I_THREADS, 1)
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const float x = (float)(int)v[c];
-                        accum[chunk * 32 + c] = pl == 0 ? x : fmaf(accum[chunk * 32 + c], 256.0f, x);
+                        accum[chunk * 32 + c] = fmaf(accum[chunk * 32 + c], 256.0f, x);      // in place: acc = 256 acc + digit
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) bar_arrive_cluster(lead_tempty0 + 8u * acc);
             }
-            if (row < p.n_rows) {
-                const float rs = (float)__ldg(p.rowsum + row);
-                const int8_t *zrow = p.z + (size_t)(p.z_row0 + row) * p.d_pad;
-                float *out = p.grad_x + (size_t)row * p.d;
-#pragma unroll
-                for (int chunk = 0; chunk < 4; ++chunk) {
-                    const int col = tj * I_BN + half * 128 + chunk * 32;
-                    if (col >= p.d) continue;
-                    const uint4 za = *reinterpret_cast<const uint4 *>(zrow + col), zb = *reinterpret_cast<const uint4 *>(zrow + col + 16);
-                    const uint32_t zw[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
-                    float r[32];
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float zs = (float)(int8_t)((zw[c >> 2] >> (8 * (c & 3))) & 0xffu);
-                        r[c] = gscale * (rs * zs - accum[chunk * 32 + c]);
-                    }
-                    if (vec_ok && col + 32 <= p.d) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *reinterpret_cast<float4 *>(out + col + 4 * q) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            if (col + c < p.d) out[col + c] = r[c];
-                    }
-                }
-            }
+            if (row < p.n_rows) gemm_i8_store_row(p, accum, row, tj * I_BN + half * 128, gscale);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
