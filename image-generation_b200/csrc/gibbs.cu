@@ -431,47 +431,52 @@ __global__ void __launch_bounds__(MAXT, 1) gibbs_kernel(const __grid_constant__ 
     }
 
     // ---- write back
-    if (p.packed_out != nullptr)
-        for (int pp = tid; pp < p.n; pp += nthr) p.packed_out[(size_t)g * p.n_pad + pp] = kernel_to_dense<CPL>(W[pp]) & dense_mask;
-    if (p.state_out != nullptr) {
-        // int8 rows in node order.  The group's rows are one contiguous range of the output, so they are assembled in
-        // the (now idle) tile stages -- the permutation order[] becomes a shared-memory byte scatter -- and streamed
-        // out with aligned 16-byte stores.  (Storing straight from the words costs nvalid single-byte global stores per
-        // spin at a stride of n: irrelevant behind 1000 sweeps, but the whole HBM cost of a short persistent-chain
-        // advance or of the 244 MB state of a Zephyr shard.)
-        const uint32_t stage_cap = p.tile_bytes * (p.resident ? (uint32_t)p.n_tiles : (p.single ? 1u : 2u));
-        int rows_per_pass = (int)((stage_cap - 16u) / (uint32_t)p.n);
-        if (rows_per_pass > nvalid) rows_per_pass = nvalid;
-        if (rows_per_pass < 1) {
-            for (int pp = tid; pp < p.n; pp += nthr) {                       // tiles smaller than one row: direct stores
-                const uint32_t w = kernel_to_dense<CPL>(W[pp]) & dense_mask;
-                const int node = p.order[pp];
-                for (int c = 0; c < nvalid; ++c)
-                    p.state_out[(size_t)(chain0 + c) * p.n + node] = (w >> c) & 1u ? (int8_t)1 : (int8_t)-1;
-            }
-        } else {
-            for (int c0 = 0; c0 < nvalid; c0 += rows_per_pass) {
-                const int rows = min(rows_per_pass, nvalid - c0);
-                int8_t *gdst = p.state_out + (size_t)(chain0 + c0) * p.n;
-                const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);   // same alignment on both sides
-                int8_t *buf = reinterpret_cast<int8_t *>(stage0) + mis;
-                __syncthreads();                                                 // previous pass streamed out
-                for (int pp = tid; pp < p.n; pp += nthr) {
-                    const uint32_t w = kernel_to_dense<CPL>(W[pp]) >> c0;
-                    const int node = p.order[pp];
-                    for (int c = 0; c < rows; ++c) buf[c * p.n + node] = (w >> c) & 1u ? (int8_t)1 : (int8_t)-1;
-                }
-                __syncthreads();
-                const int total = rows * p.n;
-                const int head = min(total, (int)((16u - mis) & 15u));
-                const int body = (total - head) >> 4;
-                for (int k = tid; k < head; k += nthr) gdst[k] = buf[k];
-                const uint4 *s4 = reinterpret_cast<const uint4 *>(buf + head);
-                uint4 *g4 = reinterpret_cast<uint4 *>(gdst + head);
-                for (int k = tid; k < body; k += nthr) g4[k] = s4[k];
-                for (int k = head + (body << 4) + tid; k < total; k += nthr) gdst[k] = buf[k];
-            }
+    for (int pp = tid; pp < p.n; pp += nthr) {
+        const uint32_t w = kernel_to_dense<CPL>(W[pp]) & dense_mask;
+        if (p.packed_out != nullptr) p.packed_out[(size_t)g * p.n_pad + pp] = w;
+        if (p.state_out != nullptr) {
+            const int node = p.order[pp];
+            for (int c = 0; c < nvalid; ++c)
+                p.state_out[(size_t)(chain0 + c) * p.n + node] = (w >> c) & 1u ? (int8_t)1 : (int8_t)-1;
         }
+    }
+}
+
+// Packed final state -> int8 rows in node order (dimod's SampleSet.record.sample layout).  A kernel of its own: the
+// sweep kernel writes only its bit-packed words (coalesced), and this one turns the words of a chain group into the
+// group's rows -- one contiguous range of the output -- by scattering bytes into SHARED memory (the permutation
+// order[] costs nothing there) and streaming the rows out with aligned 16-byte stores.  Doing the same inside the
+// sweep kernel's tail (either as nvalid single-byte global stores per spin, the round-1 form, or staged through the
+// idle tile buffers) changes ptxas's allocation for the sweep loop: 92 -> 93 registers and 1.8 % of the headline rate.
+__global__ void __launch_bounds__(256) unpack_state_kernel(const uint32_t *__restrict__ packed, int chains, int cpl, int n, int n_pad,
+                                                           const int32_t *__restrict__ order, int8_t *__restrict__ state_out,
+                                                           int rows_per_pass)
+{
+    extern __shared__ __align__(16) int8_t rows_buf[];
+    const int g = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const int chain0 = g * cpl;
+    const int nvalid = min(cpl, chains - chain0);
+    const uint32_t *words = packed + (size_t)g * n_pad;
+    for (int c0 = 0; c0 < nvalid; c0 += rows_per_pass) {
+        const int rows = min(rows_per_pass, nvalid - c0);
+        int8_t *gdst = state_out + (size_t)(chain0 + c0) * n;
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);   // same alignment on both sides
+        int8_t *buf = rows_buf + mis;
+        __syncthreads();                                                 // previous pass streamed out
+        for (int pp = tid; pp < n; pp += nthr) {
+            const uint32_t w = __ldg(words + pp) >> c0;
+            const int node = __ldg(order + pp);
+            for (int c = 0; c < rows; ++c) buf[c * n + node] = (w >> c) & 1u ? (int8_t)1 : (int8_t)-1;
+        }
+        __syncthreads();
+        const int total = rows * n;
+        const int head = min(total, (int)((16u - mis) & 15u));
+        const int body = (total - head) >> 4;
+        for (int k = tid; k < head; k += nthr) gdst[k] = buf[k];
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(buf + head);
+        uint4 *g4 = reinterpret_cast<uint4 *>(gdst + head);
+        for (int k = tid; k < body; k += nthr) g4[k] = s4[k];
+        for (int k = head + (body << 4) + tid; k < total; k += nthr) gdst[k] = buf[k];
     }
 }
 
@@ -674,8 +679,25 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
     gibbs_fn fn = pick(a->chains_per_lane, mode, a->threads, !p.single);
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // int8 rows: with a packed output buffer at hand the sweep kernel writes only its words and a second kernel unpacks
+    // them (coalesced); without one the sweep kernel stores the bytes itself
+    const bool unpack = a->state_out_dev != nullptr && a->packed_out_dev != nullptr;
+    if (unpack) p.state_out = nullptr;
     fn<<<groups, a->threads, smem, (cudaStream_t)stream>>>(p);
     B200_CUDA(cudaGetLastError());
     g_last_launches = 1;
+    if (unpack) {
+        int rows_per_pass = (int)((64u * 1024u - 16u) / (uint32_t)a->n);        // <= 64 KB of rows per CTA: three CTAs per SM
+        if (rows_per_pass > a->chains_per_lane) rows_per_pass = a->chains_per_lane;
+        if (rows_per_pass < 1) rows_per_pass = 1;
+        const size_t usmem = (size_t)rows_per_pass * a->n + 16;
+        if (usmem > (size_t)smem_optin)
+            return fail(B200GRBM_EUNSUPPORTED, "gibbs_sweeps: n=%d too large for the state unpack kernel's shared-memory row", a->n);
+        B200_CUDA(cudaFuncSetAttribute(unpack_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+        unpack_state_kernel<<<groups, 256, usmem, (cudaStream_t)stream>>>(a->packed_out_dev, a->chains, a->chains_per_lane, a->n,
+                                                                          a->n_pad, a->order_dev, a->state_out_dev, rows_per_pass);
+        B200_CUDA(cudaGetLastError());
+        g_last_launches = 2;
+    }
     return 0;
 }

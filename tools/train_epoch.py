@@ -9,13 +9,15 @@ Per rank: one HybridDVAE replica (stock-PyTorch encoder / decoder, gradients ave
 all-reduce), `chains-total / N` chains of the global chain-id space (Philox keyed by global id), annealed
 beta 0.1 -> 1; the GRBM gradient comes from the integer sufficient statistics of ALL chains and ALL data
 rows, summed over ranks with one int64 all-reduce (bit-identical on every rank, so the replicated Adam
-steps stay in lock-step without broadcasting parameters).  The MMD term uses the first `--mmd-samples`
-chains of the rank.
+steps stay in lock-step without broadcasting parameters).  The MMD term (src/model_wrapper.py:320) is the GLOBAL
+estimate over every rank's encoder spins against `--mmd-samples` chains per rank (dist.sharded_mmd_loss: int8
+all-gather, Gram tiles dealt over the ranks, one int64 all-reduce of the Hamming histograms); `--local-mmd` keeps the
+round-1 behaviour (each rank's MMD sees only its own rows).
 """
 import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
-from image_generation_b200.dist import shard_chains
+from image_generation_b200.dist import shard_chains, sharded_mmd_loss
 from image_generation_b200.dvae import HybridDVAE, synthetic_batch, train_grbm
 from image_generation_b200.losses import nll_loss
 from image_generation_b200.mmd import maximum_mean_discrepancy_loss
@@ -28,6 +30,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--mmd-samples", type=int, default=4096)
     ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--local-mmd", action="store_true")
     args = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -64,8 +67,13 @@ def main():
                                             as_tensor=False)
         samples = sample_set.samples_tensor
         spins = spins.reshape(-1, spins.shape[-1])
-        mmd = maximum_mean_discrepancy_loss(spins, samples[: args.mmd_samples].float(), kernel, path="i8")
-        (mse + mmd).backward()
+        if world > 1 and not args.local_mmd:
+            # global MMD: d(global loss)/d(local spins); the replica gradients are AVERAGED below, hence the factor
+            mmd = sharded_mmd_loss(spins, samples[: args.mmd_samples], kernel)
+            (mse + world * mmd).backward()
+        else:
+            mmd = maximum_mean_discrepancy_loss(spins, samples[: args.mmd_samples].float(), kernel, path="i8")
+            (mse + mmd).backward()
         if world > 1:  # average the replica gradients: one flattened all-reduce
             flat = torch.cat([p.grad.reshape(-1) for p in params])
             dist.all_reduce(flat)
@@ -104,7 +112,8 @@ def main():
         upd = args.chains_total * args.sweeps * 256
         print(json.dumps({"world": world, "chains_total": args.chains_total, "sweeps": args.sweeps, "steps": args.steps,
                           "ms_per_step_median": 1e3 * float(np.median(times[2:])), "mse_first_last": [log[0][0], log[-1][0]],
-                          "mmd_first_last": [log[0][1], log[-1][1]], "grbm_replicas_bit_identical": in_sync,
+                          "mmd_first_last": [log[0][1], log[-1][1]], "mmd": "local" if (args.local_mmd or world == 1) else "global (sharded_mmd_loss)",
+                          "grbm_replicas_bit_identical": in_sync,
                           "sampler_updates_per_step": upd}))
 
 
