@@ -10,7 +10,7 @@ mkdir -p build
 rm -f build/*.o libb200grbm.so
 pids=""
 # the sampler's field sums must not be contracted into FMAs (include/b200grbm_spec.h)
-for f in gibbs.cu gibbs_small.cu; do
+for f in gibbs.cu gibbs_small.cu gibbs_wide.cu; do
   if [ -f "$f" ]; then $NVCC $COMMON --fmad=false -c "$f" -o "build/${f%.cu}.o" & pids="$pids $!"; fi
 done
 for f in common.cu stats.cu mmd_simt.cu mmd_tc.cu mmd_tc2.cu gemm_tc.cu gemm_i8.cu spin_extract.cu mmd_bf16.cu tc_peak.cu; do

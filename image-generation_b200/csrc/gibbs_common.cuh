@@ -29,6 +29,7 @@ struct SweepParams {
     uint32_t tile_bytes;    // (width + 1) * threads * 8
     uint32_t resident;      // 1: all n_tiles tiles fit in shared memory and are copied once (small graphs)
     uint32_t single;        // 1: one tile stage per CTA, two CTAs per SM cover each other's copy latency
+    uint32_t drawn_offset;  // byte offset of the pre-drawn Philox words [calls][threads] x 16 B (gibbs_kernel<.., PD = true>)
     uint32_t rk[2 * B200GRBM_PHILOX_ROUNDS];
 };
 
@@ -44,6 +45,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)

@@ -1,0 +1,171 @@
+// Throughput form of the bit-packed sweep kernel: 28 chains per lane, one CTA per SM, CTA size T and table width W
+// known at compile time (Pegasus: W = 15, Zephyr: W = 20), tables through the 2-stage bulk-copy ring.
+//
+// Same arithmetic, same tables, same shared-memory layout and same results as gibbs_kernel<28, MODE> (gibbs.cu) -- this is
+// the instantiation the headline configuration runs (BASELINE.json configs[1]: Pegasus P16, 4096 chains = 147 groups of
+// 28 = one CTA per SM; reference call sites src/model_wrapper.py:309-316, src/utils/common.py:123-138), rebuilt around what the
+// round-2 profile of the generic kernel showed (profiles/r2_gibbs_ncu_summary.txt, 40.7 warp instructions per 32
+// updates at 76 % issue utilisation):
+//   * 12 % of the executed instructions were bookkeeping of the run-time geometry -- the mode flags, the 64-bit round
+//     counter, table-row address arithmetic and register moves of the rotating 7-slot loop.  With T and W as template
+//     parameters the neighbour slots are fully unrolled, every table entry is one LDS.64 at an immediate offset from a
+//     per-round base and the round loop carries a 32-bit counter.
+//   * 0.57 warps per issue slot sat in the round's __syncthreads() while the Philox draw of the next round -- a quarter
+//     of the kernel's time, and independent of the state -- waited behind it.  Here the round barrier is an mbarrier
+//     used in two halves: a warp ARRIVES when its spins of round q are written, draws the uniforms of its round-q+1
+//     lane-tasks into a per-thread shared-memory slot (4 calls x 16 bytes), and only then WAITS for the stragglers.
+#include "gibbs_packed.cuh"
+
+namespace b200grbm {
+
+constexpr int WIDE_CPL = 28;
+constexpr int WIDE_CALLS = 4;           // Philox calls per lane-task: (28 + shift) / 8 rounded up, shift in {0, 4}
+
+template <int MODE, int T, int W>
+__global__ void __launch_bounds__(T, 1) gibbs_wide_kernel(const __grid_constant__ SweepParams p)
+{
+    constexpr int CPL = WIDE_CPL;
+    constexpr uint32_t TILE_BYTES = (uint32_t)(W + 1) * T * 8u;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);                 // [0], [1]: tile stages; [2]: round barrier
+    int2 *tinfo = reinterpret_cast<int2 *>(smem_raw + 128);
+    uint32_t *Wst = reinterpret_cast<uint32_t *>(smem_raw + 128 + p.info_bytes);
+    unsigned char *stage0 = smem_raw + 128 + p.info_bytes + p.state_bytes;
+
+    const int tid = threadIdx.x;
+    const int g = blockIdx.x;
+    const int chain0 = g * CPL;
+    const int nvalid = min(CPL, p.chains - chain0);
+    const uint32_t dense_mask = (1u << nvalid) - 1u;
+    const uint32_t blk0 = p.chain_block0 + (uint32_t)(chain0 >> 2);
+    const uint32_t blk8 = blk0 >> 1;
+    const bool shift4 = (blk0 & 1u) != 0;
+    const uint32_t bar_addr = smem_u32(bars);
+    const uint32_t stage_addr = smem_u32(stage0);
+    const uint32_t n_tiles = (uint32_t)p.n_tiles;
+    const uint32_t total = (uint32_t)p.num_sweeps * n_tiles;                  // launcher: < 2^31
+    uint4 *drawn = reinterpret_cast<uint4 *>(smem_raw + p.drawn_offset) + tid;   // [call][T]
+
+    if (tid == 0) {
+        mbar_init(bar_addr, 1);
+        mbar_init(bar_addr + 8, 1);
+        mbar_init(bar_addr + 16, T / 32);                                      // one arrival per warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (total > 0) {
+            mbar_expect_tx(bar_addr, TILE_BYTES);
+            bulk_g2s(stage_addr, p.tiles, TILE_BYTES, bar_addr);
+        }
+    }
+    for (int k = tid; k < p.n_tiles; k += T) tinfo[k] = __ldg(p.tile_info + k);
+    load_group_state<CPL>(p, Wst, tid, T, g, chain0, nvalid, dense_mask, blk0);
+    __syncthreads();
+
+    // uniforms of one round for this thread's lane-task: its own slot, nobody else reads it
+    const auto draw_round = [&](uint32_t tile_next, uint32_t sweep_next) {
+        const int2 inf = tinfo[tile_next];
+        if (tid < inf.y) {
+#pragma unroll
+            for (int call = 0; call < WIDE_CALLS; ++call) {
+                uint32_t r[4];
+                philox4x32((uint32_t)(inf.x + tid), blk8 + call, sweep_next, B200GRBM_STREAM_SWEEP, p, r);
+                drawn[call * T] = make_uint4(r[0], r[1], r[2], r[3]);
+            }
+        }
+    };
+    if (total > 0) draw_round(0u, p.sweep_offset);
+
+    uint32_t q = 0;
+    for (int t = 0; t < p.num_sweeps; ++t) {
+        const float coef = __ldg(p.coef + t);
+        const uint32_t sweep = p.sweep_offset + (uint32_t)t;
+#pragma unroll 1
+        for (uint32_t tile = 0; tile < n_tiles; ++tile, ++q) {
+            const uint32_t s = q & 1u;
+            const bool more = q + 1 < total;
+            const uint32_t tile_next = tile + 1 == n_tiles ? 0u : tile + 1;
+            // stage s^1 was last read in round q-1; this thread has seen round q-1's barrier complete
+            if (tid == 0 && more) {
+                const uint32_t nb = bar_addr + 8u * (s ^ 1u);
+                mbar_expect_tx(nb, TILE_BYTES);
+                bulk_g2s(stage_addr + (s ^ 1u) * TILE_BYTES,
+                         reinterpret_cast<const unsigned char *>(p.tiles) + (size_t)tile_next * TILE_BYTES, TILE_BYTES, nb);
+            }
+            const int2 info = tinfo[tile];
+            mbar_wait(bar_addr + 8u * s, (q >> 1) & 1u);
+
+            if (tid < info.y) {
+                const int pp = info.x + tid;
+                // tile rows: 0 = f0, 1 .. W = neighbour slots {2J bits, byte offset of the neighbour's state word}
+                const uint2 *ep = reinterpret_cast<const uint2 *>(stage0 + s * TILE_BYTES) + tid;
+                float f[CPL];
+                {
+                    const float fz = u2f(ep[0].x);
+                    const uint2 e0 = ep[T];
+                    init_slot<CPL>(f, lds_word(smem_raw, e0.y), fz, u2f(e0.x));
+                }
+#pragma unroll
+                for (int k0 = 1; k0 < W; k0 += 7) {
+                    uint2 e[7];
+                    uint32_t w[7];
+#pragma unroll
+                    for (int i = 0; i < 7; ++i)
+                        if (k0 + i < W) e[i] = ep[(k0 + 1 + i) * T];
+#pragma unroll
+                    for (int i = 0; i < 7; ++i)
+                        if (k0 + i < W) w[i] = lds_word(smem_raw, e[i].y);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i)
+                        if (k0 + i < W) add_slot<CPL>(f, w[i], u2f(e[i].x));
+                }
+                const uint32_t R0[2][4] = {};
+                Wst[pp] = shift4 ? decide_word<CPL, MODE, 4, false, true>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R0, drawn, T)
+                                 : decide_word<CPL, MODE, 0, false, true>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R0, drawn, T);
+            }
+            // split round barrier: arrive (release: this warp's words are visible), draw, wait (acquire)
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar_addr + 16);
+            if (more) draw_round(tile_next, tile + 1 == n_tiles ? sweep + 1u : sweep);
+            mbar_wait(bar_addr + 16, q & 1u);
+        }
+    }
+
+    store_group_state<CPL>(p, Wst, tid, T, g, chain0, nvalid, dense_mask);
+}
+
+typedef void (*wide_fn)(const SweepParams);
+
+template <int T, int W>
+static wide_fn wide_pick_mode(int mode)
+{
+    return mode == MODE_PHILOX_FAST ? gibbs_wide_kernel<MODE_PHILOX_FAST, T, W> : gibbs_wide_kernel<MODE_PHILOX_EXACT, T, W>;
+}
+
+static wide_fn wide_pick(int mode, int threads, int width)
+{
+    if (mode != MODE_PHILOX_EXACT && mode != MODE_PHILOX_FAST) return nullptr;
+    if (threads == 640 && width == 15) return wide_pick_mode<640, 15>(mode);       // Pegasus (P16: 9 rounds of 640 lanes)
+    return nullptr;
+}
+
+// shared-memory bytes of the specialised kernel (0: no instantiation for this geometry): the generic 2-stage layout
+// plus the pre-drawn words behind it
+size_t wide_kernel_smem(int cpl, int mode, int threads, int width, size_t ring_smem, uint32_t *drawn_offset)
+{
+    if (cpl != WIDE_CPL || wide_pick(mode, threads, width) == nullptr) return 0;
+    const size_t off = (ring_smem + 127) / 128 * 128;
+    *drawn_offset = (uint32_t)off;
+    return off + (size_t)WIDE_CALLS * 16 * threads;
+}
+
+int32_t launch_gibbs_wide(const SweepParams &p, int mode, int threads, int groups, size_t smem, cudaStream_t st)
+{
+    wide_fn fn = wide_pick(mode, threads, p.width);
+    if (fn == nullptr) return fail(B200GRBM_EUNSUPPORTED, "gibbs_wide: no instantiation for threads=%d width=%d", threads, p.width);
+    B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    fn<<<groups, threads, smem, st>>>(p);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200grbm

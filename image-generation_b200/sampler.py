@@ -575,7 +575,7 @@ class BlockGibbsSampler:
         with torch.cuda.device(dev):
             _lib.check(lib.b200grbm_gibbs_sweeps(C.byref(a), _lib.current_stream(dev)))
             self.last_launches = lib.b200grbm_last_launch_count()
-            self.last_kernel = "small" if lib.b200grbm_last_sweep_kernel() == 1 else "packed"
+            self.last_kernel = {1: "small", 2: "wide"}.get(lib.b200grbm_last_sweep_kernel(), "packed")
             energies = None
             if samples is not None:
                 energies = out[1] if out is not None else torch.empty(num_reads, dtype=torch.float64, device=dev)

@@ -125,7 +125,8 @@ int32_t b200grbm_ex2_probe(float x_lo, float x_hi, int64_t n, double *max_rel_er
 int32_t b200grbm_last_launch_count(void);
 /* which sweep kernel that call chose: 0 = chains bit-packed per lane (throughput), 1 = one chain per lane column with
  * every round's table in registers (small problems: chains_per_lane == 4, <= 5 colour rounds of <= 256 spins,
- * degree <= 20, few enough chains for all CTAs to be resident at once) */
+ * degree <= 20, few enough chains for all CTAs to be resident at once), 2 = the specialised throughput kernel (28 chains
+ * per lane, compile-time CTA size and table width, pre-drawn uniforms behind a split round barrier; same results as 0) */
 int32_t b200grbm_last_sweep_kernel(void);
 
 /*
