@@ -430,6 +430,7 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
     p.sweep_offset = a->sweep_offset;
     p.chain_block0 = (uint32_t)(a->chain_offset >> 2);
     p.drawn_offset = 0;
+    p.hi43 = 0x43000000u;
     if (a->chains_per_lane <= 8 && a->ell_width % 4 != 0)
         return fail(B200GRBM_EINVAL, "gibbs_sweeps: chains_per_lane <= 8 consumes slots four at a time; ell_width=%d "
                                      "must be padded to a multiple of 4", a->ell_width);

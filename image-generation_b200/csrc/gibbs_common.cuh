@@ -29,6 +29,7 @@ struct SweepParams {
     uint32_t tile_bytes;    // (width + 1) * threads * 8
     uint32_t resident;      // 1: all n_tiles tiles fit in shared memory and are copied once (small graphs)
     uint32_t single;        // 1: one tile stage per CTA, two CTAs per SM cover each other's copy latency
+    uint32_t hi43;          // 0x43000000 (exponent of 128.0f): PRMT operand of the packed acceptance, kept out of the immediates
     uint32_t drawn_offset;  // byte offset of the pre-drawn Philox words [calls][threads] x 16 B (gibbs_kernel<.., PD = true>)
     uint32_t rk[2 * B200GRBM_PHILOX_ROUNDS];
 };

@@ -124,6 +124,70 @@ __device__ __noinline__ uint32_t fix_word_supplied(uint32_t neww, uint32_t unsur
     return neww;
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FMUL2 / FADD2 / FFMA2: one issue slot for two chains).  Each lane of a
+// packed op is the same correctly rounded IEEE operation as its scalar form, so results are unchanged; what is saved
+// is issue slots, the resource this kernel runs out of (the fma pipe takes two passes per packed op).
+__device__ __forceinline__ uint64_t pack2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// as_float(0x43000000 | halfword j of the call) = 128 + hw 2^-16.  `hi43` holds 0x43000000 in a REGISTER (PRMT takes one
+// immediate: with the constant as the immediate ptxas materialises the selector per use, one extra instruction per decision).
+__device__ __forceinline__ float uniform_big(const uint32_t (&r)[4], int j, uint32_t hi43)
+{
+    return u2f(__byte_perm(r[j >> 1], hi43, (j & 1) ? 0x7632u : 0x7610u));
+}
+
+struct Pair2Consts {
+    uint64_t coef2, one2, mone2, negc2;
+    uint32_t hi43;
+};
+
+// Two bracketed decisions (chains c_hi = c_lo + 1) with the shared steps in packed form; see decide_quick for the
+// arithmetic.  Returns d (sign bit = decision) and, if CHECK, the marks m of both chains.
+template <bool CHECK>
+__device__ __forceinline__ void decide_quick2(float f_lo, float f_hi, float big_lo, float big_hi, const Pair2Consts &k,
+                                              float &d_lo, float &d_hi, float &m_lo, float &m_hi)
+{
+    float x_lo, x_hi, e_lo, e_hi, g_lo, g_hi;
+    unpack2(mul2(pack2(f_lo, f_hi), k.coef2), x_lo, x_hi);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e_lo) : "f"(x_lo));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e_hi) : "f"(x_hi));
+    const uint64_t g2 = add2(pack2(e_lo, e_hi), k.one2);
+    const uint64_t vm2 = add2(pack2(big_lo, big_hi), k.negc2);
+    unpack2(fma2(vm2, g2, k.mone2), d_lo, d_hi);
+    if (CHECK) {
+        unpack2(g2, g_lo, g_hi);
+        m_lo = __fmaf_rn(g_lo, -B200GRBM_LAZY_K1, __fadd_rn(fabsf(d_lo), -B200GRBM_LAZY_K2));
+        m_hi = __fmaf_rn(g_hi, -B200GRBM_LAZY_K1, __fadd_rn(fabsf(d_hi), -B200GRBM_LAZY_K2));
+    }
+}
+
 // Decisions of one lane-task: the new state word of visit position pp for the CPL chains of the group.
 // Chains are taken in descending order so that one funnel shift per decision (sign bit of d into bit 0)
 // assembles the word.  SHIFT = (first global chain of the group) mod 8, in {0, 4}: Philox blocks hold 8 chains.
@@ -133,11 +197,15 @@ __device__ __noinline__ uint32_t fix_word_supplied(uint32_t neww, uint32_t unsur
 //
 // PD (throughput kernel, one CTA per SM): the words were drawn by this thread while it waited for the previous round's
 // stragglers (see the round barrier in gibbs_kernel) and sit in shared memory, call-major: drawn[call * stride].
-template <int CPL, int MODE, int SHIFT, bool PRE, bool PD = false>
+//
+// PACK2: the decisions are taken two chains at a time with packed fp32x2 arithmetic (decide_quick2); same results.
+template <int CPL, int MODE, int SHIFT, bool PRE, bool PD = false, bool PACK2 = false>
 __device__ __forceinline__ uint32_t decide_word(const float (&f)[CPL], float coef, uint32_t pp, uint32_t sweep,
                                                 uint32_t blk8, const SweepParams &p, int t, int chain0,
-                                                const uint32_t (&R)[2][4], const uint4 *drawn = nullptr, int stride = 0)
+                                                const uint32_t (&R)[2][4], const uint4 *drawn = nullptr, int stride = 0,
+                                                const Pair2Consts *k2 = nullptr)
 {
+    static_assert(!PACK2 || (MODE != MODE_SUPPLIED_EXACT && SHIFT % 2 == 0 && CPL % 2 == 0), "PACK2: Philox modes, even groups");
     constexpr int NC = (CPL + SHIFT + 7) / 8;
     static_assert(!PRE || NC <= 2, "pre-drawn Philox words: at most two calls per lane-task");
     constexpr bool CHECK = MODE != MODE_PHILOX_FAST;
@@ -163,12 +231,31 @@ __device__ __forceinline__ uint32_t decide_word(const float (&f)[CPL], float coe
             } else {
                 philox4x32(pp, blk8 + call, sweep, B200GRBM_STREAM_SWEEP, p, r);
             }
+            if constexpr (PACK2) {
 #pragma unroll
-            for (int j = 7; j >= 0; --j) {
-                const int c = 8 * call + j - SHIFT;
-                if (c < 0 || c >= CPL) continue;
-                if (CPL == 28 && (c + 1) % 7 == 0) neww <<= 1;
-                neww = __funnelshift_l(decide_quick<CHECK>(f[c], coef, uniform_midpoint(r, j), unsure), neww, 1);
+                for (int j = 7; j >= 1; j -= 2) {
+                    const int c = 8 * call + j - SHIFT;          // pair (c, c - 1): both inside the group or both outside
+                    if (c - 1 < 0 || c >= CPL) continue;
+                    float d_lo, d_hi, m_lo = 0.f, m_hi = 0.f;
+                    decide_quick2<CHECK>(f[c - 1], f[c], uniform_big(r, j - 1, k2->hi43), uniform_big(r, j, k2->hi43), *k2,
+                                         d_lo, d_hi, m_lo, m_hi);
+                    if (CPL == 28 && (c + 1) % 7 == 0) neww <<= 1;
+                    neww = __funnelshift_l(f2u(d_hi), neww, 1);
+                    if (CPL == 28 && c % 7 == 0) neww <<= 1;
+                    neww = __funnelshift_l(f2u(d_lo), neww, 1);
+                    if (CHECK) {
+                        unsure = __funnelshift_l(f2u(m_hi), unsure, 1);
+                        unsure = __funnelshift_l(f2u(m_lo), unsure, 1);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 7; j >= 0; --j) {
+                    const int c = 8 * call + j - SHIFT;
+                    if (c < 0 || c >= CPL) continue;
+                    if (CPL == 28 && (c + 1) % 7 == 0) neww <<= 1;
+                    neww = __funnelshift_l(decide_quick<CHECK>(f[c], coef, uniform_midpoint(r, j), unsure), neww, 1);
+                }
             }
         }
     }

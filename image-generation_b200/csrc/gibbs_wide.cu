@@ -19,6 +19,10 @@
 namespace b200grbm {
 
 constexpr int WIDE_CPL = 28;
+#ifndef B200_WIDE_PACK2
+#define B200_WIDE_PACK2 1
+#endif
+constexpr bool WIDE_PACK2 = B200_WIDE_PACK2 != 0;
 constexpr int WIDE_CALLS = 4;           // Philox calls per lane-task: (28 + shift) / 8 rounded up, shift in {0, 4}
 
 template <int MODE, int T, int W>
@@ -74,9 +78,16 @@ __global__ void __launch_bounds__(T, 1) gibbs_wide_kernel(const __grid_constant_
     };
     if (total > 0) draw_round(0u, p.sweep_offset);
 
+    Pair2Consts k2;
+    k2.one2 = pack2(1.0f, 1.0f);
+    k2.mone2 = pack2(-1.0f, -1.0f);
+    k2.negc2 = pack2(-(128.0f - 0x1.0p-17f), -(128.0f - 0x1.0p-17f));
+    k2.hi43 = p.hi43;                      // 0x43000000 from the parameter block: a register operand for PRMT
+
     uint32_t q = 0;
     for (int t = 0; t < p.num_sweeps; ++t) {
         const float coef = __ldg(p.coef + t);
+        k2.coef2 = pack2(coef, coef);
         const uint32_t sweep = p.sweep_offset + (uint32_t)t;
 #pragma unroll 1
         for (uint32_t tile = 0; tile < n_tiles; ++tile, ++q) {
@@ -118,8 +129,8 @@ __global__ void __launch_bounds__(T, 1) gibbs_wide_kernel(const __grid_constant_
                         if (k0 + i < W) add_slot<CPL>(f, w[i], u2f(e[i].x));
                 }
                 const uint32_t R0[2][4] = {};
-                Wst[pp] = shift4 ? decide_word<CPL, MODE, 4, false, true>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R0, drawn, T)
-                                 : decide_word<CPL, MODE, 0, false, true>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R0, drawn, T);
+                Wst[pp] = shift4 ? decide_word<CPL, MODE, 4, false, true, WIDE_PACK2>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R0, drawn, T, &k2)
+                                 : decide_word<CPL, MODE, 0, false, true, WIDE_PACK2>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R0, drawn, T, &k2);
             }
             // split round barrier: arrive (release: this warp's words are visible), draw, wait (acquire)
             __syncwarp();
