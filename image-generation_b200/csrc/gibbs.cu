@@ -91,6 +91,14 @@ __global__ void __launch_bounds__(MAXT, 1) gibbs_kernel(const __grid_constant__ 
     load_group_state<CPL>(p, W, tid, nthr, g, chain0, nvalid, dense_mask, blk0);
     __syncthreads();
 
+    // throughput groups (>= 16 chains per lane, Philox modes): decisions two chains at a time in packed fp32x2
+    constexpr bool PACK2 = CPL >= 16 && MODE != MODE_SUPPLIED_EXACT;
+    Pair2Consts k2;
+    k2.one2 = pack2(1.0f, 1.0f);
+    k2.mone2 = pack2(-1.0f, -1.0f);
+    k2.negc2 = pack2(-(128.0f - 0x1.0p-17f), -(128.0f - 0x1.0p-17f));
+    k2.hi43 = p.hi43;
+
     int tile = 0, t = 0;
     float coef = total_tiles > 0 ? __ldg(p.coef) : 0.f;
     float coef_next = p.num_sweeps > 1 ? __ldg(p.coef + 1) : 0.f;   // one sweep ahead: never waited on
@@ -131,6 +139,7 @@ __global__ void __launch_bounds__(MAXT, 1) gibbs_kernel(const __grid_constant__ 
         if (tid < info.y) {
             const int pp = info.x + tid;
             const uint32_t sweep = p.sweep_offset + (uint32_t)t;
+            k2.coef2 = pack2(coef, coef);
             // tile rows: 0 = f0, 1 .. width = neighbour slots {2J bits, byte offset of the neighbour's state word}
             const uint2 *ep = reinterpret_cast<const uint2 *>(stage0 + stage_idx * p.tile_bytes) + tid;
             float f[CPL];
@@ -222,8 +231,8 @@ __global__ void __launch_bounds__(MAXT, 1) gibbs_kernel(const __grid_constant__ 
                 W[pp] = acc & 0x7f7f7f7fu;
             }
 #else
-            W[pp] = shift4 ? decide_word<CPL, MODE, 4, PRE>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R)
-                           : decide_word<CPL, MODE, 0, PRE>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R);
+            W[pp] = shift4 ? decide_word<CPL, MODE, 4, PRE, false, PACK2>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R, nullptr, 0, &k2)
+                           : decide_word<CPL, MODE, 0, PRE, false, PACK2>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R, nullptr, 0, &k2);
 #endif
             // bits of chains beyond nvalid are masked at write-back
         }
@@ -331,7 +340,7 @@ static thread_local int32_t g_last_launches = 0;
 static thread_local int32_t g_last_kernel = 0;     // 0 = gibbs_kernel (chains bit-packed per lane), 1 = gibbs_small_kernel, 2 = gibbs_wide_kernel
 
 // gibbs_wide.cu
-size_t wide_kernel_smem(int cpl, int mode, int threads, int width, size_t ring_smem, uint32_t *drawn_offset);
+size_t wide_kernel_smem(int cpl, int mode, int threads, int width, bool single, size_t ring_smem, uint32_t *drawn_offset);
 int32_t launch_gibbs_wide(const SweepParams &p, int mode, int threads, int groups, size_t smem, cudaStream_t st);
 
 // gibbs_small.cu
@@ -488,9 +497,10 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
     // throughput geometry (28 chains per lane, one CTA per SM, tile ring, known CTA size and width): the specialised
     // kernel of gibbs_wide.cu.  B200GRBM_WIDE=0 keeps the generic kernel (same results).
     const char *wide_env = getenv("B200GRBM_WIDE");
-    const size_t smem_wide = (p.resident || p.single || (wide_env != nullptr && wide_env[0] == '0') ||
+    const size_t smem_wide = (p.resident || (wide_env != nullptr && wide_env[0] == '0') ||
                               (long long)a->num_sweeps * a->n_tiles >= (1ll << 31))
-                                 ? 0 : wide_kernel_smem(a->chains_per_lane, mode, a->threads, a->ell_width, smem, &p.drawn_offset);
+                                 ? 0 : wide_kernel_smem(a->chains_per_lane, mode, a->threads, a->ell_width, p.single != 0, smem,
+                                                        &p.drawn_offset);
     g_last_kernel = 0;
     if (smem_wide > 0 && smem_wide <= (size_t)smem_optin) {
         B200_TRY(launch_gibbs_wide(p, mode, a->threads, groups, smem_wide, (cudaStream_t)stream));

@@ -25,9 +25,14 @@ constexpr int WIDE_CPL = 28;
 constexpr bool WIDE_PACK2 = B200_WIDE_PACK2 != 0;
 constexpr int WIDE_CALLS = 4;           // Philox calls per lane-task: (28 + shift) / 8 rounded up, shift in {0, 4}
 
-template <int MODE, int T, int W>
-__global__ void __launch_bounds__(T, 1) gibbs_wide_kernel(const __grid_constant__ SweepParams p)
+//
+// SINGLE = the two-CTAs-per-SM form (Zephyr Z15: 2 x 384 threads): ONE tile stage per CTA, refilled at the top of each
+// round while the SM's other CTA computes; that other CTA also fills this one's barrier waits, so the round barrier
+// stays a __syncthreads() and the uniforms are drawn in place (no room for the slots next to two CTAs' tables anyway).
+template <int MODE, int T, int W, bool SINGLE>
+__global__ void __launch_bounds__(T, SINGLE ? 2 : 1) gibbs_wide_kernel(const __grid_constant__ SweepParams p)
 {
+    constexpr bool PD = !SINGLE;
     constexpr int CPL = WIDE_CPL;
     constexpr uint32_t TILE_BYTES = (uint32_t)(W + 1) * T * 8u;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -53,7 +58,7 @@ __global__ void __launch_bounds__(T, 1) gibbs_wide_kernel(const __grid_constant_
     if (tid == 0) {
         mbar_init(bar_addr, 1);
         mbar_init(bar_addr + 8, 1);
-        mbar_init(bar_addr + 16, T / 32);                                      // one arrival per warp
+        if (PD) mbar_init(bar_addr + 16, T / 32);                              // round barrier: one arrival per warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (total > 0) {
             mbar_expect_tx(bar_addr, TILE_BYTES);
@@ -76,7 +81,7 @@ __global__ void __launch_bounds__(T, 1) gibbs_wide_kernel(const __grid_constant_
             }
         }
     };
-    if (total > 0) draw_round(0u, p.sweep_offset);
+    if (PD && total > 0) draw_round(0u, p.sweep_offset);
 
     Pair2Consts k2;
     k2.one2 = pack2(1.0f, 1.0f);
@@ -95,19 +100,26 @@ __global__ void __launch_bounds__(T, 1) gibbs_wide_kernel(const __grid_constant_
             const bool more = q + 1 < total;
             const uint32_t tile_next = tile + 1 == n_tiles ? 0u : tile + 1;
             // stage s^1 was last read in round q-1; this thread has seen round q-1's barrier complete
-            if (tid == 0 && more) {
+            if (SINGLE) {
+                if (tid == 0 && q > 0) {
+                    mbar_expect_tx(bar_addr, TILE_BYTES);
+                    bulk_g2s(stage_addr, reinterpret_cast<const unsigned char *>(p.tiles) + (size_t)tile * TILE_BYTES, TILE_BYTES,
+                             bar_addr);
+                }
+            } else if (tid == 0 && more) {
                 const uint32_t nb = bar_addr + 8u * (s ^ 1u);
                 mbar_expect_tx(nb, TILE_BYTES);
                 bulk_g2s(stage_addr + (s ^ 1u) * TILE_BYTES,
                          reinterpret_cast<const unsigned char *>(p.tiles) + (size_t)tile_next * TILE_BYTES, TILE_BYTES, nb);
             }
             const int2 info = tinfo[tile];
-            mbar_wait(bar_addr + 8u * s, (q >> 1) & 1u);
+            if (SINGLE) mbar_wait(bar_addr, q & 1u);
+            else mbar_wait(bar_addr + 8u * s, (q >> 1) & 1u);
 
             if (tid < info.y) {
                 const int pp = info.x + tid;
                 // tile rows: 0 = f0, 1 .. W = neighbour slots {2J bits, byte offset of the neighbour's state word}
-                const uint2 *ep = reinterpret_cast<const uint2 *>(stage0 + s * TILE_BYTES) + tid;
+                const uint2 *ep = reinterpret_cast<const uint2 *>(stage0 + (SINGLE ? 0u : s * TILE_BYTES)) + tid;
                 float f[CPL];
                 {
                     const float fz = u2f(ep[0].x);
@@ -129,14 +141,18 @@ __global__ void __launch_bounds__(T, 1) gibbs_wide_kernel(const __grid_constant_
                         if (k0 + i < W) add_slot<CPL>(f, w[i], u2f(e[i].x));
                 }
                 const uint32_t R0[2][4] = {};
-                Wst[pp] = shift4 ? decide_word<CPL, MODE, 4, false, true, WIDE_PACK2>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R0, drawn, T, &k2)
-                                 : decide_word<CPL, MODE, 0, false, true, WIDE_PACK2>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R0, drawn, T, &k2);
+                Wst[pp] = shift4 ? decide_word<CPL, MODE, 4, false, PD, WIDE_PACK2>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R0, drawn, T, &k2)
+                                 : decide_word<CPL, MODE, 0, false, PD, WIDE_PACK2>(f, coef, (uint32_t)pp, sweep, blk8, p, t, chain0, R0, drawn, T, &k2);
             }
             // split round barrier: arrive (release: this warp's words are visible), draw, wait (acquire)
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(bar_addr + 16);
-            if (more) draw_round(tile_next, tile + 1 == n_tiles ? sweep + 1u : sweep);
-            mbar_wait(bar_addr + 16, q & 1u);
+            if constexpr (PD) {
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(bar_addr + 16);
+                if (more) draw_round(tile_next, tile + 1 == n_tiles ? sweep + 1u : sweep);
+                mbar_wait(bar_addr + 16, q & 1u);
+            } else {
+                __syncthreads();
+            }
         }
     }
 
@@ -145,24 +161,27 @@ __global__ void __launch_bounds__(T, 1) gibbs_wide_kernel(const __grid_constant_
 
 typedef void (*wide_fn)(const SweepParams);
 
-template <int T, int W>
+template <int T, int W, bool SINGLE>
 static wide_fn wide_pick_mode(int mode)
 {
-    return mode == MODE_PHILOX_FAST ? gibbs_wide_kernel<MODE_PHILOX_FAST, T, W> : gibbs_wide_kernel<MODE_PHILOX_EXACT, T, W>;
+    return mode == MODE_PHILOX_FAST ? gibbs_wide_kernel<MODE_PHILOX_FAST, T, W, SINGLE>
+                                    : gibbs_wide_kernel<MODE_PHILOX_EXACT, T, W, SINGLE>;
 }
 
-static wide_fn wide_pick(int mode, int threads, int width)
+static wide_fn wide_pick(int mode, int threads, int width, bool single)
 {
     if (mode != MODE_PHILOX_EXACT && mode != MODE_PHILOX_FAST) return nullptr;
-    if (threads == 640 && width == 15) return wide_pick_mode<640, 15>(mode);       // Pegasus (P16: 9 rounds of 640 lanes)
+    if (!single && threads == 640 && width == 15) return wide_pick_mode<640, 15, false>(mode);   // Pegasus P16: 9 rounds of 640 lanes
+    if (single && threads == 384 && width == 20) return wide_pick_mode<384, 20, true>(mode);     // Zephyr Z15: 20 rounds, 2 CTAs per SM
     return nullptr;
 }
 
-// shared-memory bytes of the specialised kernel (0: no instantiation for this geometry): the generic 2-stage layout
-// plus the pre-drawn words behind it
-size_t wide_kernel_smem(int cpl, int mode, int threads, int width, size_t ring_smem, uint32_t *drawn_offset)
+// shared-memory bytes of the specialised kernel (0: no instantiation for this geometry): the generic layout, plus -- in
+// the one-CTA-per-SM form -- the pre-drawn words behind it
+size_t wide_kernel_smem(int cpl, int mode, int threads, int width, bool single, size_t ring_smem, uint32_t *drawn_offset)
 {
-    if (cpl != WIDE_CPL || wide_pick(mode, threads, width) == nullptr) return 0;
+    if (cpl != WIDE_CPL || wide_pick(mode, threads, width, single) == nullptr) return 0;
+    if (single) return ring_smem;           // the launcher's one-stage size; nothing behind it
     const size_t off = (ring_smem + 127) / 128 * 128;
     *drawn_offset = (uint32_t)off;
     return off + (size_t)WIDE_CALLS * 16 * threads;
@@ -170,7 +189,7 @@ size_t wide_kernel_smem(int cpl, int mode, int threads, int width, size_t ring_s
 
 int32_t launch_gibbs_wide(const SweepParams &p, int mode, int threads, int groups, size_t smem, cudaStream_t st)
 {
-    wide_fn fn = wide_pick(mode, threads, p.width);
+    wide_fn fn = wide_pick(mode, threads, p.width, p.single != 0);
     if (fn == nullptr) return fail(B200GRBM_EUNSUPPORTED, "gibbs_wide: no instantiation for threads=%d width=%d", threads, p.width);
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -226,7 +226,7 @@ def test_full_size_cfg2_shape_bit_exact_on_sampled_chains(cuda_device):
     beta = np.geomspace(0.1, 1.0, sweeps)
     s = B.BlockGibbsSampler(g, device=cuda_device)
     got = s.sample_ising(h, J, num_reads=chains, beta_schedule=beta, seed=seed).record.sample
-    assert s.last_plan[0] == 28
+    assert s.last_plan[0] == 28 and s.last_kernel == "wide"      # the specialised throughput kernel (csrc/gibbs_wide.cu)
     csr = _oracle_csr(g)
     for block in (0, 27, 28, 1000, 4092):                   # includes a CTA boundary (28) and the ragged tail
         want = O.gibbs(csr, h, J, O.init_state(csr, 4, seed, chain_offset=block), beta, seed=seed, chain_offset=block)
@@ -392,6 +392,7 @@ def test_full_size_cfg4_shard_properties(cuda_device):
     s = B.BlockGibbsSampler(g, device=cuda_device)
     ss = s.sample_ising(h, J, num_reads=chains, num_sweeps=sweeps, seed=seed)
     x = ss.samples_tensor
+    assert s.last_kernel == "wide" and s.last_plan == (28, 384)   # two-CTAs-per-SM form of csrc/gibbs_wide.cu
     csr = _oracle_csr(g)
     for block in (0, 28 * 500, 32764):
         want = O.gibbs(csr, h, J, O.init_state(csr, 4, seed, chain_offset=block), [1.0] * sweeps, seed=seed, chain_offset=block)
@@ -411,6 +412,27 @@ def test_full_size_cfg4_shard_properties(cuda_device):
         xs = sh.sample_ising(h, J, num_reads=cnt, num_sweeps=sweeps, seed=seed).samples_tensor
         parts.append(edge_statistics(pack_spins(xs, sh.device_graph), cnt, sh.device_graph))
     assert torch.equal(parts[0][0] + parts[1][0], s1) and torch.equal(parts[0][1] + parts[1][1], s2)
+
+
+@pytest.mark.parametrize("graph,chains", [("p16", 4096), ("p16", 4000), ("z15", 8400)])
+@pytest.mark.parametrize("accept", ["exact", "fast"])
+def test_specialised_throughput_kernel_equals_generic_kernel(cuda_device, monkeypatch, graph, chains, accept):
+    """gibbs_wide_kernel (compile-time geometry, pre-drawn uniforms behind a split round barrier, packed fp32x2
+    acceptance) against gibbs_kernel<28> on the same launch: identical samples and energies in both acceptance modes,
+    annealed schedule, ragged last group, a shard that starts inside a Philox block."""
+    g = B.IsingGraph.pegasus(16) if graph == "p16" else B.IsingGraph.zephyr(15)
+    rng = np.random.default_rng(21)
+    h = (0.05 * rng.uniform(-0.5, 0.5, g.n)).astype(np.float32)
+    J = (0.05 * rng.uniform(-5, 5, g.n_edges)).astype(np.float32)
+    beta = np.geomspace(0.2, 3.0, 5)
+    out = {}
+    for wide in ("1", "0"):
+        monkeypatch.setenv("B200GRBM_WIDE", wide)
+        s = B.BlockGibbsSampler(g, device=cuda_device, accept=accept, chain_offset=4)
+        ss = s.sample_ising(h, J, num_reads=chains, beta_schedule=beta, seed=77)
+        out[wide] = (ss.record.sample.copy(), ss.record.energy.copy(), s.last_kernel)
+    assert out["1"][2] == "wide" and out["0"][2] == "packed"
+    assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
 
 
 # ------------------------------------------------------------------ one-chain-per-lane kernel (small problems)
