@@ -16,7 +16,7 @@ the N + E int64 counters.
 `value`  : device-resident throughput (h/J and state in HBM; CUDA events, max over ranks).
 `e2e`    : the same metric through the reference-facing call sampler.sample_ising(h, J, num_reads, ...)
            with HOST h/J arrays in and HOST samples out (pinned H2D + D2H inside the timed region).
-`roofline`: dominant kernel b200grbm::gibbs_kernel.  SURVEY.md section 8(d): the sweep is not HBM bound (one
+`roofline`: dominant kernel b200grbm::gibbs_wide_kernel (csrc/gibbs_wide.cu; gibbs_kernel for other geometries).  SURVEY.md section 8(d): the sweep is not HBM bound (one
            state read + write per launch); algorithmic bytes are (mean degree + 1) per update against the
            shared-memory roof n_SM x 128 B/clk x f_SM; the HBM view is reported next to it.
 `cpu_baseline`: the oracle port's textbook double-precision sequential heat bath on the box's host cores (N = 1 only).
@@ -161,7 +161,7 @@ def run_reference(args):
 def _load_profile_metrics():
     """ncu-derived constants of the dominant kernel, written by tools/ncu_summary.py --json from the committed capture
     (never literals in this file)."""
-    for name in ("r2_gibbs_ncu_metrics.json", "r1_gibbs_v5_ncu_metrics.json"):
+    for name in ("r2_gibbs_wide_ncu_metrics.json", "r2_gibbs_ncu_metrics.json", "r1_gibbs_v5_ncu_metrics.json"):
         path = os.path.join(ROOT, "profiles", name)
         if os.path.exists(path):
             try:
@@ -256,6 +256,8 @@ def run_b200(args):
     updates_per_step = chains * sweeps * g.n * world
     value = updates_per_step * args.steps / total_s
     timed_plan = sampler.last_plan
+    timed_kernel = {"wide": "b200grbm::gibbs_wide_kernel", "small": "b200grbm::gibbs_small_kernel"}.get(
+        sampler.last_kernel, "b200grbm::gibbs_kernel")
 
     # ---- end to end through the reference-facing call, host buffers in and out
     h_pin, J_pin = torch.from_numpy(h).pin_memory(), torch.from_numpy(J).pin_memory()
@@ -314,7 +316,7 @@ def run_b200(args):
     hbm_bytes = 2.0 * chains * g.n                      # int8 state written once (+ read when resuming chains)
     prof = _load_profile_metrics()
     roofline = {
-        "bound": "smem", "kernel": "b200grbm::gibbs_kernel", "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
+        "bound": "smem", "kernel": timed_kernel, "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
         "frac": achieved / smem_peak,
         "traffic": None, "algorithmic_bytes_per_update": P16_MEAN_DEGREE + 1.0, "updates_per_launch": upd_per_launch,
         "kernel_ms": kernel_s * 1e3,

@@ -17,13 +17,13 @@ case "${1:-all}" in
       python bench.py --steps 2 --warmup 3 --sweeps 100 --cpu-seconds 1 > gpurun_out/ncu_launch.log 2>&1 ;;&
   ncu|all)
     # dominant kernel: P16, 4096 chains, 20 sweeps (updates in capture = 4096 * 20 * 5640)
-    timeout 600 $NCU -k regex:gibbs_kernel -s 1 -c 1 -o gpurun_out/gibbs -f \
+    timeout 600 $NCU -k regex:gibbs_wide -s 1 -c 1 -o gpurun_out/gibbs_wide -f \
       python bench.py --steps 1 --warmup 3 --sweeps 20 --cpu-seconds 1 --skip-extra > gpurun_out/ncu_gibbs.log 2>&1
     # the reference's default call on the one-chain-per-lane kernel
     timeout 300 $NCU -k regex:gibbs_small -s 1 -c 1 -o gpurun_out/gibbs_small -f \
       python tools/bench_configs.py --graph cfg1 --chains 256 --sweeps 200 > gpurun_out/ncu_small.log 2>&1
     # Zephyr Z15 shard: one tile stage, two CTAs per SM; and the packed energy kernel behind it
-    timeout 300 $NCU -k regex:gibbs_kernel -s 1 -c 1 -o gpurun_out/gibbs_z15 -f \
+    timeout 300 $NCU -k regex:gibbs_wide -s 1 -c 1 -o gpurun_out/gibbs_z15 -f \
       python tools/bench_configs.py --graph z15 --chains 32768 --sweeps 10 > gpurun_out/ncu_z15.log 2>&1
     timeout 300 $NCU -k regex:energy_packed -s 1 -c 1 -o gpurun_out/energy_packed -f \
       python tools/bench_configs.py --graph z15 --chains 32768 --sweeps 10 > gpurun_out/ncu_energy.log 2>&1
@@ -41,6 +41,6 @@ case "${1:-all}" in
     timeout 200 python tools/bench_configs.py --graph cfg1 --chains 256 --sweeps 1000 ;;
 esac
 # then, on the build box (r2 = this round):
-#   python tools/ncu_summary.py gpurun_out/gibbs.ncu-rep profiles/r2_gibbs_ncu_summary.txt --json profiles/r2_gibbs_ncu_metrics.json --updates 462028800
+#   python tools/ncu_summary.py gpurun_out/gibbs_wide.ncu-rep profiles/r2_gibbs_wide_ncu_summary.txt --json profiles/r2_gibbs_wide_ncu_metrics.json --updates 462028800
 #   python tools/ncu_summary.py gpurun_out/<x>.ncu-rep profiles/r2_<x>_ncu_summary.txt
 #   python tools/sass_histogram.py > profiles/r2_sass_opcode_histogram.txt
