@@ -29,6 +29,9 @@ constexpr int WIDE_CALLS = 4;           // Philox calls per lane-task: (28 + shi
 // SINGLE = the two-CTAs-per-SM form (Zephyr Z15: 2 x 384 threads): ONE tile stage per CTA, refilled at the top of each
 // round while the SM's other CTA computes; that other CTA also fills this one's barrier waits, so the round barrier
 // stays a __syncthreads() and the uniforms are drawn in place (no room for the slots next to two CTAs' tables anyway).
+// (Tried: the tile copy split into three chunks with a barrier each -- rows of slot 0 and the first batch, then one
+// chunk per further batch -- so that a round starts after a third of the copy: 36.3 -> 39.3 ms on the Z15 shard, the
+// extra waits and smaller copies cost more than the earlier start saves.)
 template <int MODE, int T, int W, bool SINGLE>
 __global__ void __launch_bounds__(T, SINGLE ? 2 : 1) gibbs_wide_kernel(const __grid_constant__ SweepParams p)
 {
@@ -58,7 +61,11 @@ __global__ void __launch_bounds__(T, SINGLE ? 2 : 1) gibbs_wide_kernel(const __g
     if (tid == 0) {
         mbar_init(bar_addr, 1);
         mbar_init(bar_addr + 8, 1);
-        if (PD) mbar_init(bar_addr + 16, T / 32);                              // round barrier: one arrival per warp
+#ifdef B200_WIDE_ARRIVE_ALL     // sanitizer build: every thread arrives itself (racecheck does not follow __syncwarp + lane 0)
+        if (PD) mbar_init(bar_addr + 16, T);
+#else
+        if (PD) mbar_init(bar_addr + 16, T / 32);         // round barrier: one arrival per warp
+#endif
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (total > 0) {
             mbar_expect_tx(bar_addr, TILE_BYTES);
@@ -146,8 +153,12 @@ __global__ void __launch_bounds__(T, SINGLE ? 2 : 1) gibbs_wide_kernel(const __g
             }
             // split round barrier: arrive (release: this warp's words are visible), draw, wait (acquire)
             if constexpr (PD) {
+#ifdef B200_WIDE_ARRIVE_ALL
+                mbar_arrive(bar_addr + 16);
+#else
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(bar_addr + 16);
+#endif
                 if (more) draw_round(tile_next, tile + 1 == n_tiles ? sweep + 1u : sweep);
                 mbar_wait(bar_addr + 16, q & 1u);
             } else {
