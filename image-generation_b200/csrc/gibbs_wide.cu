@@ -184,6 +184,7 @@ static wide_fn wide_pick(int mode, int threads, int width, bool single)
     if (mode != MODE_PHILOX_EXACT && mode != MODE_PHILOX_FAST) return nullptr;
     if (!single && threads == 640 && width == 15) return wide_pick_mode<640, 15, false>(mode);   // Pegasus P16: 9 rounds of 640 lanes
     if (single && threads == 384 && width == 20) return wide_pick_mode<384, 20, true>(mode);     // Zephyr Z15: 20 rounds, 2 CTAs per SM
+    if (!single && threads == 480 && width == 20) return wide_pick_mode<480, 20, false>(mode);   // Zephyr Z15, < 296 groups: 16 rounds
     return nullptr;
 }
 
