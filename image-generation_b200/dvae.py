@@ -52,11 +52,33 @@ def _down_stack(widths) -> nn.Sequential:
     return nn.Sequential(*mods[:-1])          # no activation after the last block
 
 
+class _NearestUp2x(torch.autograd.Function):
+    """``nn.Upsample(scale_factor=2)`` (nearest) with its gradient written as a 2x2 sum pooling.  Same values; the stock
+    ``upsample_nearest2d_backward`` kernel takes 0.8 ms per call on the decoder's (1024, C, H, W) activations -- four calls
+    were 42 % of the GPU time of a training step (torch.profiler on a B200) -- a pooling kernel takes ~20 us."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return torch.nn.functional.interpolate(x, scale_factor=2, mode="nearest")
+
+    @staticmethod
+    def backward(ctx, g):
+        return torch.nn.functional.avg_pool2d(g, 2, divisor_override=1)
+
+
+class Upsample2x(nn.Module):
+    """Parameter-free stand-in for ``nn.Upsample(scale_factor=2)`` at the same position of the decoder stack
+    (state-dict keys are positional, so the reference's ``dvae.pth`` loads unchanged)."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return _NearestUp2x.apply(x)
+
+
 def _up_stack(widths) -> nn.Sequential:
     mods = []
     for cin, cout in zip(widths[:-1], widths[1:]):
         mods += [nn.ConvTranspose2d(cin, cout, 3, padding=1), nn.BatchNorm2d(cout), nn.Dropout2d(0.2),
-                 nn.Upsample(scale_factor=2), nn.LeakyReLU()]
+                 Upsample2x(), nn.LeakyReLU()]
     mods.append(nn.ConvTranspose2d(widths[-1], widths[-1], 3, padding=1))
     return nn.Sequential(*mods)
 
@@ -191,9 +213,9 @@ class HybridDVAE:
         self.sampler_kwargs = dict(num_reads=self.NUM_READS, answer_mode="raw", auto_scale=False,
                                    annealing_time=self.ANNEALING_TIME, label="Examples - ML MNIST Image Gen")
         self._dvae_optimizer = torch.optim.Adam(self._dvae.parameters(), lr=self.AUTOENCODER_INITIAL_LR,
-                                                weight_decay=self.AUTOENCODER_WEIGHT_DECAY)
+                                                weight_decay=self.AUTOENCODER_WEIGHT_DECAY, fused=self.device.type == "cuda")
         self._grbm_optimizer = torch.optim.Adam(self._grbm.parameters(), lr=self.BM_INITIAL_LR,
-                                                weight_decay=self.BM_WEIGHT_DECAY)
+                                                weight_decay=self.BM_WEIGHT_DECAY, fused=self.device.type == "cuda")
 
     def train_init(self, n_epochs: int, n_batches: int) -> None:
         self._prefetched = None
@@ -330,7 +352,7 @@ class HybridDVAE:
         self._chains = None
         # a checkpoint with another edge count replaces the parameter objects: rebind the optimizer to them
         self._grbm_optimizer = torch.optim.Adam(self._grbm.parameters(), lr=self.BM_INITIAL_LR,
-                                                weight_decay=self.BM_WEIGHT_DECAY)
+                                                weight_decay=self.BM_WEIGHT_DECAY, fused=self.device.type == "cuda")
 
     def state_dicts(self) -> dict:
         """``{"dvae.pth": ..., "grbm.pth": ...}`` with the reference's key layout (src/model_wrapper.py:148-162)."""
