@@ -14,6 +14,18 @@
 //     of the kernel's time, and independent of the state -- waited behind it.  Here the round barrier is an mbarrier
 //     used in two halves: a warp ARRIVES when its spins of round q are written, draws the uniforms of its round-q+1
 //     lane-tasks into a per-thread shared-memory slot (4 calls x 16 bytes), and only then WAITS for the stragglers.
+//
+// Measured and dropped on top of this version (P16, 4096 chains x 1000 sweeps, 28.2-28.3 ms; source-level ncu shows the
+// neighbour / decision / draw phases at 5.1-5.4 cycles per warp instruction with five warps per scheduler, i.e. at the
+// issue limit, the remaining 20 % being the ~46-instruction round prologue at 9 cycles per instruction and the wait for
+// the round's slowest warp):
+//   * neighbour slots fetched 4, 5 or 14 at a time instead of 7: 28.15-28.19 ms, no difference;
+//   * two rounds per loop iteration so that the tile stage (hence every table address and barrier parity) is a
+//     compile-time constant: the executed loop body doubles to ~35 KB of SASS, past the instruction cache's comfortable
+//     size: 28.56 ms;
+//   * round geometry carried in registers, parities toggled instead of derived from the round counter (fewer prologue
+//     instructions): 28.29 ms on P16, Z15 36.3 -> 36.6 ms -- the prologue's cost is latency after the barrier, not
+//     instruction count.
 #include "gibbs_packed.cuh"
 
 namespace b200grbm {
