@@ -1,3 +1,5 @@
+"""torch.profiler view of one DVAE+GRBM training step (BASELINE.json configs[0]) on a B200: wall time per step, top CPU ops, top CUDA kernels.
+This is how the stock upsample_nearest2d_backward kernel was found to be 42 % of the step (image-generation_b200/dvae.py, Upsample2x)."""
 import os, sys, time
 sys.path.insert(0, ".")
 import numpy as np, torch
