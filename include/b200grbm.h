@@ -104,6 +104,14 @@ typedef struct b200grbm_sweep_args {
  * sampler.sample_ising(h, J, num_reads=chains, ...) -- the call GraphRestrictedBoltzmannMachine
  * .sample makes (boundary: src/utils/common.py:123-138 builds the sampler and its kwargs).
  * Runs num_sweeps colour-blocked heat-bath sweeps on `chains` independent chains.
+ *
+ * Kernel choice (results are identical whichever runs; b200grbm_last_sweep_kernel tells which did):
+ *   chains_per_lane == 4 and a small graph (<= 5 rounds of <= 256 spins, degree <= 20)  -> gibbs_small_kernel
+ *   chains_per_lane == 28, Philox uniforms, and (threads, ell_width) one of (640, 15) [Pegasus P16], (480, 20) [Zephyr,
+ *     one CTA per SM], (384, 20) with >= 2 groups per SM [Zephyr, two CTAs per SM]                 -> gibbs_wide_kernel
+ *   anything else                                                                                  -> gibbs_kernel
+ * Environment switches for A/B measurements and the parity tests of the variants: B200GRBM_SMALL=0, B200GRBM_WIDE=0
+ * (fall back to gibbs_kernel), B200GRBM_MMD_TILE=1|2, B200GRBM_GEMM_TILE=1|2 (single-CTA / CTA-pair tensor-core kernels).
  */
 int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *args, void *stream);
 
