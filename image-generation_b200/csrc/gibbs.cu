@@ -42,6 +42,7 @@
 //     The result is bit-identical to evaluating the contract everywhere (oracle/oracle.c).
 #include "gibbs_packed.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -50,20 +51,30 @@ namespace b200grbm {
 // MAXT = largest CTA this instantiation may be launched with.  768 caps ptxas at 80 registers per thread (and is the
 // one two 384-thread CTAs per SM need); the 28-chain kernels also exist for MAXT = 640 -- 96 registers, a looser
 // schedule of the acceptance phase: 32.8 -> 32.0 ms on P16 (9 rounds of 640 lanes).
-template <int CPL, int MODE, int MAXT = 768>
+//
+// MG = several chain groups per CTA (resident tables only; see below).  A template parameter because the group barriers
+// are named barriers with a run-time id: such a kernel reserves all 16 barriers of a CTA, which would cap the SM at two
+// CTAs in the modes that want more.
+template <int CPL, int MODE, int MAXT = 768, bool MG = false>
 __global__ void __launch_bounds__(MAXT, 1) gibbs_kernel(const __grid_constant__ SweepParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);                 // 2 mbarriers (16 B, padded to 128)
     int2 *tinfo = reinterpret_cast<int2 *>(smem_raw + 128);                  // round table, copied once
-    uint32_t *W = reinterpret_cast<uint32_t *>(smem_raw + 128 + p.info_bytes);
-    unsigned char *stage0 = smem_raw + 128 + p.info_bytes + p.state_bytes;
+    // Small graphs with many chain groups (the reference's 256-latent model scaled up in chains, BASELINE configs[4]):
+    // gpc > 1 groups share one CTA and ONE resident copy of the tables.  A group is tpg threads (a "sub-CTA" with its
+    // own state words and its own named barrier); with one group per CTA the 54 KB of tables per CTA cap the SM at
+    // four two-warp CTAs -- two warps per scheduler.
+    const int gi = MG ? (int)threadIdx.x / p.tpg : 0;                       // group within the CTA
+    const unsigned char *sbase = smem_raw + (size_t)gi * p.state_bytes;      // the tiles' .nbr offsets are relative to this
+    uint32_t *W = reinterpret_cast<uint32_t *>(smem_raw + 128 + p.info_bytes + (size_t)gi * p.state_bytes);
+    unsigned char *stage0 = smem_raw + 128 + p.info_bytes + (size_t)(MG ? p.gpc : 1) * p.state_bytes;
 
-    const int tid = threadIdx.x;
-    const int nthr = blockDim.x;
-    const int g = blockIdx.x;
+    const int tid = MG ? (int)threadIdx.x - gi * p.tpg : (int)threadIdx.x;
+    const int nthr = MG ? p.tpg : (int)blockDim.x;
+    const int g = MG ? (int)blockIdx.x * p.gpc + gi : (int)blockIdx.x;
     const int chain0 = g * CPL;  // first chain of this group, local to the call
-    const int nvalid = min(CPL, p.chains - chain0);
+    const int nvalid = max(0, min(CPL, p.chains - chain0));                  // 0: no such group (last CTA)
     const uint32_t dense_mask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
     const uint32_t blk0 = p.chain_block0 + (uint32_t)(chain0 >> 2);   // global chain / 4 (initial-state stream)
     const uint32_t blk8 = blk0 >> 1;                                   // global chain / 8 (sweep streams)
@@ -72,7 +83,7 @@ __global__ void __launch_bounds__(MAXT, 1) gibbs_kernel(const __grid_constant__ 
     const uint32_t stage_addr = smem_u32(stage0);
     const long long total_tiles = (long long)p.num_sweeps * p.n_tiles;
 
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         mbar_init(bar_addr, 1);
         mbar_init(bar_addr + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -86,10 +97,11 @@ __global__ void __launch_bounds__(MAXT, 1) gibbs_kernel(const __grid_constant__ 
             bulk_g2s(stage_addr, p.tiles, p.tile_bytes, bar_addr);
         }
     }
-    for (int k = tid; k < p.n_tiles; k += nthr) tinfo[k] = __ldg(p.tile_info + k);
+    for (int k = threadIdx.x; k < p.n_tiles; k += blockDim.x) tinfo[k] = __ldg(p.tile_info + k);
 
-    load_group_state<CPL>(p, W, tid, nthr, g, chain0, nvalid, dense_mask, blk0);
+    if (nvalid > 0) load_group_state<CPL>(p, W, tid, nthr, g, chain0, nvalid, dense_mask, blk0);
     __syncthreads();
+    if (nvalid == 0) return;               // padding group of the last CTA: no CTA-wide barrier after this point
 
     // throughput groups (>= 16 chains per lane, Philox modes): decisions two chains at a time in packed fp32x2
     constexpr bool PACK2 = CPL >= 16 && MODE != MODE_SUPPLIED_EXACT;
@@ -169,14 +181,14 @@ __global__ void __launch_bounds__(MAXT, 1) gibbs_kernel(const __grid_constant__ 
                     for (int i = 0; i < 8; ++i) e[i] = ep[i * nthr];
                     ep += 8 * nthr;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) w[i] = lds_word(smem_raw, e[i].y);
+                    for (int i = 0; i < 8; ++i) w[i] = lds_word(sbase, e[i].y);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) add_slot<CPL>(f, w[i], u2f(e[i].x));
                 }
                 if (k < p.width) {
                     const uint2 e0 = ep[0], e1 = ep[nthr], e2 = ep[2 * nthr], e3 = ep[3 * nthr];
-                    const uint32_t w0 = lds_word(smem_raw, e0.y), w1 = lds_word(smem_raw, e1.y),
-                                   w2 = lds_word(smem_raw, e2.y), w3 = lds_word(smem_raw, e3.y);
+                    const uint32_t w0 = lds_word(sbase, e0.y), w1 = lds_word(sbase, e1.y),
+                                   w2 = lds_word(sbase, e2.y), w3 = lds_word(sbase, e3.y);
                     add_slot<CPL>(f, w0, u2f(e0.x));
                     add_slot<CPL>(f, w1, u2f(e1.x));
                     add_slot<CPL>(f, w2, u2f(e2.x));
@@ -189,7 +201,7 @@ __global__ void __launch_bounds__(MAXT, 1) gibbs_kernel(const __grid_constant__ 
                 {
                     const uint2 e0 = *ep;
                     ep += nthr;
-                    init_slot<CPL>(f, lds_word(smem_raw, e0.y), fz, u2f(e0.x));
+                    init_slot<CPL>(f, lds_word(sbase, e0.y), fz, u2f(e0.x));
                 }
                 int k = 1;
 #ifdef B200_EXP_NOSLOTS      // timing experiment: acceptance phase only
@@ -202,7 +214,7 @@ __global__ void __launch_bounds__(MAXT, 1) gibbs_kernel(const __grid_constant__ 
                     for (int i = 0; i < 7; ++i) e[i] = ep[i * nthr];
                     ep += 7 * nthr;
 #pragma unroll
-                    for (int i = 0; i < 7; ++i) w[i] = lds_word(smem_raw, e[i].y);
+                    for (int i = 0; i < 7; ++i) w[i] = lds_word(sbase, e[i].y);
 #pragma unroll
                     for (int i = 0; i < 7; ++i) add_slot<CPL>(f, w[i], u2f(e[i].x));
                     k += 7;
@@ -213,13 +225,13 @@ __global__ void __launch_bounds__(MAXT, 1) gibbs_kernel(const __grid_constant__ 
                 for (; k + 1 < p.width; k += 2) {
                     const uint2 ea = ep[0], eb = ep[nthr];
                     ep += 2 * nthr;
-                    const uint32_t wa = lds_word(smem_raw, ea.y), wb = lds_word(smem_raw, eb.y);
+                    const uint32_t wa = lds_word(sbase, ea.y), wb = lds_word(sbase, eb.y);
                     add_slot<CPL>(f, wa, u2f(ea.x));
                     add_slot<CPL>(f, wb, u2f(eb.x));
                 }
                 if (k < p.width) {
                     const uint2 ea = *ep;
-                    add_slot<CPL>(f, lds_word(smem_raw, ea.y), u2f(ea.x));
+                    add_slot<CPL>(f, lds_word(sbase, ea.y), u2f(ea.x));
                 }
             }
 
@@ -237,7 +249,8 @@ __global__ void __launch_bounds__(MAXT, 1) gibbs_kernel(const __grid_constant__ 
             // bits of chains beyond nvalid are masked at write-back
         }
 #ifndef B200_EXP_NOBARRIER   // timing experiment only (tools/build_variant.sh): results are wrong without it
-        __syncthreads();
+        if constexpr (MG) group_bar_sync(1 + gi, nthr);  // the group's own named barrier (ids 1 .. 15)
+        else __syncthreads();
 #endif
         if (++tile == p.n_tiles) {
             tile = 0;
@@ -316,8 +329,11 @@ static gibbs_fn pick_mode(int mode)
     }
 }
 
-static gibbs_fn pick(int cpl, int mode, int threads, bool one_cta_per_sm)
+static gibbs_fn pick(int cpl, int mode, int threads, bool one_cta_per_sm, bool multi_group = false)
 {
+    if (multi_group)
+        return cpl != 28 || mode == MODE_SUPPLIED_EXACT ? nullptr
+               : (mode == MODE_PHILOX_FAST ? gibbs_kernel<28, MODE_PHILOX_FAST, 768, true> : gibbs_kernel<28, MODE_PHILOX_EXACT, 768, true>);
     if (cpl == 28 && threads <= 640 && one_cta_per_sm) {
         switch (mode) {
             case MODE_PHILOX_EXACT: return gibbs_kernel<28, MODE_PHILOX_EXACT, 640>;
@@ -439,6 +455,8 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
     p.sweep_offset = a->sweep_offset;
     p.chain_block0 = (uint32_t)(a->chain_offset >> 2);
     p.drawn_offset = 0;
+    p.gpc = 1;
+    p.tpg = a->threads;
     p.hi43 = 0x43000000u;
     if (a->chains_per_lane <= 8 && a->ell_width % 4 != 0)
         return fail(B200GRBM_EINVAL, "gibbs_sweeps: chains_per_lane <= 8 consumes slots four at a time; ell_width=%d "
@@ -477,6 +495,42 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
     p.resident = (a->n_tiles <= 2 || (smem_resident <= (size_t)smem_optin &&
                                       (size_t)a->n_tiles * p.tile_bytes < (1u << 20))) ? 1u : 0u;
     if (p.resident) smem = smem_resident;
+    // resident tables + many groups: several groups per CTA share the one copy of the tables (see the kernel)
+    const int groups_all = (a->chains + a->chains_per_lane - 1) / a->chains_per_lane;
+    p.gpc = 1;
+    p.tpg = a->threads;
+    if (p.resident && pick(a->chains_per_lane, mode, a->threads, false, true) != nullptr) {
+        const char *gpc_env = getenv("B200GRBM_GPC");
+        const int forced = gpc_env != nullptr ? atoi(gpc_env) : 0;
+        const int sms = sm_count() > 0 ? sm_count() : 148;
+        int smem_sm_all = 0;
+        B200_CUDA(cudaDeviceGetAttribute(&smem_sm_all, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        // cost model (relative time): whole waves of `per_sm` CTAs per SM plus a partial last wave; an SM with w resident
+        // warps runs at w / (w + 4.35) of its peak (fitted on the 256-spin graph: 131072 chains x 100 sweeps take 7.95 ms
+        // with one group per CTA = 8 warps per SM, 6.20 ms with four = 24 warps)
+        const double wpg = a->threads / 32.0;
+        const auto sm_time = [&](int ctas_on_sm, int gpc) {
+            const double w = ctas_on_sm * gpc * wpg;
+            return ctas_on_sm * gpc * (w + 4.35) / w;
+        };
+        double best = 1e300;
+        for (int gpc = 1; gpc <= 15 && gpc * a->threads <= 768; ++gpc) {
+            if (forced > 0 && gpc != forced) continue;
+            const size_t smem_cta = smem + (size_t)(gpc - 1) * p.state_bytes;
+            if (smem_cta > (size_t)smem_optin) break;
+            const int ctas = (groups_all + gpc - 1) / gpc;
+            int per_sm = (int)std::min<size_t>({(size_t)(65536 / (gpc * a->threads * 80)), (size_t)smem_sm_all / (smem_cta + 1024),
+                                                (size_t)(2048 / (gpc * a->threads)), (size_t)32});
+            if (per_sm < 1) per_sm = 1;
+            const int slots = sms * per_sm, full = ctas / slots, rem = ctas - full * slots;
+            const double time = full * sm_time(per_sm, gpc) + (rem > 0 ? sm_time((rem + sms - 1) / sms, gpc) : 0.0);
+            if (time < best * 0.98) {           // a larger CTA has to win by 2 %
+                best = time;
+                p.gpc = gpc;
+            }
+        }
+        smem += (size_t)(p.gpc - 1) * p.state_bytes;
+    }
     // many groups, narrow CTAs: ONE tile stage per CTA and two CTAs per SM -- twice the warps per scheduler, each
     // CTA's round barrier and copy latency covered by the other (Zephyr Z15: 2 x 384 threads instead of 1 x 480)
     const int groups = (a->chains + a->chains_per_lane - 1) / a->chains_per_lane;
@@ -506,10 +560,10 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
         B200_TRY(launch_gibbs_wide(p, mode, a->threads, groups, smem_wide, (cudaStream_t)stream));
         g_last_kernel = 2;
     } else {
-        gibbs_fn fn = pick(a->chains_per_lane, mode, a->threads, !p.single);
+        gibbs_fn fn = pick(a->chains_per_lane, mode, a->threads * p.gpc, !p.single && p.gpc == 1, p.gpc > 1);
         B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        fn<<<groups, a->threads, smem, (cudaStream_t)stream>>>(p);
+        fn<<<(groups + p.gpc - 1) / p.gpc, a->threads * p.gpc, smem, (cudaStream_t)stream>>>(p);
         B200_CUDA(cudaGetLastError());
     }
     g_last_launches = 1;

@@ -29,6 +29,7 @@ struct SweepParams {
     uint32_t tile_bytes;    // (width + 1) * threads * 8
     uint32_t resident;      // 1: all n_tiles tiles fit in shared memory and are copied once (small graphs)
     uint32_t single;        // 1: one tile stage per CTA, two CTAs per SM cover each other's copy latency
+    int gpc, tpg;           // gibbs_kernel, resident tables only: chain groups per CTA and threads per group (gpc == 1: the CTA)
     uint32_t hi43;          // 0x43000000 (exponent of 128.0f): PRMT operand of the packed acceptance, kept out of the immediates
     uint32_t drawn_offset;  // byte offset of the pre-drawn Philox words [calls][threads] x 16 B (gibbs_kernel<.., PD = true>)
     uint32_t rk[2 * B200GRBM_PHILOX_ROUNDS];
@@ -46,6 +47,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// named barrier over one chain group of a multi-group CTA (id 1 .. 15, n_threads a multiple of 32)
+__device__ __forceinline__ void group_bar_sync(int id, int n_threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)

@@ -435,6 +435,34 @@ def test_specialised_throughput_kernel_equals_generic_kernel(cuda_device, monkey
     assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
 
 
+@pytest.mark.parametrize("chains", [20000, 33333])
+def test_several_chain_groups_per_cta_share_the_resident_tables(cuda_device, golden, monkeypatch, chains):
+    """Small graph, many chains (the reference's 256-latent model scaled up in chains, BASELINE configs[4]): chain groups
+    share a CTA and one resident copy of the tables.  Same samples as one group per CTA (B200GRBM_GPC=1), for any number
+    of groups per CTA incl. a ragged last CTA, and the oracle replays sampled chain blocks."""
+    name = "Advantage2_system1_10_epochs"
+    z, _ = golden
+    g = B.IsingGraph.build(256, z[name + "/edge_i"], z[name + "/edge_j"])
+    h, J = _problem(g, 31)
+    beta = np.geomspace(0.1, 1.0, 7)
+    out = {}
+    for gpc in ("1", "3", "11", ""):
+        if gpc:
+            monkeypatch.setenv("B200GRBM_GPC", gpc)
+        else:
+            monkeypatch.delenv("B200GRBM_GPC")
+        s = B.BlockGibbsSampler(g, device=cuda_device)
+        ss = s.sample_ising(h, J, num_reads=chains, beta_schedule=beta, seed=13)
+        assert s.last_plan[0] == 28 and s.last_kernel == "packed"
+        out[gpc] = (ss.record.sample.copy(), ss.record.energy.copy())
+    for gpc in ("3", "11", ""):
+        assert np.array_equal(out[gpc][0], out["1"][0]) and np.array_equal(out[gpc][1], out["1"][1]), gpc
+    csr = _oracle_csr(g)
+    for block in (0, 28 * 11, chains - 4 - chains % 4):
+        want = O.gibbs(csr, h, J, O.init_state(csr, 4, 13, chain_offset=block), beta, seed=13, chain_offset=block)
+        assert np.array_equal(out[""][0][block:block + 4], want), block
+
+
 # ------------------------------------------------------------------ one-chain-per-lane kernel (small problems)
 
 @pytest.mark.parametrize("graph,chains", [("ckpt", 256), ("p3", 70), ("p4", 37), ("z2", 9)])
