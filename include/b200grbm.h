@@ -110,6 +110,8 @@ typedef struct b200grbm_sweep_args {
  *   chains_per_lane == 28, Philox uniforms, and (threads, ell_width) one of (640, 15) [Pegasus P16], (480, 20) [Zephyr,
  *     one CTA per SM], (384, 20) with >= 2 groups per SM [Zephyr, two CTAs per SM]                 -> gibbs_wide_kernel
  *   anything else                                                                                  -> gibbs_kernel
+ *     (small graphs whose tables stay resident in shared memory, 28 chains per lane, many groups: several chain groups
+ *      share one CTA and one copy of the tables; B200GRBM_GPC=n forces n groups per CTA)
  * Environment switches for A/B measurements and the parity tests of the variants: B200GRBM_SMALL=0, B200GRBM_WIDE=0
  * (fall back to gibbs_kernel), B200GRBM_MMD_TILE=1|2, B200GRBM_GEMM_TILE=1|2 (single-CTA / CTA-pair tensor-core kernels).
  */

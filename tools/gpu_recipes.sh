@@ -38,7 +38,9 @@ case "${1:-all}" in
     timeout 200 python tools/bench_configs.py --graph z15 --chains 32768 --sweeps 100      # per-GPU shard of BASELINE cfg4
     timeout 200 python tools/bench_configs.py --graph p16 --chains 4096 --sweeps 1000 --anneal
     timeout 200 python tools/bench_configs.py --graph p16 --chains 4096 --sweeps 1000 --accept fast
-    timeout 200 python tools/bench_configs.py --graph cfg1 --chains 256 --sweeps 1000 ;;
+    timeout 200 python tools/bench_configs.py --graph cfg1 --chains 256 --sweeps 1000
+    timeout 200 python tools/bench_configs.py --graph cfg1 --chains 131072 --sweeps 100 --anneal   # per-GPU share of BASELINE cfg5 (1 M chains on 8 GPUs)
+    timeout 200 python tools/bench_configs.py --graph z15 --chains 4096 --sweeps 300 ;;
 esac
 # then, on the build box (r2 = this round):
 #   python tools/ncu_summary.py gpurun_out/gibbs_wide.ncu-rep profiles/r2_gibbs_wide_ncu_summary.txt --json profiles/r2_gibbs_wide_ncu_metrics.json --updates 462028800
