@@ -43,6 +43,7 @@ def main():
     off, cnt = shard_chains(args.chains_total, rank, world)
     model = HybridDVAE(range(256), edges, device=dev, parameters={"NUM_READS": cnt, "BATCH_SIZE": args.batch},
                        sampler_kwargs=dict(num_sweeps=args.sweeps, beta_range=(0.1, 1.0), chain_offset=off))
+    torch.manual_seed(20240)      # the networks are built before train_init seeds torch: fix the initialisation of this tool's runs
     model.setup()
     if world > 1:      # identical initial parameters on every rank
         for p in list(model._dvae.parameters()) + list(model._grbm.parameters()):
