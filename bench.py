@@ -509,7 +509,8 @@ def bench_mmd_sharded(dev, rank, world, m_each=8192, d=5640, iters=3):
 def bench_sweep_variants(dev, g, h, J, iters=3):
     """The sweep kernels off the headline configuration: fast (MUFU, 16-bit uniform) acceptance, an annealed schedule on
     the same P16 problem, the per-GPU shard of BASELINE.json configs[3] at 8 GPUs (Zephyr Z15, 32 768 chains, 100 sweeps),
-    and the reference's own default call (256 reads on the 256-spin Advantage2 sub-graph, configs[0]).  Device-resident,
+    the reference's own default call (256 reads on the 256-spin Advantage2 sub-graph, configs[0]) and the same graph with a
+    GPU's share of configs[4]'s 1 M annealed chains (several chain groups per CTA on resident tables).  Device-resident,
     CUDA events, no L2 flush (state and tables live in shared memory / registers)."""
     import torch
 
@@ -579,6 +580,8 @@ def bench_sweep_variants(dev, g, h, J, iters=3):
     hc = np.clip(np.float32(0.05) * ck[name + "/linear"], -4, 4).astype(np.float32)
     Jc = np.clip(np.float32(0.05) * ck[name + "/quadratic"], -1, 1).astype(np.float32)
     out["cfg1_256_reads_256_spins"] = timed(gc, hc, Jc, 256, 1000)
+    # per-GPU share of BASELINE.json configs[4] on 8 GPUs: 1 M annealed chains of the 256-latent model, 100 sweeps per step
+    out["cfg5_shard_131072_chains_256_spins_annealed"] = timed(gc, hc, Jc, 131072, 100, beta_range=(0.1, 1.0))
     return out
 
 

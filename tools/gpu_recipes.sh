@@ -22,6 +22,9 @@ case "${1:-all}" in
     # the reference's default call on the one-chain-per-lane kernel
     timeout 300 $NCU -k regex:gibbs_small -s 1 -c 1 -o gpurun_out/gibbs_small -f \
       python tools/bench_configs.py --graph cfg1 --chains 256 --sweeps 200 > gpurun_out/ncu_small.log 2>&1
+    # the 256-spin graph with many chains (per-GPU share of cfg5): several chain groups per CTA, resident tables
+    timeout 300 $NCU -k regex:gibbs_kernel -s 1 -c 1 -o gpurun_out/gibbs_mg -f \
+      python tools/bench_configs.py --graph cfg1 --chains 131072 --sweeps 10 > gpurun_out/ncu_mg.log 2>&1
     # Zephyr Z15 shard: one tile stage, two CTAs per SM; and the packed energy kernel behind it
     timeout 300 $NCU -k regex:gibbs_wide -s 1 -c 1 -o gpurun_out/gibbs_z15 -f \
       python tools/bench_configs.py --graph z15 --chains 32768 --sweeps 10 > gpurun_out/ncu_z15.log 2>&1
