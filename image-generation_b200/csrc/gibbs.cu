@@ -505,13 +505,14 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
         const int sms = sm_count() > 0 ? sm_count() : 148;
         int smem_sm_all = 0;
         B200_CUDA(cudaDeviceGetAttribute(&smem_sm_all, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-        // cost model (relative time): whole waves of `per_sm` CTAs per SM plus a partial last wave; an SM with w resident
-        // warps runs at w / (w + 4.35) of its peak (fitted on the 256-spin graph: 131072 chains x 100 sweeps take 7.95 ms
-        // with one group per CTA = 8 warps per SM, 6.20 ms with four = 24 warps)
+        // cost model (relative time; the same one as sampler.py::_plan_resident): whole waves of `per_sm` CTAs per SM
+        // plus a partial last wave; an SM with w >= 8 resident warps runs at w / (w + 4.35) of its peak (fitted on the
+        // 256-spin graph: 131072 chains x 100 sweeps take 7.95 ms with one group per CTA = 8 warps per SM, 6.20 ms with four
+        // = 24 warps) and in proportion to w below that
         const double wpg = a->threads / 32.0;
         const auto sm_time = [&](int ctas_on_sm, int gpc) {
             const double w = ctas_on_sm * gpc * wpg;
-            return ctas_on_sm * gpc * (w + 4.35) / w;
+            return ctas_on_sm * gpc / (w >= 8.0 ? w / (w + 4.35) : w / 12.35);
         };
         double best = 1e300;
         for (int gpc = 1; gpc <= 15 && gpc * a->threads <= 768; ++gpc) {

@@ -94,6 +94,11 @@ def plan_launch(chains: int, colour_sizes: Sequence[int], sm_count: int = 148, n
     SMs: 28 -> 147 CTAs in one wave beats 32 -> 128 CTAs; 256 chains: 4 -> 64 CTAs, a 3x shorter
     critical path than 28 -> 10 CTAs; 262144 chains: 28 again (many waves, overhead amortised).
     """
+    n = n or sum(colour_sizes)
+    threads = plan_threads(colour_sizes, n, ell_width)
+    small = _plan_resident(chains, colour_sizes, sm_count, n, ell_width, threads)
+    if small is not None:
+        return small, threads
     best = None
     for cpl in (28, 32, 24, 16, 8, 4):
         groups = -(-chains // cpl)
@@ -101,9 +106,61 @@ def plan_launch(chains: int, colour_sizes: Sequence[int], sm_count: int = 148, n
         if best is None or cost < best[0] - 1e-9:
             best = (cost, cpl)
     cpl = best[1]
-    n = n or sum(colour_sizes)
-    threads = plan_threads(colour_sizes, n, ell_width)
     return cpl, _plan_two_ctas(-(-chains // cpl), colour_sizes, sm_count, n, ell_width, threads)
+
+
+#: registers per thread of gibbs_kernel<CPL, PHILOX_EXACT, 768> (ptxas -v), for the occupancy estimate below
+_CPL_REGS = {4: 72, 8: 72, 16: 72, 24: 80, 28: 80, 32: 80}
+
+
+def _plan_resident(chains: int, colour_sizes: Sequence[int], sm_count: int, n: int, ell_width: int,
+                   threads: int) -> Optional[int]:
+    """Chains per lane for SMALL graphs -- every round's table resident in shared memory, several CTAs per SM (and,
+    for 28 chains per lane, several chain groups per CTA: ``b200grbm_gibbs_sweeps`` picks that itself) -- or ``None``
+    when the tables do not stay resident (Pegasus P16, Zephyr Z15: the rule above).
+
+    There the one-CTA-per-SM wave count says little: 4096 chains on the 256-spin graph are 147 two-warp CTAs with 28
+    chains per lane -- two warps per SM -- and run in 8.3 ms per 1000 sweeps, against 4.9 ms with 8 chains per lane
+    (512 CTAs, four per SM).  Model: a lane-task of ``cpl`` chains costs ``fixed + per_chain * cpl`` issue slots; an SM with
+    w >= 8 resident warps runs at w / (w + 4.35) of its peak (fitted on B200: 131072 chains x 100 sweeps, 7.95 ms at 8
+    warps per SM vs 6.20 ms at 24) and in proportion to w below that; a launch is whole waves of resident CTAs plus a
+    partial one.  Reproduces the measured best choice on the 256-spin graph: 1024 and 2048 chains -> 4, 4096 -> 8,
+    8192 -> 16, 16384 and 131072 -> 28 (tools/bench_configs.py --graph cfg1 --cpl ...)."""
+    sizes = [s for s in colour_sizes if s > 0] or [1]
+    n_tiles = sum(-(-s // threads) for s in sizes)
+    sm_count = max(sm_count, 1)
+
+    def sm_time(ctas_on_sm, groups_per_cta, cost):
+        w = ctas_on_sm * groups_per_cta * threads / 32.0
+        rate = w / (w + 4.35) if w >= 8.0 else w / 12.35          # below 8 warps an SM is latency-bound: linear in w
+        return ctas_on_sm * groups_per_cta * cost / rate
+
+    best = None
+    for cpl in (28, 32, 24, 16, 8, 4):
+        width = -(-ell_width // 4) * 4 if cpl <= 8 else ell_width
+        tile = (width + 1) * threads * 8
+        state = (n * 4 + 127) // 128 * 128
+        smem1 = sweep_smem_bytes(n, width, threads, n_tiles) + max(0, n_tiles - 2) * tile
+        if n_tiles > 2 and (smem1 > SMEM_LIMIT or n_tiles * tile >= (1 << 20)):
+            return None                                    # tables are streamed: not this model
+        cost = 160.0 + 2.2 * width + cpl * (1.15 * width + 14.0)
+        groups = -(-chains // cpl)
+        t_best = None
+        for gpc in range(1, (768 // threads if cpl == 28 else 1) + 1):
+            smem = smem1 + (gpc - 1) * state
+            if smem > SMEM_LIMIT:
+                break
+            ctas = -(-groups // gpc)
+            per_sm = max(1, min(65536 // (gpc * threads * _CPL_REGS[cpl]), SMEM_PER_SM // (smem + 1024),
+                                2048 // (gpc * threads), 32))
+            slots = sm_count * per_sm
+            full, rem = divmod(ctas, slots)
+            t = full * sm_time(per_sm, gpc, cost) + (sm_time(-(-rem // sm_count), gpc, cost) if rem else 0.0)
+            if t_best is None or t < t_best:
+                t_best = t
+        if best is None or t_best < 0.97 * best[0]:
+            best = (t_best, cpl)
+    return best[1]
 
 
 SMEM_PER_SM = 228 * 1024   # shared memory of one sm_100 SM (each resident CTA also reserves 1 KB)

@@ -194,3 +194,18 @@ def test_greedy_get_subgraph_is_deterministic_and_connected():
     assert seen == chosen
     mapping = B.get_graph_mapping(a)
     assert sorted(mapping.values()) == list(range(40))
+
+
+def test_plan_launch_small_graphs_with_resident_tables():
+    """Small graphs (tables resident, several CTAs per SM): chains per lane follow the occupancy model, reproducing the
+    choices measured on a B200 for the 256-spin Advantage2 sub-graph (tools/bench_configs.py --graph cfg1 --cpl ...)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grbm_checkpoints.npz"))
+    name = "Advantage2_system1_10_epochs"
+    g = B.IsingGraph.build(256, z[name + "/edge_i"], z[name + "/edge_j"])
+    sizes = np.diff(g.colour_start).tolist()
+    want = {256: 4, 1024: 4, 2048: 4, 4096: 8, 8192: 16, 16384: 28, 20000: 28, 33333: 28, 131072: 28}
+    for chains, cpl in want.items():
+        assert B.plan_launch(chains, sizes, 148, g.n, g.ell_width) == (cpl, 64), chains
+    # the big fabric graphs stream their tables: the wave rule is untouched
+    assert B.plan_launch(4096, [640] * 8 + [520], 148, 5640, 15) == (28, 640)
