@@ -44,12 +44,17 @@ constexpr int WIDE_CALLS = 4;           // Philox calls per lane-task: (28 + shi
 // (Tried: the tile copy split into three chunks with a barrier each -- rows of slot 0 and the first batch, then one
 // chunk per further batch -- so that a round starts after a third of the copy: 36.3 -> 39.3 ms on the Z15 shard, the
 // extra waits and smaller copies cost more than the earlier start saves.)
-template <int MODE, int T, int W, bool SINGLE>
-__global__ void __launch_bounds__(T, SINGLE ? 2 : 1) gibbs_wide_kernel(const __grid_constant__ SweepParams p)
+//
+// TC = 0: the CTA size is a run-time value (any Pegasus- / Zephyr-width graph whose planned CTA size has no instantiation
+// of its own); table rows are then one multiply apart instead of an immediate offset.
+template <int MODE, int TC, int W, bool SINGLE>
+__global__ void __launch_bounds__(TC > 0 ? TC : (SINGLE ? 384 : 768), SINGLE ? 2 : 1)
+    gibbs_wide_kernel(const __grid_constant__ SweepParams p)
 {
     constexpr bool PD = !SINGLE;
+    const int T = TC > 0 ? TC : (int)blockDim.x;
     constexpr int CPL = WIDE_CPL;
-    constexpr uint32_t TILE_BYTES = (uint32_t)(W + 1) * T * 8u;
+    const uint32_t TILE_BYTES = (uint32_t)(W + 1) * (uint32_t)T * 8u;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);                 // [0], [1]: tile stages; [2]: round barrier
     int2 *tinfo = reinterpret_cast<int2 *>(smem_raw + 128);
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(T, SINGLE ? 2 : 1) gibbs_wide_kernel(const __g
 
 typedef void (*wide_fn)(const SweepParams);
 
-template <int T, int W, bool SINGLE>
+template <int T, int W, bool SINGLE>      // T = 0: run-time CTA size
 static wide_fn wide_pick_mode(int mode)
 {
     return mode == MODE_PHILOX_FAST ? gibbs_wide_kernel<MODE_PHILOX_FAST, T, W, SINGLE>
@@ -197,6 +202,9 @@ static wide_fn wide_pick(int mode, int threads, int width, bool single)
     if (!single && threads == 640 && width == 15) return wide_pick_mode<640, 15, false>(mode);   // Pegasus P16: 9 rounds of 640 lanes
     if (single && threads == 384 && width == 20) return wide_pick_mode<384, 20, true>(mode);     // Zephyr Z15: 20 rounds, 2 CTAs per SM
     if (!single && threads == 480 && width == 20) return wide_pick_mode<480, 20, false>(mode);   // Zephyr Z15, < 296 groups: 16 rounds
+    // any other CTA size on a Pegasus-width (15) or Zephyr-width (20) table: run-time T
+    if (width == 15) return single ? (threads <= 384 ? wide_pick_mode<0, 15, true>(mode) : nullptr) : wide_pick_mode<0, 15, false>(mode);
+    if (width == 20) return single ? (threads <= 384 ? wide_pick_mode<0, 20, true>(mode) : nullptr) : wide_pick_mode<0, 20, false>(mode);
     return nullptr;
 }
 

@@ -107,8 +107,9 @@ typedef struct b200grbm_sweep_args {
  *
  * Kernel choice (results are identical whichever runs; b200grbm_last_sweep_kernel tells which did):
  *   chains_per_lane == 4 and a small graph (<= 5 rounds of <= 256 spins, degree <= 20)  -> gibbs_small_kernel
- *   chains_per_lane == 28, Philox uniforms, and (threads, ell_width) one of (640, 15) [Pegasus P16], (480, 20) [Zephyr,
- *     one CTA per SM], (384, 20) with >= 2 groups per SM [Zephyr, two CTAs per SM]                 -> gibbs_wide_kernel
+ *   chains_per_lane == 28, Philox uniforms, streamed tables of width 15 (Pegasus) or 20 (Zephyr) whose pre-drawn
+ *     uniforms fit behind the tile stages: compile-time CTA size for (640, 15) [P16], (480, 20) and (384, 20) with
+ *     >= 2 groups per SM [Z15]; any other CTA size as a run-time value                             -> gibbs_wide_kernel
  *   anything else                                                                                  -> gibbs_kernel
  *     (small graphs whose tables stay resident in shared memory, 28 chains per lane, many groups: several chain groups
  *      share one CTA and one copy of the tables; B200GRBM_GPC=n forces n groups per CTA)

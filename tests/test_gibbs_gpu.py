@@ -414,13 +414,13 @@ def test_full_size_cfg4_shard_properties(cuda_device):
     assert torch.equal(parts[0][0] + parts[1][0], s1) and torch.equal(parts[0][1] + parts[1][1], s2)
 
 
-@pytest.mark.parametrize("graph,chains", [("p16", 4096), ("p16", 4000), ("z15", 12000), ("z15", 4096)])
+@pytest.mark.parametrize("graph,chains", [("p16", 4096), ("p16", 4000), ("z15", 12000), ("z15", 4096), ("z8", 4100), ("p12", 4096)])
 @pytest.mark.parametrize("accept", ["exact", "fast"])
 def test_specialised_throughput_kernel_equals_generic_kernel(cuda_device, monkeypatch, graph, chains, accept):
     """gibbs_wide_kernel (compile-time geometry, pre-drawn uniforms behind a split round barrier, packed fp32x2
     acceptance) against gibbs_kernel<28> on the same launch: identical samples and energies in both acceptance modes,
     annealed schedule, ragged last group, a shard that starts inside a Philox block."""
-    g = B.IsingGraph.pegasus(16) if graph == "p16" else B.IsingGraph.zephyr(15)
+    g = (B.IsingGraph.pegasus if graph[0] == "p" else B.IsingGraph.zephyr)(int(graph[1:]))   # z8: run-time CTA size form
     rng = np.random.default_rng(21)
     h = (0.05 * rng.uniform(-0.5, 0.5, g.n)).astype(np.float32)
     J = (0.05 * rng.uniform(-5, 5, g.n_edges)).astype(np.float32)

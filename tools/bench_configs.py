@@ -25,7 +25,9 @@ if args.graph == "cfg1":       # the 256-spin Advantage2 subgraph of the referen
     name = "Advantage2_system1_10_epochs"
     g = B.IsingGraph.build(256, z[name + "/edge_i"], z[name + "/edge_j"])
 else:
-    g = B.IsingGraph.zephyr(15) if args.graph == "z15" else B.IsingGraph.pegasus(16)
+    import re
+    m = re.fullmatch(r"([pz])(\d+)", args.graph)
+    g = (B.IsingGraph.zephyr if m.group(1) == "z" else B.IsingGraph.pegasus)(int(m.group(2)))
 rng = np.random.default_rng(0)
 h = (0.05 * rng.uniform(-0.05, 0.05, g.n)).astype(np.float32)
 J = (0.05 * rng.uniform(-5, 5, g.n_edges)).astype(np.float32)
