@@ -356,7 +356,8 @@ static thread_local int32_t g_last_launches = 0;
 static thread_local int32_t g_last_kernel = 0;     // 0 = gibbs_kernel (chains bit-packed per lane), 1 = gibbs_small_kernel, 2 = gibbs_wide_kernel
 
 // gibbs_wide.cu
-size_t wide_kernel_smem(int cpl, int mode, int threads, int width, bool single, size_t ring_smem, uint32_t *drawn_offset);
+size_t wide_kernel_smem(int cpl, int mode, int threads, int width, bool single, size_t ring_smem, size_t smem_limit,
+                        uint32_t *drawn_offset);
 int32_t launch_gibbs_wide(const SweepParams &p, int mode, int threads, int groups, size_t smem, cudaStream_t st);
 
 // gibbs_small.cu
@@ -555,7 +556,7 @@ extern "C" int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *a, void *str
     const size_t smem_wide = (p.resident || (wide_env != nullptr && wide_env[0] == '0') ||
                               (long long)a->num_sweeps * a->n_tiles >= (1ll << 31))
                                  ? 0 : wide_kernel_smem(a->chains_per_lane, mode, a->threads, a->ell_width, p.single != 0, smem,
-                                                        &p.drawn_offset);
+                                                        (size_t)smem_optin, &p.drawn_offset);
     g_last_kernel = 0;
     if (smem_wide > 0 && smem_wide <= (size_t)smem_optin) {
         B200_TRY(launch_gibbs_wide(p, mode, a->threads, groups, smem_wide, (cudaStream_t)stream));

@@ -47,11 +47,15 @@ constexpr int WIDE_CALLS = 4;           // Philox calls per lane-task: (28 + shi
 //
 // TC = 0: the CTA size is a run-time value (any Pegasus- / Zephyr-width graph whose planned CTA size has no instantiation
 // of its own); table rows are then one multiply apart instead of an immediate offset.
-template <int MODE, int TC, int W, bool SINGLE>
+//
+// PD = false on the ring (one CTA per SM): the form for CTAs whose pre-drawn slots do not fit behind two tile stages
+// (Zephyr Z12, the Advantage2 fabric: 608 threads x 21 rows x 2 stages = 204 KB) -- __syncthreads() round barrier and
+// uniforms drawn in place, but still the unrolled, immediate-offset neighbour loop and the packed decisions.
+template <int MODE, int TC, int W, bool SINGLE, bool PD = !SINGLE>
 __global__ void __launch_bounds__(TC > 0 ? TC : (SINGLE ? 384 : 768), SINGLE ? 2 : 1)
     gibbs_wide_kernel(const __grid_constant__ SweepParams p)
 {
-    constexpr bool PD = !SINGLE;
+    static_assert(!(SINGLE && PD), "pre-drawn uniforms need the one-CTA-per-SM ring form");
     const int T = TC > 0 ? TC : (int)blockDim.x;
     constexpr int CPL = WIDE_CPL;
     const uint32_t TILE_BYTES = (uint32_t)(W + 1) * (uint32_t)T * 8u;
@@ -189,16 +193,18 @@ __global__ void __launch_bounds__(TC > 0 ? TC : (SINGLE ? 384 : 768), SINGLE ? 2
 
 typedef void (*wide_fn)(const SweepParams);
 
-template <int T, int W, bool SINGLE>      // T = 0: run-time CTA size
+template <int T, int W, bool SINGLE, bool PD = !SINGLE>      // T = 0: run-time CTA size
 static wide_fn wide_pick_mode(int mode)
 {
-    return mode == MODE_PHILOX_FAST ? gibbs_wide_kernel<MODE_PHILOX_FAST, T, W, SINGLE>
-                                    : gibbs_wide_kernel<MODE_PHILOX_EXACT, T, W, SINGLE>;
+    return mode == MODE_PHILOX_FAST ? gibbs_wide_kernel<MODE_PHILOX_FAST, T, W, SINGLE, PD>
+                                    : gibbs_wide_kernel<MODE_PHILOX_EXACT, T, W, SINGLE, PD>;
 }
 
-static wide_fn wide_pick(int mode, int threads, int width, bool single)
+static wide_fn wide_pick(int mode, int threads, int width, bool single, bool predraw = true)
 {
     if (mode != MODE_PHILOX_EXACT && mode != MODE_PHILOX_FAST) return nullptr;
+    if (!single && !predraw)            // ring without room for the slots
+        return width == 15 ? wide_pick_mode<0, 15, false, false>(mode) : width == 20 ? wide_pick_mode<0, 20, false, false>(mode) : nullptr;
     if (!single && threads == 640 && width == 15) return wide_pick_mode<640, 15, false>(mode);   // Pegasus P16: 9 rounds of 640 lanes
     if (single && threads == 384 && width == 20) return wide_pick_mode<384, 20, true>(mode);     // Zephyr Z15: 20 rounds, 2 CTAs per SM
     if (!single && threads == 480 && width == 20) return wide_pick_mode<480, 20, false>(mode);   // Zephyr Z15, < 296 groups: 16 rounds
@@ -210,18 +216,21 @@ static wide_fn wide_pick(int mode, int threads, int width, bool single)
 
 // shared-memory bytes of the specialised kernel (0: no instantiation for this geometry): the generic layout, plus -- in
 // the one-CTA-per-SM form -- the pre-drawn words behind it
-size_t wide_kernel_smem(int cpl, int mode, int threads, int width, bool single, size_t ring_smem, uint32_t *drawn_offset)
+size_t wide_kernel_smem(int cpl, int mode, int threads, int width, bool single, size_t ring_smem, size_t smem_limit,
+                        uint32_t *drawn_offset)
 {
     if (cpl != WIDE_CPL || wide_pick(mode, threads, width, single) == nullptr) return 0;
+    *drawn_offset = 0;                      // 0 = no pre-drawn slots
     if (single) return ring_smem;           // the launcher's one-stage size; nothing behind it
     const size_t off = (ring_smem + 127) / 128 * 128;
+    if (off + (size_t)WIDE_CALLS * 16 * threads > smem_limit) return ring_smem;      // ring, uniforms drawn in place
     *drawn_offset = (uint32_t)off;
     return off + (size_t)WIDE_CALLS * 16 * threads;
 }
 
 int32_t launch_gibbs_wide(const SweepParams &p, int mode, int threads, int groups, size_t smem, cudaStream_t st)
 {
-    wide_fn fn = wide_pick(mode, threads, p.width, p.single != 0);
+    wide_fn fn = wide_pick(mode, threads, p.width, p.single != 0, p.drawn_offset != 0);
     if (fn == nullptr) return fail(B200GRBM_EUNSUPPORTED, "gibbs_wide: no instantiation for threads=%d width=%d", threads, p.width);
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -414,7 +414,7 @@ def test_full_size_cfg4_shard_properties(cuda_device):
     assert torch.equal(parts[0][0] + parts[1][0], s1) and torch.equal(parts[0][1] + parts[1][1], s2)
 
 
-@pytest.mark.parametrize("graph,chains", [("p16", 4096), ("p16", 4000), ("z15", 12000), ("z15", 4096), ("z8", 4100), ("p12", 4096)])
+@pytest.mark.parametrize("graph,chains", [("p16", 4096), ("p16", 4000), ("z15", 12000), ("z15", 4096), ("z8", 4100), ("p12", 4096), ("z12", 4096)])
 @pytest.mark.parametrize("accept", ["exact", "fast"])
 def test_specialised_throughput_kernel_equals_generic_kernel(cuda_device, monkeypatch, graph, chains, accept):
     """gibbs_wide_kernel (compile-time geometry, pre-drawn uniforms behind a split round barrier, packed fp32x2
