@@ -463,6 +463,18 @@ def test_several_chain_groups_per_cta_share_the_resident_tables(cuda_device, gol
         assert np.array_equal(out[""][0][block:block + 4], want), block
 
 
+def test_fuzz_slice_random_graphs_and_chain_counts_bit_exact(cuda_device):
+    """Ten seconds of tools/fuzz_sampler.py (fixed seed): random graphs, chain counts and offsets through every planner
+    branch, first / middle / last chain blocks replayed by the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_sampler.py"), "7", "10"], cwd=root, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "fuzz OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 # ------------------------------------------------------------------ one-chain-per-lane kernel (small problems)
 
 @pytest.mark.parametrize("graph,chains", [("ckpt", 256), ("p3", 70), ("p4", 37), ("z2", 9)])
