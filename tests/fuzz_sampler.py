@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Fuzz of the sampler against the CPU oracle:  python tools/fuzz_sampler.py SEED SECONDS  (one B200).
+"""Fuzz of the sampler against the CPU oracle:  python tests/fuzz_sampler.py SEED SECONDS  (test infrastructure: it runs the oracle)  (one B200).
 
 Random graphs (Pegasus P2..P6, Zephyr Z1..Z5, random graphs of 8..700 spins with degree <= 20), random chain counts from 1
 to 40000 (every planner branch: small-problem kernel, 4 .. 32 chains per lane, several chain groups per CTA, resident and

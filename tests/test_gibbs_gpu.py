@@ -464,13 +464,13 @@ def test_several_chain_groups_per_cta_share_the_resident_tables(cuda_device, gol
 
 
 def test_fuzz_slice_random_graphs_and_chain_counts_bit_exact(cuda_device):
-    """Ten seconds of tools/fuzz_sampler.py (fixed seed): random graphs, chain counts and offsets through every planner
+    """Ten seconds of tests/fuzz_sampler.py (fixed seed): random graphs, chain counts and offsets through every planner
     branch, first / middle / last chain blocks replayed by the oracle."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_sampler.py"), "7", "10"], cwd=root, capture_output=True,
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz_sampler.py"), "7", "10"], cwd=root, capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0 and "fuzz OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
