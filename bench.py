@@ -26,7 +26,8 @@ multi-GPU configurations):
 `cfg4`       : configs[3] -- Zephyr Z15, 262 144 chains split over the N ranks (STRONG scaling), 100 sweeps, integer
                statistics + the NCCL int64 all-reduce per step; at N > 1 rank 0 also runs the whole job alone, in the
                same process, for `strong_scaling_vs_n1`.
-`mmd_sharded`: configs[2] with the 8 192 + 8 192 rows sharded over the ranks: int8 all-gather, each rank contracts
+`mmd_sharded`: configs[2] with the 8 192 + 8 192 rows sharded over the ranks: rows exchanged as one bit per spin, pulled
+               from the peers' memory over NVLink by the kernel that writes the int8 Gram operand, each rank contracts
                its share of the Gram tiles, one int64 all-reduce of the Hamming histograms; checked equal, count for
                count and bit for bit, to the single-GPU result.
 """
@@ -447,9 +448,22 @@ def bench_cfg4(dev, rank, world, total_chains=262144, sweeps=100, steps=4, warmu
     return out
 
 
+def _mmd_exchange_report(world, m, d_pad, d):
+    """What sharded_mmd_loss moved between the ranks: rows as one bit per spin pulled over NVLink by the unpack kernel
+    ("p2p"), the same bit rows through an NCCL all-gather ("bits"), or int8 rows through NCCL ("int8")."""
+    from image_generation_b200.dist import _DeviceOps
+    mode = _DeviceOps.last_exchange
+    if world == 1:
+        return {"mode": mode, "row_bytes_per_rank_inbound": 0, "allreduce_int64_bytes": 0}
+    total = m * d_pad if mode == "int8" else m * d_pad // 8
+    return {"mode": mode, "collective_on_rows": "none (peer loads over NVLink, flag-synchronised)" if mode == "p2p" else "nccl all-gather",
+            "row_bytes_total": int(total), "row_bytes_per_rank_inbound": int(total * (world - 1) // world),
+            "allreduce_int64_bytes": int(3 * (d + 1) * 8)}
+
+
 def bench_mmd_sharded(dev, rank, world, m_each=8192, d=5640, iters=3):
     """BASELINE.json configs[2] with its rows sharded over the ranks (m_each / N encoder rows and as many samples per
-    rank): dist.sharded_mmd_loss = int8 all-gather of both blocks, every rank contracts its share of the Gram tiles into
+    rank): dist.sharded_mmd_loss = bit-row exchange over NVLink peer memory (csrc/peer_exchange.cu), every rank contracts its share of the Gram tiles into
     Hamming histograms, one int64 all-reduce, float64 evaluation; backward for the rank's own rows."""
     import torch
     import torch.distributed as dist
@@ -501,8 +515,7 @@ def bench_mmd_sharded(dev, rank, world, m_each=8192, d=5640, iters=3):
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
     return {"workload": f"MMD {m_x} x {m_y} rows, D = {d}, 7 kernels, rows sharded over {world} GPU(s) (BASELINE.json configs[2])",
             "forward_ms": float(t[0]), "backward_ms": float(t[1]), "rows_per_gpu": mx,
-            "exchange": {"allgather_int8_bytes": int(2 * m_x * zi.shape[1]), "allreduce_int64_bytes": int(3 * (d + 1) * 8)} if world > 1
-            else {"allgather_int8_bytes": 0, "allreduce_int64_bytes": 0},
+            "exchange": _mmd_exchange_report(world, m_x + m_y, zi.shape[1], d),
             "value": float(val.detach()), "bit_identical_to_single_gpu_on_every_rank": bool(int(same.item()) == 1)}
 
 

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libb200grbm.so")
 
 ACCEPT_EXACT = 0
 ACCEPT_FAST = 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class B200Error(RuntimeError):
@@ -94,6 +94,14 @@ SIGNATURES = {
     "b200grbm_mmd_forward_bf16": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _vp], _i32),
     "b200grbm_mmd_coef_bf16": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _f32, _f32, _vp, _vp, _i32,
                                 _vp], _i32),
+    "b200grbm_spin_pack_bits_f32": ([_vp, _i32, _i32, _vp, _i32, _i32, _vp], _i32),
+    "b200grbm_spin_pack_bits_i8": ([_vp, _i32, _i32, _vp, _i32, _i32, _vp], _i32),
+    "b200grbm_peer_signal": ([_vp, C.c_uint32, _vp], _i32),
+    "b200grbm_bits_to_rows": ([C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _i32, _i32, _i32, _vp, C.c_uint32, _vp], _i32),
+    "b200grbm_peer_alloc": ([C.c_int64, C.POINTER(_vp), _vp], _i32),
+    "b200grbm_peer_open": ([_vp, C.POINTER(_vp)], _i32),
+    "b200grbm_peer_close": ([_vp], _i32),
+    "b200grbm_peer_free": ([_vp], _i32),
     "b200grbm_tensor_peak": ([_i32, _i32, C.POINTER(C.c_double), _vp], _i32),
     "b200grbm_mmd_backward_f32": ([_vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _f32, _f32, _vp, _vp, _vp,
                                    _vp], _i32),

@@ -13,7 +13,7 @@ pids=""
 for f in gibbs.cu gibbs_small.cu gibbs_wide.cu; do
   if [ -f "$f" ]; then $NVCC $COMMON --fmad=false -c "$f" -o "build/${f%.cu}.o" & pids="$pids $!"; fi
 done
-for f in common.cu stats.cu mmd_simt.cu mmd_tc.cu mmd_tc2.cu gemm_tc.cu gemm_i8.cu spin_extract.cu mmd_bf16.cu tc_peak.cu; do
+for f in common.cu stats.cu mmd_simt.cu mmd_tc.cu mmd_tc2.cu gemm_tc.cu gemm_i8.cu spin_extract.cu peer_exchange.cu mmd_bf16.cu tc_peak.cu; do
   if [ -f "$f" ]; then $NVCC $COMMON -c "$f" -o "build/${f%.cu}.o" & pids="$pids $!"; fi
 done
 # `wait` without arguments returns 0 even when a job failed: wait for every compile by PID

@@ -113,17 +113,20 @@ def _estimate(sums, m_x: int, m_y: int, kernel: GaussianKernel, estimator: str):
     if estimator == "unbiased":
         if m_x < 2 or m_y < 2:
             raise ValueError("the unbiased MMD estimator needs at least two rows in x and in y")
+        w_xx = 2.0 / (m_x * (m_x - 1))
+    else:
+        w_xx = 2.0 / (m_x * m_x)
+    w_xy = -2.0 * scale / (m_x * m_y)
+    if sums.numel() >= 5:       # the histogram evaluation kernel already formed the estimate (same formula, float64)
+        return sums[4], scale * w_xx, w_xy
+    if estimator == "unbiased":
         xx = (sums[0] - diag * m_x) / (m_x * (m_x - 1))
         yy = (sums[1] - diag * m_y) / (m_y * (m_y - 1))
-        w_xx = 2.0 / (m_x * (m_x - 1))
     else:
         xx = sums[0] / (m_x * m_x)
         yy = sums[1] / (m_y * m_y)
-        w_xx = 2.0 / (m_x * m_x)
-    if sums.numel() >= 5:       # the histogram evaluation kernel already formed the estimate (same formula, float64)
-        return sums[4], scale * w_xx, -2.0 * scale / (m_x * m_y)
     xy = sums[2] / (m_x * m_y)
-    return scale * (xx + yy - 2.0 * xy), scale * w_xx, -2.0 * scale / (m_x * m_y)
+    return scale * (xx + yy - 2.0 * xy), scale * w_xx, w_xy
 
 
 class _MMDFunction(torch.autograd.Function):

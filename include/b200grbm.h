@@ -11,7 +11,9 @@
  *     shape errors, or a positive cudaError_t; b200grbm_last_error() returns a
  *     thread-local message for the last non-zero return.  No exceptions cross the ABI.
  *   - all *_dev pointers are device pointers owned by the caller (PyTorch in the host
- *     layer); the library never allocates or frees persistent device memory.
+ *     layer); the library never allocates or frees persistent device memory -- the one exception is the
+ *     explicit exchange-buffer pair b200grbm_peer_alloc / b200grbm_peer_free (memory that must be exportable
+ *     to the other ranks of the box), which the caller owns between the two calls.
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
  *     synchronises the device.
  *   - there is no CPU fallback: on a machine without an sm_100 device every compute entry
@@ -26,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200GRBM_ABI_VERSION 3
+#define B200GRBM_ABI_VERSION 4
 
 #define B200GRBM_EINVAL (-1)   /* bad argument / shape */
 #define B200GRBM_EUNSUPPORTED (-2) /* configuration not compiled in (e.g. chains_per_lane) */
@@ -326,6 +328,36 @@ int32_t b200grbm_mmd_coef_bf16(const void *z_hi_dev, const void *z_lo_dev, const
                                int32_t m_y, int32_t k_pad, int32_t n_kernels, float mul_factor, int32_t squared,
                                float bandwidth, const double *sums_dev, float w_xx, float w_xy, void *coef_hi_dev,
                                void *coef_lo_dev, int32_t m_pad, void *stream);
+
+/*
+ * Cross-rank row exchange of the sharded MMD (the reference has no collective -- its
+ * maximum_mean_discrepancy_loss call at src/model_wrapper.py:320 sees the whole batch in one process).  Rows are +-1,
+ * so ranks exchange ONE BIT per spin and the expansion to the int8 Gram operand is fused with the transfer.
+ *
+ * b200grbm_spin_pack_bits_*: rows [rows][d] (f32 by sign, or int8) -> bits_dev[(row_off + r) * words_per_row + w],
+ *   bit k of word w = (spin 32 w + k is +1), columns >= d zero; words_per_row >= ceil(d / 32).
+ * b200grbm_peer_signal: stream-ordered st.release.sys of `value` into a flag word ("my bit rows of step `value` are
+ *   complete"), to be polled by the other ranks' b200grbm_bits_to_rows.
+ * b200grbm_bits_to_rows: bits_ptrs[r] (HOST array of `world` DEVICE pointers: rank r's bit rows, [mx_loc + my_loc]
+ *   [words_per_row], local or peer-mapped) -> z_dev int8 [world * (mx_loc + my_loc)][32 * words_per_row], the stacked
+ *   matrix [x_0 .. x_{W-1}; y_0 .. y_{W-1}] of b200grbm_mmd_hist_i8 (padding columns zero).  flag_ptrs (HOST array or
+ *   NULL): where non-NULL the kernel waits (ld.acquire.sys) until *flag_ptrs[r] >= step before reading rank r; a peer
+ *   that never signals traps the kernel after 4 s instead of hanging the device.  world <= 16.
+ * b200grbm_peer_alloc / _free: cudaMalloc'd, zeroed buffer plus its 64-byte cudaIpcMemHandle_t (handle_out: HOST, 64
+ *   bytes) for the other ranks; b200grbm_peer_open / _close: map / unmap a peer's buffer in this process
+ *   (cudaIpcOpenMemHandle with lazy peer access).  These four synchronise the device; they are setup calls.
+ */
+int32_t b200grbm_spin_pack_bits_f32(const float *x_dev, int32_t rows, int32_t d, uint32_t *bits_dev, int32_t words_per_row,
+                                    int32_t row_off, void *stream);
+int32_t b200grbm_spin_pack_bits_i8(const int8_t *x_dev, int32_t rows, int32_t d, uint32_t *bits_dev, int32_t words_per_row,
+                                   int32_t row_off, void *stream);
+int32_t b200grbm_peer_signal(uint32_t *flag_dev, uint32_t value, void *stream);
+int32_t b200grbm_bits_to_rows(const void *const *bits_ptrs, const void *const *flag_ptrs, int32_t world, int32_t mx_loc,
+                              int32_t my_loc, int32_t d, int32_t words_per_row, int8_t *z_dev, uint32_t step, void *stream);
+int32_t b200grbm_peer_alloc(int64_t bytes, void **ptr_out, void *handle_out);
+int32_t b200grbm_peer_open(const void *handle, void **ptr_out);
+int32_t b200grbm_peer_close(void *ptr);
+int32_t b200grbm_peer_free(void *ptr);
 
 #ifdef __cplusplus
 }

@@ -77,8 +77,36 @@ class _NumpyOps:
     gradient) on the gloo backend."""
 
     @staticmethod
-    def pack(rows):
-        return torch.sign(rows).to(torch.int8)
+    def alloc(m, d, device):
+        return torch.full((m, d), 77, dtype=torch.int8)         # poison: every row must be written or received
+
+    @staticmethod
+    def pack_into(rows, z, row_off):
+        z[row_off:row_off + rows.shape[0]] = torch.sign(rows).to(torch.int8)
+
+    mode = "int8"
+
+    @staticmethod
+    def pack_bits(x_local, y_local):
+        """numpy restatement of csrc/peer_exchange.cu::spin_pack_bits_kernel: bit k of word w = spin 32 w + k is +1."""
+        rows = np.concatenate([x_local.detach().numpy(), y_local.detach().numpy()]) > 0
+        wpr = -(-rows.shape[1] // 128) * 4
+        padded = np.zeros((rows.shape[0], 32 * wpr), dtype=np.uint8)
+        padded[:, :rows.shape[1]] = rows
+        return torch.from_numpy(np.packbits(padded, axis=1, bitorder="little").view(np.int32).copy())
+
+    @staticmethod
+    def unpack_bits(every, mx_loc, my_loc, d):
+        """... and of bits_to_rows_kernel: source r row i -> x block r (i < mx_loc) or y block r; padding columns zero."""
+        world, rows_loc, wpr = every.shape
+        bits = np.unpackbits(every.numpy().view(np.uint8).reshape(world, rows_loc, 4 * wpr), axis=2, bitorder="little")
+        spins = (bits.astype(np.int8) * 2 - 1)[:, :, :d]
+        return torch.from_numpy(np.concatenate([spins[:, :mx_loc].reshape(-1, d), spins[:, mx_loc:].reshape(-1, d)]))
+
+    @classmethod
+    def exchange(cls, x_local, y_local, rank, world, group):
+        from image_generation_b200.dist import exchange_bits, exchange_int8
+        return (exchange_bits if cls.mode == "bits" else exchange_int8)(cls, x_local, y_local, rank, world, group)
 
     @staticmethod
     def histograms(z, m_x, d, shard):
@@ -119,12 +147,16 @@ def _mmd_worker(rank, world, port, out):
         kern = B.GaussianKernel(7)
         val = sharded_mmd_loss(x, y, kern, _ops=_NumpyOps)
         val.backward()
+        # the bit-row exchange (one bit per spin on the wire) assembles the same matrix: identical value
+        ops_bits = type("_NumpyOpsBits", (_NumpyOps,), {"mode": "bits"})
+        val_bits = sharded_mmd_loss(x.detach(), y, kern, _ops=ops_bits)
         bw = O.gaussian_kernel_matrix(np.concatenate([x_all, y_all]).astype(np.float64))[1]
         want, grad = O.mmd(x_all, y_all, bandwidth=bw, return_grad=True)
         ok = abs(float(val) - want) < 1e-6 and np.allclose(x.grad.numpy(), grad[rank * mx:(rank + 1) * mx], rtol=1e-5, atol=1e-9)
         vals = [torch.zeros(1, dtype=torch.float32) for _ in range(world)]
         dist.all_gather(vals, val.detach().reshape(1))
-        out[rank] = bool(ok and all(torch.equal(v, vals[0]) for v in vals))     # bit-identical on every rank
+        out[rank] = bool(ok and torch.equal(val_bits, val.detach())
+                         and all(torch.equal(v, vals[0]) for v in vals))        # bit-identical on every rank
     finally:
         dist.destroy_process_group()
 
