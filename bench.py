@@ -296,6 +296,8 @@ def run_b200(args):
     # every rank leaves the process group here, together; the CPU baseline and the side metrics
     # below are rank-0-only work with no collective in them
     if world > 1:
+        from image_generation_b200.dist import release_peer_buffers
+        release_peer_buffers()               # the NVLink exchange buffers of mmd_sharded (collective)
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:

@@ -25,7 +25,11 @@
 //     size: 28.56 ms;
 //   * round geometry carried in registers, parities toggled instead of derived from the round counter (fewer prologue
 //     instructions): 28.29 ms on P16, Z15 36.3 -> 36.6 ms -- the prologue's cost is latency after the barrier, not
-//     instruction count.
+//     instruction count;
+//   * the bracket width -(K2 + K1 g) of two chains in one packed FFMA2 followed by one FADD per chain (1.5 issue slots
+//     per decision instead of 2; 16 SASS instructions fewer per lane-task): P16 28.35 -> 28.58 ms, Z15 36.4 -> 36.1 ms,
+//     i.e. inside the box-to-box spread on Zephyr and a loss on Pegasus, where the fma pipe (two passes per packed
+//     op) is the busier resource.
 #include "gibbs_packed.cuh"
 
 namespace b200grbm {

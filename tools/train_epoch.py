@@ -105,6 +105,8 @@ def main():
         flags = torch.tensor([int(same)], device=dev)
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         in_sync = bool(flags.item())
+        from image_generation_b200.dist import release_peer_buffers
+        release_peer_buffers()
         dist.barrier()
         dist.destroy_process_group()
     else:
