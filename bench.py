@@ -463,7 +463,7 @@ def _mmd_exchange_report(world, m, d_pad, d):
             "allreduce_int64_bytes": int(3 * (d + 1) * 8)}
 
 
-def bench_mmd_sharded(dev, rank, world, m_each=8192, d=5640, iters=3):
+def bench_mmd_sharded(dev, rank, world, m_each=8192, d=5640, iters=8):
     """BASELINE.json configs[2] with its rows sharded over the ranks (m_each / N encoder rows and as many samples per
     rank): dist.sharded_mmd_loss = bit-row exchange over NVLink peer memory (csrc/peer_exchange.cu), every rank contracts its share of the Gram tiles into
     Hamming histograms, one int64 all-reduce, float64 evaluation; backward for the rank's own rows."""
@@ -492,7 +492,7 @@ def bench_mmd_sharded(dev, rank, world, m_each=8192, d=5640, iters=3):
         e2.record()
         return val, e0, e1, e2
 
-    for _ in range(2):
+    for _ in range(3):
         call()
     torch.cuda.synchronize(dev)
     if world > 1:
