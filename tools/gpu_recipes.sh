@@ -36,7 +36,12 @@ case "${1:-all}" in
     timeout 300 $NCU -k regex:mmd_gram_i8_kernel -s 1 -c 1 -o gpurun_out/mmd_coef -f \
       python tools/bench_mmd.py --stage backward --iters 1 > gpurun_out/ncu_mmd2.log 2>&1
     timeout 300 $NCU -k regex:gemm_i8_planes_2cta -s 1 -c 1 -o gpurun_out/gemm_i8 -f \
-      python tools/bench_mmd.py --stage backward --iters 1 > gpurun_out/ncu_mmd3.log 2>&1 ;;&
+      python tools/bench_mmd.py --stage backward --iters 1 > gpurun_out/ncu_mmd3.log 2>&1
+    # cross-rank MMD exchange: bit-row pack and the expand kernel (cfg3 sizes on one GPU; memcheck / racecheck on a small case)
+    timeout 300 $NCU -k regex:"spin_pack_bits|bits_to_rows" -s 3 -c 3 -o gpurun_out/peer_kernels -f \
+      python tools/run_peer_kernels.py > gpurun_out/ncu_peer.log 2>&1
+    ROWS=512 D=700 timeout 300 compute-sanitizer --tool memcheck python tools/run_peer_kernels.py > gpurun_out/memcheck_peer.log 2>&1
+    ROWS=512 D=700 timeout 300 compute-sanitizer --tool racecheck python tools/run_peer_kernels.py > gpurun_out/racecheck_peer.log 2>&1 ;;&
   configs|all)
     timeout 200 python tools/bench_configs.py --graph z15 --chains 32768 --sweeps 100      # per-GPU shard of BASELINE cfg4
     timeout 200 python tools/bench_configs.py --graph p16 --chains 4096 --sweeps 1000 --anneal
@@ -44,6 +49,13 @@ case "${1:-all}" in
     timeout 200 python tools/bench_configs.py --graph cfg1 --chains 256 --sweeps 1000
     timeout 200 python tools/bench_configs.py --graph cfg1 --chains 131072 --sweeps 100 --anneal   # per-GPU share of BASELINE cfg5 (1 M chains on 8 GPUs)
     timeout 200 python tools/bench_configs.py --graph z15 --chains 4096 --sweeps 300 ;;
+  multi)
+    # on N GPUs (gpurun --gpus N): the sharded MMD with each exchange mode, then the bench line
+    N=${2:-2}
+    timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+      tools/bench_mmd_sharded.py > gpurun_out/mmd_sharded_modes_n$N.json 2> gpurun_out/mmd_sharded_modes_n$N.err
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
+      bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err ;;
 esac
 # then, on the build box (r2 = this round):
 #   python tools/ncu_summary.py gpurun_out/gibbs_wide.ncu-rep profiles/r2_gibbs_wide_ncu_summary.txt --json profiles/r2_gibbs_wide_ncu_metrics.json --updates 462028800
