@@ -699,6 +699,11 @@ def bench_dvae_step(dev, steps=20, warmup=5):
         out["persistent_chains_20_sweeps_ms_per_step"] = run(persistent=20)
     except Exception as exc:  # a side metric must never take the bench line down
         out["persistent_chains_error"] = repr(exc)
+    try:    # the stock-PyTorch nets (forward + backward) replayed as two CUDA graphs: the step stops being launch-bound
+        out["graphed_nets_ms_per_step"] = run(graphed=True)
+        out["graphed_nets_persistent_chains_20_sweeps_ms_per_step"] = run(graphed=True, persistent=20)
+    except Exception as exc:
+        out["graphed_nets_error"] = repr(exc)
     try:
         out["cpu_baseline"] = cpu_dvae_step(z, name, edges)
     except Exception as exc:

@@ -225,3 +225,60 @@ def test_persistent_chains_in_the_training_step(cuda_device, golden):
     seed = model2._chains.seed
     want = O.gibbs(csr, h, J, O.init_state(csr, 256, seed), [1.0] * k, seed=seed)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_cuda_graphed_nets_follow_the_eager_training_run(cuda_device, golden):
+    """``graphed=True`` replays the stock encoder / decoder stack (forward and backward) as CUDA graphs.  With the two
+    random layers out of the way (heaviside latent-to-discrete, dropout off) the run is deterministic, so it must follow
+    the eager run: same losses, same parameters, same batch-norm statistics (the capture's warm-up iterations are
+    kept out of them).  A batch of another shape falls back to the eager stack."""
+    z, _ = golden
+    name = "Advantage2_system1_10_epochs"
+    edges = list(zip(z[name + "/edge_i"].tolist(), z[name + "/edge_j"].tolist()))
+    runs = []
+    for graphed in (False, True):
+        torch.manual_seed(11)
+        model = HybridDVAE(range(256), edges, device=cuda_device, sampler_kwargs=dict(num_sweeps=30), graphed=graphed,
+                           parameters={"LATENT_TO_DISCRETE": "heaviside", "N_REPLICAS": 1})
+        model.setup()
+        for m in model._dvae.modules():
+            if isinstance(m, torch.nn.Dropout2d):
+                m.p = 0.0
+        model.train_init(n_epochs=1, n_batches=12)
+        for k in range(11):
+            model.step((synthetic_batch(128, seed=k % 3), None), epoch=0)
+        model.step((synthetic_batch(64, seed=5), None), epoch=0)            # ragged last batch: eager path
+        assert (model._graphed_net is not None) == graphed
+        runs.append((np.array(model.losses["mse_losses"]), np.array(model.losses["dvae_losses"]),
+                     {k: v.detach().clone() for k, v in model._dvae.state_dict().items()},
+                     model._grbm._linear.detach().clone()))
+    (mse_a, dv_a, sd_a, h_a), (mse_b, dv_b, sd_b, h_b) = runs
+    np.testing.assert_allclose(mse_b, mse_a, rtol=2e-3)
+    np.testing.assert_allclose(dv_b, dv_a, rtol=2e-3, atol=1e-5)
+    assert mse_a[-2] < mse_a[0]
+    for k in sd_a:
+        if sd_a[k].dtype.is_floating_point:
+            # (two trajectories through a sign function: atomics-ordered reductions in cuDNN flip a few latents)
+            assert torch.allclose(sd_a[k], sd_b[k], rtol=2e-2, atol=5e-3), k
+        else:
+            assert torch.equal(sd_a[k], sd_b[k]), k                         # num_batches_tracked: warm-up not counted
+    assert torch.allclose(h_a, h_b, rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_cuda_graphed_nets_default_configuration_trains(cuda_device, golden):
+    z, _ = golden
+    name = "Advantage2_system1_10_epochs"
+    edges = list(zip(z[name + "/edge_i"].tolist(), z[name + "/edge_j"].tolist()))
+    model = HybridDVAE(range(256), edges, device=cuda_device, sampler_kwargs=dict(num_sweeps=50), graphed=True, persistent=5)
+    model.setup()
+    model.train_init(n_epochs=1, n_batches=12)
+    for k in range(12):
+        mse = model.step((synthetic_batch(128, seed=k % 3), None), epoch=0)
+    assert torch.isfinite(mse) and model.losses["mse_losses"][-1] < model.losses["mse_losses"][0]
+    # (a graphed call returns the capture's static output buffers: copy before the next replay overwrites them)
+    spins_a = model._forward_nets(synthetic_batch(128, seed=0, device=cuda_device), 8)[0].detach().clone()
+    assert set(torch.unique(spins_a.detach().round()).tolist()) <= {-1.0, 1.0}        # Gumbel noise is redrawn per replay
+    spins_b = model._forward_nets(synthetic_batch(128, seed=0, device=cuda_device), 8)[0]
+    assert not torch.equal(spins_a, spins_b.detach())
