@@ -313,7 +313,8 @@ class _DeviceOps:
         mode = os.environ.get("B200GRBM_MMD_EXCHANGE", "p2p")
         if mode not in ("p2p", "bits", "int8"):
             raise ValueError("B200GRBM_MMD_EXCHANGE must be p2p, bits or int8")
-        if mode == "int8":
+        if mode == "int8" or (world == 1 and "B200GRBM_MMD_EXCHANGE" not in os.environ):
+            # (a single rank has nothing to exchange: its rows go straight into the Gram layout)
             cls.last_exchange = "int8"
             return exchange_int8(cls, x_local, y_local, rank, world, group)
         if mode == "p2p" and world > 1:
