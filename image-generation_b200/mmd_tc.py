@@ -199,7 +199,12 @@ def mmd_backward_i8(zi: torch.Tensor, d: int, m_x: int, kernel, sums: torch.Tens
     ``hist``: the forward's Hamming histograms (the fixed-point range then covers only distances that occur)."""
     m, d_pad = zi.shape
     dev = zi.device
-    n_planes = GRAD_PLANES if n_planes is None else int(n_planes)
+    if n_planes is None:
+        # one fixed-point scale serves the x-x and the x-y coefficients: when their weights differ by more than 8x
+        # (very unequal row counts) the smaller block would keep fewer than 13 of the 16 bits -- take the third plane
+        lo, hi = sorted((abs(float(w_xx)), abs(float(w_xy))))
+        n_planes = max(GRAD_PLANES, 3) if (lo > 0.0 and hi > 8.0 * lo) else GRAD_PLANES
+    n_planes = int(n_planes)
     row0, n_rows = (0, m_x) if rows is None else rows
     m_pad = (m + 127) // 128 * 128
     rows_alloc = (n_rows + 127) // 128 * 128

@@ -476,3 +476,15 @@ def test_spin_extract_layouts(cuda_device):
     flag = torch.zeros(1, dtype=torch.int32, device=cuda_device)
     pack_pair_i8(bad, torch.from_numpy(y).to(cuda_device), nonspin=flag)
     assert int(flag) == 1
+
+
+def test_fuzz_slice_random_shapes_and_switches(cuda_device):
+    """Ten seconds of tests/fuzz_mmd.py (fixed seed): random ragged shapes, structured clouds, every kernel switch, tile
+    sharding and the bit-row layout -- histograms exact, value / gradient against the float64 oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz_mmd.py"), "3", "10"], cwd=root, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "fuzz OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
