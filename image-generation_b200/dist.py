@@ -156,7 +156,8 @@ class PeerBitExchange:
                 if ok:
                     self.own = p.value
         got: list = [None] * self.world
-        dist.all_gather_object(got, (bool(ok), bytes(handle)), group=group)
+        with torch.cuda.device(self.device):     # object collectives stage through the CURRENT device on NCCL
+            dist.all_gather_object(got, (bool(ok), bytes(handle)), group=group)
         ok = all(g[0] for g in got)
         if ok:
             with torch.cuda.device(self.device):
