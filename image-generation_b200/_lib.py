@@ -82,6 +82,8 @@ SIGNATURES = {
     "b200grbm_mmd_forward_f32": ([_vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _vp], _i32),
     "b200grbm_mmd_pack_i8": ([_vp, _i32, _i32, _i32, _vp, _vp], _i32),
     "b200grbm_mmd_hist_i8": ([_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "b200grbm_mmd_hist_fp4": ([_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp], _i32),
+    "b200grbm_pack_fp4_i8": ([_vp, _i32, _i32, _vp, _i32, _vp], _i32),
     "b200grbm_mmd_eval_hist": ([_vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _i32, C.c_double, _vp, _vp], _i32),
     "b200grbm_mmd_forward_i8": ([_vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _i32, C.c_double, _vp, _vp, _vp], _i32),
     "b200grbm_spin_extract_f32": ([_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _f32, _vp], _i32),

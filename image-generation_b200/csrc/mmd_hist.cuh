@@ -60,15 +60,50 @@ struct HistAccumulator {
     }
 };
 
+// The same count for fp32 accumulators (mmd_gram_fp4_kernel) of a pure tile: (D - g) / 2 is formed in fp32 (exact: an
+// integer <= D), clamped there, and read out of the mantissa of  x + 2^23  -- no float-to-int conversion (F2I runs on the
+// quarter-rate conversion pipe), no shifts.
+__device__ __forceinline__ void hist_count_chunk_f32(const uint32_t (&v)[32], HistAccumulator &acc, float half_d, float d_f)
+{
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const float h = fminf(fmaxf(__fmaf_rn(u2f(v[c]), -0.5f, half_d), 0.0f), d_f);
+        atomicAdd(acc.bins + (f2u(__fadd_rn(h, 8388608.0f)) & 0x7fffffu), 1u);
+    }
+}
+
+// How a tile's entries are counted:
+//   TILE_PURE  : the whole tile lies strictly above the diagonal inside one block -> shared-memory counters
+//   TILE_DIAG  : a tile ON the diagonal of the x x x or y x y block, fully inside the matrix: entries right of the
+//                diagonal -> the same shared-memory counters, the 128 diagonal entries -> global histogram (weight 1),
+//                entries left of the diagonal are the mirror images and are skipped
+//   TILE_MIXED : block boundary / matrix edge inside the tile -> guarded, weighted, straight to the global histogram
+// (Every diagonal tile used to take the TILE_MIXED path: 32 768 global 64-bit atomics on a few hundred addresses.  With
+// one or two such tiles per CTA and none on others that was the tail of the whole launch.)
+enum { TILE_MIXED = 0, TILE_PURE = 1, TILE_DIAG = 2 };
+
+__device__ __forceinline__ int tile_mode(bool strict_upper, bool in_bounds, bool rows_x, bool rows_y, bool cols_x, bool cols_y)
+{
+    if (!in_bounds || !(rows_x || rows_y) || !(cols_x || cols_y)) return TILE_MIXED;
+    if (strict_upper) return TILE_PURE;
+    return (rows_x && cols_x) || (rows_y && cols_y) ? TILE_DIAG : TILE_MIXED;
+}
+
 // 32 Gram entries of one accumulator row (one tcgen05.ld chunk) into the histograms.
-//   pure  : the whole tile lies strictly above the diagonal inside one block -> shared-memory counters
-//   !pure : diagonal / boundary / edge tile -> guarded, weighted, straight to the global histogram
-__device__ __forceinline__ void hist_count_chunk(const uint32_t (&v)[32], bool pure, HistAccumulator &acc, int two_d,
+__device__ __forceinline__ void hist_count_chunk(const uint32_t (&v)[32], int mode, HistAccumulator &acc, int two_d,
                                                  int row, int col_first, int m_x, int m)
 {
-    if (pure) {
+    if (mode == TILE_PURE) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) atomicAdd(acc.bins + hamming_index(two_d, (int)v[c], acc.d), 1u);
+    } else if (mode == TILE_DIAG) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int col = col_first + c;
+            const int h = hamming_index(two_d, (int)v[c], acc.d);
+            if (col > row) atomicAdd(acc.bins + h, 1u);
+            else if (col == row) atomicAdd(acc.global + (size_t)acc.type * (size_t)(acc.d + 1) + h, 1ull);
+        }
     } else {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {

@@ -218,13 +218,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
             const uint32_t acc = (uint32_t)it & 1u, acc_ph = ((uint32_t)it >> 1) & 1u;
             const int row0 = row_origin + ti * BM, col0 = tj * BN;
             const int row = row0 + quarter * 32 + lane;
-            bool pure = false;
+            int mode = TILE_MIXED;
             if (p.pass == TC_PASS_HIST) {
                 const bool strict_upper = ti < 2 * tj;          // every column of the tile is right of every row
                 const bool rows_x = row0 + BM <= p.m_x, rows_y = row0 >= p.m_x;
                 const bool cols_x = col0 + BN <= p.m_x, cols_y = col0 >= p.m_x;
-                pure = strict_upper && (row0 + BM <= p.m) && (col0 + BN <= p.m) && (rows_x || rows_y) && (cols_x || cols_y);
-                if (pure) {
+                mode = tile_mode(strict_upper, (row0 + BM <= p.m) && (col0 + BN <= p.m), rows_x, rows_y, cols_x, cols_y);
+                if (mode != TILE_MIXED) {
                     const int type = rows_x && cols_x ? HIST_XX : (rows_y && cols_y ? HIST_YY : HIST_XY);
                     if (type != hacc.type) {         // uniform over the epilogue threads: same tile sequence
                         hacc.flush(epi_tid, EPI_WARPS * 32);
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
                 __syncwarp();                                   // tcgen05.ld is .sync.aligned
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + (uint32_t)cbase, v);
                 if (p.pass == TC_PASS_HIST) {
-                    hist_count_chunk(v, pure, hacc, two_d, row, col0 + cbase, p.m_x, p.m);
+                    hist_count_chunk(v, mode, hacc, two_d, row, col0 + cbase, p.m_x, p.m);
                 } else if (row - p.row0 < p.n_rows) {
                     // 32 consecutive coefficients of this thread's row -> base-256 digits, 32 bytes per plane
                     uint32_t dig[3][8];
@@ -300,6 +300,219 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FP4 form of the forward pass.  +-1 and the zero padding are exact in e2m1, so the same integer Gram comes out of
+// tcgen05.mma.kind::mxf4 on packed 4-bit operands: HALF the operand bytes per Gram entry (and twice the tensor rate) of
+// int8.  The Gram kernels are bound by shared-memory bandwidth -- every k-block is written once by TMA and read once by
+// the MMAs -- so the time follows the bytes.  Block scale factors are all 2^0: the TMEM columns behind the accumulators
+// are filled with UE8M0 ones once, so whatever slot an instruction reads holds a one.  fp32 accumulation of +-1 products
+// is exact (|sum| <= D < 2^24); the epilogue converts back to the integer Gram entry and counts as the int8 kernel does.
+//
+// Scale factors take TMEM columns, so two 256-column accumulators no longer fit.  A 128 x 256 tile is therefore
+// contracted as two 128 x 128 SUB-TILES (column halves) through THREE 128-column accumulators, which keeps the epilogue
+// of one sub-tile under the MMAs of the next; a stage holds 128 rows of A and 128 rows of B (32 KB, 6 stages).
+#ifndef B200_F4_SPLIT
+#define B200_F4_SPLIT 0
+#endif
+#if B200_F4_SPLIT                            // two 128-column sub-tiles through three accumulators (see below)
+constexpr int F4_BN = 128, F4_ACCS = 3;
+#else                                        // one 256-column accumulator, mainloop and epilogue take turns
+constexpr int F4_BN = 256, F4_ACCS = 1;
+#endif
+constexpr int F4_NSUB = BN / F4_BN;
+constexpr int F4_STAGE_BYTES = A_BYTES + F4_BN * BK;
+constexpr uint32_t F4_SF_COL = F4_ACCS * F4_BN;          // scale-factor columns behind the accumulators
+
+__global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+    unsigned char *stage_base = smem;                                        // S x 32 KB, 1024-aligned
+    uint32_t *table = reinterpret_cast<uint32_t *>(smem + (size_t)S * F4_STAGE_BYTES);       // d + 1 counters
+    const size_t table_bytes = ((size_t)(p.d + 1) * 4 + 15) / 16 * 16;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * F4_STAGE_BYTES + table_bytes);
+    // bars: full[S], empty[S], tmem_full[3], tmem_empty[3]; then the TMEM base address
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 2 * F4_ACCS);
+    const uint32_t full0 = smem_addr(bars), empty0 = full0 + 8u * S, tfull0 = empty0 + 8u * S, tempty0 = tfull0 + 8u * F4_ACCS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { bar_init(full0 + 8u * s, 1); bar_init(empty0 + 8u * s, 1); }
+        for (int a = 0; a < F4_ACCS; ++a) { bar_init(tfull0 + 8u * a, 1); bar_init(tempty0 + 8u * a, EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_addr(tmem_slot), TMEM_COLS);
+    for (int k = threadIdx.x; k <= p.d; k += blockDim.x) table[k] = 0u;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp >= 2 && warp < 6) {                 // one warp per TMEM lane quarter: scale-factor columns <- UE8M0 1.0
+        uint32_t ones[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) ones[c] = 0x7f7f7f7fu;
+        for (uint32_t col = F4_SF_COL; col < TMEM_COLS; col += 32)
+            tmem_st_32x32b_x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + col, ones);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int n_local = local_tiles(p);
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int u = blockIdx.x; u < n_local; u += gridDim.x) {
+                int ti, tj;
+                tile_coords(p, u * p.shard_world + p.shard_rank, ti, tj);
+                for (int h = 0; h < F4_NSUB; ++h)
+                    for (int kb = 0; kb < p.n_kblocks; ++kb) {
+                        bar_wait(empty0 + 8u * s, ph ^ 1u);
+                        const uint32_t fb = full0 + 8u * s;
+                        const uint32_t a_dst = smem_addr(stage_base + (size_t)s * F4_STAGE_BYTES);
+                        bar_expect_tx(fb, F4_STAGE_BYTES);
+                        tma_load_2d(a_dst, &tmap, kb * BK, ti * BM, fb);
+#pragma unroll
+                        for (int b = 0; b < F4_BN / 128; ++b)
+                            tma_load_2d(a_dst + A_BYTES + b * A_BYTES, &tmap, kb * BK, tj * BN + h * F4_BN + b * 128, fb);
+                        if (++s == S) { s = 0; ph ^= 1u; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_mxf4(BM, F4_BN);
+            const uint32_t sfa = tmem_base + F4_SF_COL, sfb = tmem_base + F4_SF_COL + 64;
+            int s = 0;
+            uint32_t ph = 0;
+            uint32_t acc = 0, acc_ph = 0;
+            for (int u = blockIdx.x; u < n_local; u += gridDim.x) {
+                for (int h = 0; h < F4_NSUB; ++h) {
+                    bar_wait(tempty0 + 8u * acc, acc_ph ^ 1u);          // epilogue has drained this accumulator
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d_tmem = tmem_base + acc * F4_BN;
+                    for (int kb = 0; kb < p.n_kblocks; ++kb) {
+                        bar_wait(full0 + 8u * s, ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_addr = smem_addr(stage_base + (size_t)s * F4_STAGE_BYTES);
+                        const uint64_t adesc = umma_desc_sw128(a_addr);
+                        const uint64_t bdesc = umma_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 32; ++k)       // K = 64 e2m1 = 32 bytes = +2 in the address field
+                            umma_mxf4(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, sfa, sfb,
+                                      (kb | k) != 0 ? 1u : 0u);
+                        umma_commit(empty0 + 8u * s);
+                        if (++s == S) { s = 0; ph ^= 1u; }
+                    }
+                    umma_commit(tfull0 + 8u * acc);
+                    if (++acc == F4_ACCS) { acc = 0; acc_ph ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int ew = warp - 2;                 // 0..7
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                // column half of the sub-tile
+        const int epi_tid = threadIdx.x - 64;
+        const int two_d = 2 * p.d;
+        HistAccumulator hacc = {table, p.hist, p.d, -1};
+        uint32_t acc = 0, acc_ph = 0;
+        for (int u = blockIdx.x; u < n_local; u += gridDim.x) {
+            int ti, tj;
+            tile_coords(p, u * p.shard_world + p.shard_rank, ti, tj);
+            const int row0 = ti * BM, col0 = tj * BN;
+            const int row = row0 + quarter * 32 + lane;
+            const bool strict_upper = ti < 2 * tj;
+            const bool rows_x = row0 + BM <= p.m_x, rows_y = row0 >= p.m_x;
+            const bool cols_x = col0 + BN <= p.m_x, cols_y = col0 >= p.m_x;
+            const int mode = tile_mode(strict_upper, (row0 + BM <= p.m) && (col0 + BN <= p.m), rows_x, rows_y, cols_x, cols_y);
+            if (mode != TILE_MIXED) {
+                const int type = rows_x && cols_x ? HIST_XX : (rows_y && cols_y ? HIST_YY : HIST_XY);
+                if (type != hacc.type) {             // uniform over the epilogue threads: same tile sequence
+                    hacc.flush(epi_tid, EPI_WARPS * 32);
+                    hacc.type = type;
+                }
+            }
+            for (int h = 0; h < F4_NSUB; ++h) {
+                bar_wait(tfull0 + 8u * acc, acc_ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const float half_d = 0.5f * (float)p.d, d_f = (float)p.d;
+                // the row chunks of this warp, the TMEM load of chunk k + 1 in flight while chunk k is counted
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * F4_BN + (uint32_t)(half * (F4_BN / 2));
+                const auto count = [&](uint32_t (&v)[32], int chunk) {
+                    if (mode == TILE_PURE) {
+                        hist_count_chunk_f32(v, hacc, half_d, d_f);
+                    } else {
+                        // fp32 -> int: the accumulator holds an integer |g| <= D < 2^22, so the low mantissa bits of
+                        // g + 1.5 * 2^23 are g in two's complement
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = (uint32_t)(__float_as_int(__fadd_rn(u2f(v[c]), 12582912.0f)) - 0x4B400000);
+                        hist_count_chunk(v, mode, hacc, two_d, row, col0 + h * F4_BN + half * (F4_BN / 2) + chunk * 32, p.m_x, p.m);
+                    }
+                };
+                uint32_t va[32], vb[32];
+                __syncwarp();                                       // tcgen05.ld is .sync.aligned
+                tmem_ld_32x32b_x32_issue(t_row, va);
+#pragma unroll
+                for (int chunk = 0; chunk < F4_BN / 64; chunk += 2) {
+                    tmem_ld_wait(va);
+                    tmem_ld_32x32b_x32_issue(t_row + 32u * (uint32_t)(chunk + 1), vb);
+                    count(va, chunk);
+                    __syncwarp();
+                    tmem_ld_wait(vb);
+                    if (chunk + 2 < F4_BN / 64) tmem_ld_32x32b_x32_issue(t_row + 32u * (uint32_t)(chunk + 2), va);
+                    count(vb, chunk + 1);
+                    __syncwarp();
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) bar_arrive(tempty0 + 8u * acc);
+                if (++acc == F4_ACCS) { acc = 0; acc_ph ^= 1u; }
+            }
+        }
+        hacc.flush(epi_tid, EPI_WARPS * 32);
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// int8 +-1 / 0 rows -> packed e2m1 (two per byte, element 2k in the low nibble): +1 = 0x2, -1 = 0xA, 0 = 0x0.
+// One thread = 16 spins in (one 16-byte load), 8 bytes out.
+__global__ void pack_fp4_i8_kernel(const int8_t *__restrict__ rows, int m, int d_pad, uint8_t *__restrict__ out, int row_bytes)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int per_row = row_bytes / 8;
+    if (idx >= (size_t)m * per_row) return;
+    const int r = (int)(idx / per_row), g = (int)(idx % per_row);
+    uint32_t lo = 0u, hi = 0u;
+    if (16 * g < d_pad) {                                   // d_pad is a multiple of 16: whole groups
+        const uint4 v = *reinterpret_cast<const uint4 *>(rows + (size_t)r * d_pad + 16 * g);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t nib = 0u;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int8_t sp = (int8_t)(w[q] >> (8 * b));
+                nib |= (sp > 0 ? 0x2u : (sp < 0 ? 0xAu : 0u)) << (4 * b);
+            }
+            if (q < 2) lo |= nib << (16 * q); else hi |= nib << (16 * (q - 2));
+        }
+    }
+    *reinterpret_cast<uint2 *>(out + (size_t)r * row_bytes + 8 * g) = make_uint2(lo, hi);
 }
 
 // distance of two +-1 rows at Hamming distance h:  ||a - b|| = 2 sqrt(h)  (squared: 4 h)
@@ -521,11 +734,12 @@ extern "C" int32_t b200grbm_mmd_pack_i8(const float *z_dev, int32_t m, int32_t d
     return 0;
 }
 
-extern "C" int32_t b200grbm_mmd_hist_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,
-                                        int32_t shard_rank, int32_t shard_world, uint64_t *hist_dev, void *stream)
+// fp4 = false: z_dev int8 [m][d_pad]; fp4 = true: z_dev packed e2m1 [m][d_pad bytes] (two spins per byte)
+static int32_t mmd_hist_impl(const void *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad, int32_t shard_rank,
+                             int32_t shard_world, uint64_t *hist_dev, void *stream, bool fp4)
 {
-    if (m_x <= 0 || m_y <= 0 || d <= 0 || d_pad < d || d_pad % 16 != 0)
-        return fail(B200GRBM_EINVAL, "mmd_hist_i8: m_x=%d m_y=%d d=%d d_pad=%d", m_x, m_y, d, d_pad);
+    if (m_x <= 0 || m_y <= 0 || d <= 0 || d_pad < (fp4 ? (d + 1) / 2 : d) || d_pad % 16 != 0 || (fp4 && d_pad % 128 != 0))
+        return fail(B200GRBM_EINVAL, "mmd_hist_%s: m_x=%d m_y=%d d=%d row bytes=%d", fp4 ? "fp4" : "i8", m_x, m_y, d, d_pad);
     if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world)
         return fail(B200GRBM_EINVAL, "mmd_hist_i8: shard %d of %d", shard_rank, shard_world);
     if (!z_dev || !hist_dev) return fail(B200GRBM_EINVAL, "mmd_hist_i8: NULL pointer argument");
@@ -540,7 +754,7 @@ extern "C" int32_t b200grbm_mmd_hist_i8(const int8_t *z_dev, int32_t m_x, int32_
 
     CUtensorMap tmap;
     B200_TRY(make_tensor_map_2d(&tmap, z_dev, CU_TENSOR_MAP_DATA_TYPE_UINT8, (uint64_t)d_pad, (uint64_t)m, (uint64_t)d_pad, BK, 128));
-    if (use_pair_kernel(m, d_pad))
+    if (!fp4 && use_pair_kernel(m, d_pad))
         return launch_gram_i8_2cta(tmap, m_x, m, d, d_pad, reinterpret_cast<unsigned long long *>(hist_dev), shard_rank,
                                    shard_world, st);
 
@@ -582,12 +796,57 @@ extern "C" int32_t b200grbm_mmd_hist_i8(const int8_t *z_dev, int32_t m_x, int32_
                 return fail(B200GRBM_EINVAL, "mmd_hist_i8: internal tile enumeration mismatch (%d vs %d)", start, p.total_tiles);
         }
     }
-    B200_CUDA(cudaFuncSetAttribute(mmd_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int sms = sm_count() > 0 ? sm_count() : 148;
     const int n_local = p.total_tiles > shard_rank ? (p.total_tiles - shard_rank + shard_world - 1) / shard_world : 0;
     if (n_local == 0) return 0;
     const int grid = n_local < sms ? n_local : sms;
-    mmd_gram_i8_kernel<<<grid, TC_THREADS, smem, st>>>(tmap, p);
+    if (fp4) {
+        // as many stages as fit, at most 6
+        int dev = 0, smem_optin = 0;
+        B200_CUDA(cudaGetDevice(&dev));
+        B200_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        const size_t table_bytes = ((size_t)(d + 1) * 4 + 15) / 16 * 16;
+        int s4 = 6;
+        size_t smem4 = 0;
+        for (; s4 >= 2; --s4) {
+            smem4 = (size_t)s4 * F4_STAGE_BYTES + table_bytes + (2 * s4 + 2 * F4_ACCS) * 8 + 16 + 1024;
+            if (smem4 <= (size_t)smem_optin) break;
+        }
+        if (s4 < 2) return fail(B200GRBM_EUNSUPPORTED, "mmd_hist_fp4: d=%d needs a %zu B table, too large for shared memory", d, table_bytes);
+        p.stages = s4;
+        B200_CUDA(cudaFuncSetAttribute(mmd_gram_fp4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        mmd_gram_fp4_kernel<<<grid, TC_THREADS, smem4, st>>>(tmap, p);
+    } else {
+        B200_CUDA(cudaFuncSetAttribute(mmd_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mmd_gram_i8_kernel<<<grid, TC_THREADS, smem, st>>>(tmap, p);
+    }
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int32_t b200grbm_mmd_hist_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t d_pad,
+                                        int32_t shard_rank, int32_t shard_world, uint64_t *hist_dev, void *stream)
+{
+    return mmd_hist_impl(z_dev, m_x, m_y, d, d_pad, shard_rank, shard_world, hist_dev, stream, false);
+}
+
+extern "C" int32_t b200grbm_mmd_hist_fp4(const uint8_t *z4_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t row_bytes,
+                                         int32_t shard_rank, int32_t shard_world, uint64_t *hist_dev, void *stream)
+{
+    return mmd_hist_impl(z4_dev, m_x, m_y, d, row_bytes, shard_rank, shard_world, hist_dev, stream, true);
+}
+
+extern "C" int32_t b200grbm_pack_fp4_i8(const int8_t *rows_dev, int32_t m, int32_t d_pad, uint8_t *out_dev, int32_t row_bytes,
+                                        void *stream)
+{
+    if (m <= 0 || d_pad <= 0 || d_pad % 16 != 0 || row_bytes % 128 != 0 || (long long)row_bytes * 2 < d_pad)
+        return fail(B200GRBM_EINVAL, "pack_fp4_i8: m=%d d_pad=%d row_bytes=%d (row_bytes a multiple of 128 >= d_pad / 2)", m, d_pad,
+                    row_bytes);
+    if (!rows_dev || !out_dev || ((reinterpret_cast<uintptr_t>(rows_dev) | reinterpret_cast<uintptr_t>(out_dev)) & 15u) != 0)
+        return fail(B200GRBM_EINVAL, "pack_fp4_i8: NULL or unaligned pointer");
+    B200_TRY(require_device());
+    const size_t total = (size_t)m * (row_bytes / 8);
+    pack_fp4_i8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows_dev, m, d_pad, out_dev, row_bytes);
     B200_CUDA(cudaGetLastError());
     return 0;
 }

@@ -136,9 +136,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
             const bool strict_upper = J > I;
             const bool rows_x = row0 + 128 <= p.m_x, rows_y = row0 >= p.m_x;
             const bool cols_x = col0 + 256 <= p.m_x, cols_y = col0 >= p.m_x;
-            const bool pure = strict_upper && (row0 + 128 <= p.m) && (col0 + 256 <= p.m) && (rows_x || rows_y) &&
-                              (cols_x || cols_y);
-            if (pure) {
+            const int mode = tile_mode(strict_upper, (row0 + 128 <= p.m) && (col0 + 256 <= p.m), rows_x, rows_y, cols_x, cols_y);
+            if (mode != TILE_MIXED) {
                 const int type = rows_x && cols_x ? HIST_XX : (rows_y && cols_y ? HIST_YY : HIST_XY);
                 if (type != hacc.type) {             // uniform over this CTA's epilogue threads
                     hacc.flush(epi_tid, P_EPI_WARPS * 32);
@@ -153,7 +152,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
                 const int cbase = half * 128 + chunk * 32;
                 __syncwarp();
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + (uint32_t)cbase, v);
-                hist_count_chunk(v, pure, hacc, two_d, row, col0 + cbase, p.m_x, p.m);
+                hist_count_chunk(v, mode, hacc, two_d, row, col0 + cbase, p.m_x, p.m);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();

@@ -96,6 +96,29 @@ def pack_pair_i8(x: torch.Tensor, y: torch.Tensor, need_grad: bool = False, stat
     return PackedPair(rows, zt, m_x, d, stats)
 
 
+def use_fp4_gram() -> bool:
+    """Forward Gram on packed e2m1 operands (``tcgen05.mma.kind::mxf4``) instead of int8: same integer histograms at
+    half the operand bytes.  ``B200GRBM_MMD_FP4=0|1`` overrides the default."""
+    import os
+    return os.environ.get("B200GRBM_MMD_FP4", FP4_GRAM_DEFAULT) == "1"
+
+
+#: default of :func:`use_fp4_gram`
+FP4_GRAM_DEFAULT = "0"
+
+
+def pack_fp4(zi: torch.Tensor) -> torch.Tensor:
+    """int8 ``(m, d_pad)`` rows of +-1 / 0 -> packed e2m1 ``(m, row_bytes)`` uint8, two spins per byte, ``row_bytes`` a
+    multiple of 128 (one 128-byte TMA box row = 256 spins)."""
+    m, d_pad = zi.shape
+    row_bytes = (d_pad + 255) // 256 * 128
+    out = torch.empty((m, row_bytes), dtype=torch.uint8, device=zi.device)
+    lib = _lib.load()
+    with torch.cuda.device(zi.device):
+        _lib.check(lib.b200grbm_pack_fp4_i8(_lib.ptr(zi), m, d_pad, _lib.ptr(out), row_bytes, _lib.current_stream(zi.device)))
+    return out
+
+
 def mmd_histograms_i8(zi: torch.Tensor, m_x: int, d: int, shard: tuple = (0, 1), hist: torch.Tensor = None) -> torch.Tensor:
     """Hamming-distance histograms ``(3, d + 1)`` int64 (xx, yy, xy ordered-pair counts) of the padded int8 rows
     ``zi = [x; y]`` from ONE tcgen05 Gram pass.  ``shard = (rank, world)`` contracts only every ``world``-th tile:
@@ -104,6 +127,12 @@ def mmd_histograms_i8(zi: torch.Tensor, m_x: int, d: int, shard: tuple = (0, 1),
     if hist is None:
         hist = torch.zeros((3, d + 1), dtype=torch.int64, device=zi.device)
     lib = _lib.load()
+    if use_fp4_gram():
+        z4 = pack_fp4(zi)
+        with torch.cuda.device(zi.device):
+            _lib.check(lib.b200grbm_mmd_hist_fp4(_lib.ptr(z4), m_x, m - m_x, d, z4.shape[1], int(shard[0]), int(shard[1]),
+                                                 _lib.ptr(hist), _lib.current_stream(zi.device)))
+        return hist
     with torch.cuda.device(zi.device):
         _lib.check(lib.b200grbm_mmd_hist_i8(_lib.ptr(zi), m_x, m - m_x, d, zi.shape[1], int(shard[0]), int(shard[1]),
                                             _lib.ptr(hist), _lib.current_stream(zi.device)))
@@ -149,6 +178,11 @@ def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = No
     unbiased, scale = _estimator_args(kernel, estimator if (m_x >= 2 and m - m_x >= 2) else "biased", m_x, m - m_x)
     if sums is None:
         sums = torch.empty(5, dtype=torch.float64, device=z.device)
+    if use_fp4_gram():
+        hist = mmd_histograms_i8(zi, m_x, d)
+        sums = mmd_sums_from_histograms(hist, m_x, m - m_x, kernel, sums=sums,
+                                        estimator="unbiased" if unbiased else "biased")
+        return (sums, hist) if return_hist else sums
     hist = torch.empty((3, d + 1), dtype=torch.int64, device=z.device)     # workspace, zeroed by the call
     lib = _lib.load()
     bw = -1.0 if kernel.bandwidth is None else kernel.bandwidth

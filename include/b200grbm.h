@@ -330,6 +330,17 @@ int32_t b200grbm_mmd_coef_bf16(const void *z_hi_dev, const void *z_lo_dev, const
                                void *coef_lo_dev, int32_t m_pad, void *stream);
 
 /*
+ * FP4 form of the forward Gram pass: +-1 (and the zero padding) are exact in e2m1, so the same Hamming histograms come
+ * from tcgen05.mma.kind::mxf4 (block scale factors all 2^0, fp32 accumulation of +-1 products is exact) at half the
+ * operand bytes and twice the tensor rate of int8.  b200grbm_pack_fp4_i8 converts the int8 rows [m][d_pad] of
+ * b200grbm_spin_extract_* into packed e2m1 rows [m][row_bytes] (two spins per byte, row_bytes a multiple of 128 with
+ * 2 * row_bytes >= d_pad, padding zero); b200grbm_mmd_hist_fp4 has the contract of b200grbm_mmd_hist_i8 on them.
+ */
+int32_t b200grbm_pack_fp4_i8(const int8_t *rows_dev, int32_t m, int32_t d_pad, uint8_t *out_dev, int32_t row_bytes, void *stream);
+int32_t b200grbm_mmd_hist_fp4(const uint8_t *z4_dev, int32_t m_x, int32_t m_y, int32_t d, int32_t row_bytes,
+                              int32_t shard_rank, int32_t shard_world, uint64_t *hist_dev, void *stream);
+
+/*
  * Cross-rank row exchange of the sharded MMD (the reference has no collective -- its
  * maximum_mean_discrepancy_loss call at src/model_wrapper.py:320 sees the whole batch in one process).  Rows are +-1,
  * so ranks exchange ONE BIT per spin and the expansion to the int8 Gram operand is fused with the transfer.
