@@ -602,7 +602,7 @@ def bench_sweep_variants(dev, g, h, J, iters=3):
 
 def bench_mmd(dev, peaks, m_each=8192, d=5640, iters=5):
     """BASELINE.json configs[2]: fused mixture-of-RBF MMD, 8192 encoder latents vs 8192 GRBM samples,
-    latent dim = P16 graph size, +-1 rows on the tcgen05 int8 path (auto bandwidth from ONE Gram pass)."""
+    latent dim = P16 graph size, +-1 rows on tensor cores (e2m1 operands at this size; auto bandwidth from ONE Gram pass)."""
     import torch
 
     import image_generation_b200 as B
@@ -632,17 +632,31 @@ def bench_mmd(dev, peaks, m_each=8192, d=5640, iters=5):
         ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
         m = 2 * m_each
         tiles = (m // 256) * (m // 256 + 1)                     # upper triangle of 128 x 256 tiles
-        executed = 2.0 * tiles * 128 * 256 * (-(-d // 128) * 128)
+        from image_generation_b200.mmd_tc import use_fp4_gram
+        fp4 = use_fp4_gram(m)
+        k_pad = -(-d // 256) * 256 if fp4 else -(-d // 128) * 128
+        executed = 2.0 * tiles * 128 * 256 * k_pad
         i8_2x = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        # what bounds the pass is shared-memory bandwidth: every k-block (48 KB of operands) is written once by TMA and
+        # read once by the MMAs, 128 B/clk per SM
+        operand_bytes = 2.0 * tiles * (128 + 256) * (k_pad // 2 if fp4 else k_pad)
+        smem_peak = 148 * 128 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e9
         out[label] = {
-            "ms": ms, "gram_passes": 1, "input_GBps": m * d / ms / 1e6,
+            "ms": ms, "gram_passes": 1, "operands": "e2m1 (tcgen05.mma.kind::mxf4, unit block scales)" if fp4 else "int8 (kind::i8)",
+            "input_GBps": m * d / ms / 1e6,
             "tflops_as_reference_computes_it": 2.0 * m * m * d / ms / 1e9,
-            "roofline": {"bound": "tensor", "achieved": executed / ms / 1e9, "peak": i8_probe, "unit": "TOP/s",
-                         "frac": executed / ms / 1e9 / i8_probe, "traffic": None,
-                         "peak_source": "int8 tcgen05 probe on this device (b200grbm_tensor_peak, resident zero operands)",
+            "roofline": {"bound": "tensor", "achieved": executed / ms / 1e9, "peak": (2.0 if fp4 else 1.0) * i8_probe, "unit": "TOP/s",
+                         "frac": executed / ms / 1e9 / ((2.0 if fp4 else 1.0) * i8_probe), "traffic": None,
+                         "peak_source": ("2 x " if fp4 else "") + "int8 tcgen05 probe on this device (b200grbm_tensor_peak, resident zero "
+                                        "operands)" + ("; e2m1 runs at twice the int8 rate" if fp4 else ""),
                          "frac_of_2x_bf16_burst": executed / ms / 1e9 / i8_2x, "peak_2x_bf16_burst": i8_2x,
-                         "executed_ops": executed, "note": "symmetric: only the upper triangle of tiles is contracted; the "
-                                                           "epilogue counts Hamming distances (integer histograms), one pass"}}
+                         "executed_ops": executed,
+                         "shared_memory": {"achieved": operand_bytes / ms / 1e6, "peak": smem_peak, "unit": "GB/s",
+                                           "frac": operand_bytes / ms / 1e6 / smem_peak,
+                                           "note": "operand bytes written by TMA + read by the MMAs, against 148 SMs x 128 B/clk; "
+                                                   "includes the packing pass and the histogram evaluation in the time"},
+                         "note": "symmetric: only the upper triangle of tiles is contracted; the epilogue counts Hamming "
+                                 "distances (integer histograms), one pass"}}
     # value + gradient wrt x through the reference's own call, no extra arguments (src/model_wrapper.py:320-326)
     x = z[:m_each].float().requires_grad_(True)
     y = z[m_each:].float()
@@ -661,7 +675,7 @@ def bench_mmd(dev, peaks, m_each=8192, d=5640, iters=5):
     torch.cuda.synchronize(dev)
     out["loss_call"] = {"forward_ms": e0.elapsed_time(e1), "backward_ms": e1.elapsed_time(e2), "dispatched_to": M.last_path,
                         "note": "maximum_mean_discrepancy_loss(x=, y=, kernel=GaussianKernel(7)) from fp32 inputs, default path: fused spin "
-                                "extraction (rows + transpose) + spin check + 1 Gram pass; backward = int8 Gram coefficient pass "
+                                "extraction (rows + transpose) + spin check + 1 Gram pass (e2m1 operands); backward = int8 Gram coefficient pass "
                                 "(2 fixed-point digit planes) + tcgen05 int8 GEMM"}
     out["workload"] = f"MMD {m_each} x {m_each} rows, D = {d}, 7 kernels, int8 +-1 rows (BASELINE.json configs[2])"
     return out

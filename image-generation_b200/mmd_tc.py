@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["pack_rows_i8", "pack_pair_i8", "spin_extract", "PackedPair", "mmd_histograms_i8", "mmd_sums_from_histograms",
+__all__ = ["use_fp4_gram", "pack_fp4", "pack_rows_i8", "pack_pair_i8", "spin_extract", "PackedPair", "mmd_histograms_i8", "mmd_sums_from_histograms",
            "mmd_block_sums_i8", "mmd_block_sums_bf16", "mmd_backward_bf16", "mmd_backward_i8", "gemm_bf16_tn",
            "transpose_i8", "GRAD_PLANES"]
 
@@ -96,15 +96,21 @@ def pack_pair_i8(x: torch.Tensor, y: torch.Tensor, need_grad: bool = False, stat
     return PackedPair(rows, zt, m_x, d, stats)
 
 
-def use_fp4_gram() -> bool:
-    """Forward Gram on packed e2m1 operands (``tcgen05.mma.kind::mxf4``) instead of int8: same integer histograms at
-    half the operand bytes.  ``B200GRBM_MMD_FP4=0|1`` overrides the default."""
+#: rows (x and y together) from which the forward Gram runs on packed e2m1 operands by default
+FP4_GRAM_MIN_ROWS = 2048
+
+
+def use_fp4_gram(m: int = 1 << 30) -> bool:
+    """Forward Gram on packed e2m1 operands (``tcgen05.mma.kind::mxf4``, unit block scales) instead of int8: the same
+    integer histograms -- +-1 and 0 are exact in e2m1, fp32 accumulation of +-1 products is exact -- from half the
+    operand bytes (the Gram kernels are bound by shared-memory bandwidth, so the time follows the bytes: cfg3 0.47 ->
+    0.34 ms including the packing pass).  Default from ``FP4_GRAM_MIN_ROWS`` rows up (below that the extra packing launch
+    costs more than it saves); ``B200GRBM_MMD_FP4=0|1`` forces one form."""
     import os
-    return os.environ.get("B200GRBM_MMD_FP4", FP4_GRAM_DEFAULT) == "1"
-
-
-#: default of :func:`use_fp4_gram`
-FP4_GRAM_DEFAULT = "0"
+    env = os.environ.get("B200GRBM_MMD_FP4")
+    if env in ("0", "1"):
+        return env == "1"
+    return m >= FP4_GRAM_MIN_ROWS
 
 
 def pack_fp4(zi: torch.Tensor) -> torch.Tensor:
@@ -127,7 +133,8 @@ def mmd_histograms_i8(zi: torch.Tensor, m_x: int, d: int, shard: tuple = (0, 1),
     if hist is None:
         hist = torch.zeros((3, d + 1), dtype=torch.int64, device=zi.device)
     lib = _lib.load()
-    if use_fp4_gram():
+    # (a rank that contracts a small share of the tiles would spend longer packing the whole matrix than it saves)
+    if use_fp4_gram(m if int(shard[1]) <= 2 else 0):
         z4 = pack_fp4(zi)
         with torch.cuda.device(zi.device):
             _lib.check(lib.b200grbm_mmd_hist_fp4(_lib.ptr(z4), m_x, m - m_x, d, z4.shape[1], int(shard[0]), int(shard[1]),
@@ -178,7 +185,7 @@ def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = No
     unbiased, scale = _estimator_args(kernel, estimator if (m_x >= 2 and m - m_x >= 2) else "biased", m_x, m - m_x)
     if sums is None:
         sums = torch.empty(5, dtype=torch.float64, device=z.device)
-    if use_fp4_gram():
+    if use_fp4_gram(m):
         hist = mmd_histograms_i8(zi, m_x, d)
         sums = mmd_sums_from_histograms(hist, m_x, m - m_x, kernel, sums=sums,
                                         estimator="unbiased" if unbiased else "biased")

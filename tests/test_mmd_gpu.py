@@ -488,3 +488,31 @@ def test_fuzz_slice_random_shapes_and_switches(cuda_device):
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz_mmd.py"), "3", "10"], cwd=root, capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0 and "fuzz OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("m_x,m_y,d", [(2, 3, 5), (128, 256, 256), (300, 200, 77), (513, 640, 900), (1024, 1030, 5640)])
+def test_fp4_gram_gives_the_int8_histograms(cuda_device, monkeypatch, m_x, m_y, d):
+    """The e2m1 form of the forward pass (tcgen05.mma.kind::mxf4, unit block scales, fp32 accumulators) against the int8
+    form and the oracle: the three Hamming histograms are equal count for count -- whole, and dealt to three ranks --
+    for both single-CTA tile kernels and the CTA-pair kernel, diagonal and ragged edge tiles included."""
+    from image_generation_b200 import mmd_tc
+    g = torch.Generator(device=cuda_device).manual_seed(m_x * 7 + d)
+    z = (torch.randint(0, 2, (m_x + m_y, d), generator=g, device=cuda_device) * 2 - 1).to(torch.int8)
+    z[m_x:, : d // 4] = 1
+    zi, _ = mmd_tc.pack_rows_i8(z)
+    got = {}
+    for fp4, tile in (("0", "1"), ("0", "2"), ("1", "1")):
+        monkeypatch.setenv("B200GRBM_MMD_FP4", fp4)
+        monkeypatch.setenv("B200GRBM_MMD_TILE", tile)
+        got[(fp4, tile)] = mmd_tc.mmd_histograms_i8(zi, m_x, d)
+        parts = sum(mmd_tc.mmd_histograms_i8(zi, m_x, d, (r, 3)) for r in range(3))
+        assert torch.equal(parts, got[(fp4, tile)])
+    assert torch.equal(got[("0", "1")], got[("1", "1")]) and torch.equal(got[("0", "1")], got[("0", "2")])
+    if m_x + m_y <= 1200 and d <= 900:
+        want = O.hamming_histograms(z.cpu().numpy(), m_x)
+        assert np.array_equal(got[("1", "1")].cpu().numpy(), want)
+    z4 = mmd_tc.pack_fp4(zi).cpu().numpy()
+    nib = np.where(zi.cpu().numpy() > 0, 0x2, np.where(zi.cpu().numpy() < 0, 0xA, 0)).astype(np.uint8)
+    want4 = np.zeros_like(z4)
+    want4[:, : nib.shape[1] // 2] = nib[:, 0::2] | (nib[:, 1::2] << 4)
+    assert np.array_equal(z4, want4)
