@@ -310,13 +310,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_i8_kernel(const __grid
 // are filled with UE8M0 ones once, so whatever slot an instruction reads holds a one.  fp32 accumulation of +-1 products
 // is exact (|sum| <= D < 2^24); the epilogue converts back to the integer Gram entry and counts as the int8 kernel does.
 //
-// Scale factors take TMEM columns, so two 256-column accumulators no longer fit.  A 128 x 256 tile is therefore
-// contracted as two 128 x 128 SUB-TILES (column halves) through THREE 128-column accumulators, which keeps the epilogue
-// of one sub-tile under the MMAs of the next; a stage holds 128 rows of A and 128 rows of B (32 KB, 6 stages).
+// Scale factors take TMEM columns, so two 256-column accumulators no longer fit: the shipped form has ONE 256-column
+// accumulator, mainloop and epilogue take turns.  Measured at cfg3 (8192 + 8192 rows, D = 5640; times include the
+// 0.04 ms packing pass and the histogram evaluation):
+//   int8, CTA pair (mmd_tc2.cu) / single CTA                      0.47 / 0.45 ms
+//   e2m1, one 256-column accumulator (this kernel)                0.34 ms
+//   e2m1, two 128 x 128 sub-tiles through three 128-column accumulators (B200_F4_SPLIT=1: the epilogue of one sub-tile
+//     under the MMAs of the next, but A is staged twice and B reuse halves)                                0.45 ms
+//   per-lane conflict-free counters over a 256-distance window instead of ATOMS.POPC.INC on the CTA histogram, index
+//     arithmetic in fp32 without F2I, TMEM load of the next chunk in flight while one is counted: no change each
+//   the same pass as the Gram of the backward's coefficient pass: slower than int8 (1.53 vs 1.45 ms backward), because
+//     that epilogue (245 MB of plane stores) is the longer half and here it is not overlapped -- not shipped
+// What did matter (for the int8 kernels as much as for this one: 0.61 -> 0.47 ms) was the diagonal tiles, see
+// mmd_hist.cuh TILE_DIAG.
 #ifndef B200_F4_SPLIT
 #define B200_F4_SPLIT 0
 #endif
-#if B200_F4_SPLIT                            // two 128-column sub-tiles through three accumulators (see below)
+#if B200_F4_SPLIT                            // two 128-column sub-tiles through three accumulators (see above)
 constexpr int F4_BN = 128, F4_ACCS = 3;
 #else                                        // one 256-column accumulator, mainloop and epilogue take turns
 constexpr int F4_BN = 256, F4_ACCS = 1;
@@ -671,23 +681,25 @@ int32_t make_tensor_map_2d(CUtensorMap *map, const void *base, CUtensorMapDataTy
 int32_t launch_gram_i8_2cta(const CUtensorMap &tmap, int m_x, int m, int d, int d_pad, unsigned long long *hist,
                             int shard_rank, int shard_world, cudaStream_t st);
 
-// Forward tile shape.  The single-CTA kernel reads 48 KB of operands per k-block from shared memory and receives as
-// many from TMA: against the 128 B/clk of shared-memory bandwidth that alone caps it near 70 % of the tensor rate
-// (742 clk per k-block measured, 512 ideal), and every shared-memory access of the counting epilogue comes on top.
-// The CTA-pair kernel (mmd_tc2.cu) stages 32 KB per k-block and CTA; with the counting epilogue it is the faster one
-// at every size that fills the machine (cfg3: 0.60 vs 0.69 ms), so it is the default from 74 pair-tiles up.
-// B200GRBM_MMD_TILE=1|2 forces one of them (A/B measurements, parity tests of both).
+// Forward tile shape (int8 operands; from 2048 rows up the host layer runs the e2m1 kernel above instead).  The
+// single-CTA kernel reads 48 KB of operands per k-block from shared memory and receives as many from TMA: against the
+// 128 B/clk of shared-memory bandwidth that alone caps it near 70 % of the tensor rate (742 clk per k-block measured,
+// 512 ideal).  The CTA-pair kernel (mmd_tc2.cu) stages 32 KB per k-block and CTA and is the default from 74 pair-tiles
+// up; since the diagonal tiles are counted in shared memory the two are within 4 % of each other at cfg3 (0.47 pair /
+// 0.45 single).  B200GRBM_MMD_TILE=1|2 forces one of them (A/B measurements, parity tests of both).
 //
-// Counting experiments (cfg3, B200), all exact, kept here because they explain the design:
-//   ATOMS per entry on a CTA histogram (this version)                         single 0.69 ms   pair 0.60 ms
+// Counting experiments (cfg3, B200), all exact.  They were read as "the counting takes shared-memory bandwidth from the
+// MMA operand stream" until the e2m1 kernel, whose mainloop and epilogue do not overlap, showed the same cost with the
+// index arithmetic alone: the time was the TAIL -- the 128 diagonal tiles, one or two per CTA on some CTAs and none on
+// others, each doing 32 768 global 64-bit atomics (mmd_hist.cuh, TILE_DIAG; ncu's "epilogue warps wait for accumulators a
+// third of the time" was the other CTAs idling behind it):
+//   ATOMS per entry on a CTA histogram, diagonal tiles through global atomics single 0.69 ms   pair 0.60 ms
+//   ... diagonal tiles through the CTA histogram as well (this version)       single 0.45 ms   pair 0.47 ms
 //   per-lane byte counters in shared memory (conflict-free, no atomics),
-//     windows of 224 / 288 distances, flushed per tile into the CTA histogram single 0.72 ms   pair 0.62 ms
+//     windows of 224 / 288 distances, flushed per tile into the CTA histogram single 0.72 ms   pair 0.62 ms  (old tail)
 //   the same windows flushed straight to the global histogram                 single 1.43 ms   (8 M atomics on ~300
 //                                                                             hot addresses serialise in L2)
-//   epilogue that reads TMEM and counts nothing, 3 stages                     single 0.50 ms
-// ncu (source view) shows the epilogue warps WAITING for accumulators a third of the time in every variant: the
-// counting is not latency- or issue-bound, it takes shared-memory bandwidth from the MMA operand stream, and any
-// counter scheme with >= 2 shared-memory wavefronts per 32 entries costs about the same.
+//   epilogue that reads TMEM and counts nothing, 3 stages                     single 0.50 ms  (old tail)
 static bool use_pair_kernel(int m, int d_pad)
 {
     const char *env = getenv("B200GRBM_MMD_TILE");
