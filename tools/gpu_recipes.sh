@@ -30,8 +30,10 @@ case "${1:-all}" in
       python tools/bench_configs.py --graph z15 --chains 32768 --sweeps 10 > gpurun_out/ncu_z15.log 2>&1
     timeout 300 $NCU -k regex:energy_packed -s 1 -c 1 -o gpurun_out/energy_packed -f \
       python tools/bench_configs.py --graph z15 --chains 32768 --sweeps 10 > gpurun_out/ncu_energy.log 2>&1
-    # MMD cfg3: forward (CTA-pair Gram + counting epilogue), coefficient pass, int8 GEMM
-    timeout 300 $NCU -k regex:mmd_gram_i8_2cta -s 2 -c 1 -o gpurun_out/mmd_hist -f \
+    # MMD cfg3: forward (e2m1 Gram + counting epilogue; the int8 CTA-pair form of the same pass), coefficient pass, int8 GEMM
+    timeout 300 $NCU -k regex:mmd_gram_fp4 -s 2 -c 1 -o gpurun_out/mmd_fp4 -f \
+      python tools/bench_mmd.py --stage forward --iters 1 > gpurun_out/ncu_mmd0.log 2>&1
+    B200GRBM_MMD_FP4=0 timeout 300 $NCU -k regex:mmd_gram_i8_2cta -s 2 -c 1 -o gpurun_out/mmd_hist -f \
       python tools/bench_mmd.py --stage forward --iters 1 > gpurun_out/ncu_mmd1.log 2>&1
     timeout 300 $NCU -k regex:mmd_gram_i8_kernel -s 1 -c 1 -o gpurun_out/mmd_coef -f \
       python tools/bench_mmd.py --stage backward --iters 1 > gpurun_out/ncu_mmd2.log 2>&1
