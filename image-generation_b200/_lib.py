@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libb200grbm.so")
 
 ACCEPT_EXACT = 0
 ACCEPT_FAST = 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class B200Error(RuntimeError):
@@ -86,8 +86,8 @@ SIGNATURES = {
     "b200grbm_pack_fp4_i8": ([_vp, _i32, _i32, _vp, _i32, _vp], _i32),
     "b200grbm_mmd_eval_hist": ([_vp, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _i32, C.c_double, _vp, _vp], _i32),
     "b200grbm_mmd_forward_i8": ([_vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _i32, C.c_double, _vp, _vp, _vp], _i32),
-    "b200grbm_spin_extract_f32": ([_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _f32, _vp], _i32),
-    "b200grbm_spin_extract_i8": ([_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _f32, _vp], _i32),
+    "b200grbm_spin_extract_f32": ([_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _f32, _vp, _i32, _vp], _i32),
+    "b200grbm_spin_extract_i8": ([_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _f32, _vp, _i32, _vp], _i32),
     "b200grbm_transpose_i8": ([_vp, _i32, _i32, _i32, _vp, _i32, _vp], _i32),
     "b200grbm_mmd_coef_i8": ([_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _f32, _vp, _vp, _f32, _f32, _vp, _vp,
                               _i32, _i32, _i32, _vp, _vp, _vp], _i32),

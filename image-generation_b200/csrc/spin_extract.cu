@@ -7,6 +7,8 @@
 //   rows    int8 [row_off + r][d_pad]      the Gram operand of the tcgen05 MMD kernels (zero-padded columns)
 //   zt      int8 [i][row_off + r]          the same matrix transposed: B operand of the backward GEMM (gemm_i8.cu)
 //   packed  u32  [r / 32][pos[i]]          bit-packed words in visit-position order for the integer edge statistics
+//   rows4   e2m1 [row_off + r][row_bytes4] the Gram operand of the FP4 forward pass (two spins per byte: +1 = 0x2,
+//                                          -1 = 0xA, padding 0 -- mmd_tc.cu, mmd_gram_fp4_kernel)
 // Each output is optional.  HBM-bound: reads rows x d x sizeof(T) once; every store is a full 16-byte (rows, zt when the
 // row offset is 16-aligned) or 4-byte (packed) transaction.
 #include "common.cuh"
@@ -19,7 +21,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) spin_extract_kernel(const T *__restrict__ x, int rows, int d, int8_t *__restrict__ out_rows,
                                                            int d_pad, int row_off, int8_t *__restrict__ zt, int zt_pitch,
                                                            uint32_t *__restrict__ packed, const int32_t *__restrict__ pos,
-                                                           int n_pad, int32_t *__restrict__ nonspin, float tol)
+                                                           int n_pad, int32_t *__restrict__ nonspin, float tol,
+                                                           uint8_t *__restrict__ rows4, int row_bytes4)
 {
     // +4 bytes of row padding: the transposed reads below walk a column with a stride of 68 bytes (17 words)
     __shared__ __align__(16) int8_t tile[SX_ROWS][SX_COLS + 4];
@@ -44,6 +47,26 @@ __global__ void __launch_bounds__(256) spin_extract_kernel(const T *__restrict__
                 const uint32_t *src = reinterpret_cast<const uint32_t *>(&tile[r][16 * s]);
                 *reinterpret_cast<uint4 *>(out_rows + (size_t)(row_off + r0 + r) * d_pad + c0 + 16 * s) =
                     make_uint4(src[0], src[1], src[2], src[3]);
+            }
+        }
+    }
+    if (rows4 != nullptr) {             // 128 rows x 2 segments of 32 spins = 16 bytes
+        for (int k = threadIdx.x; k < SX_ROWS * 2; k += blockDim.x) {
+            const int r = k >> 1, sg = k & 1;
+            if (r0 + r < rows && c0 / 2 + 16 * sg < row_bytes4) {
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t nib = 0u;
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        const int8_t sp = tile[r][32 * sg + 8 * q + b];
+                        nib |= (sp > 0 ? 0x2u : (sp < 0 ? 0xAu : 0u)) << (4 * b);
+                    }
+                    w[q] = nib;
+                }
+                *reinterpret_cast<uint4 *>(rows4 + (size_t)(row_off + r0 + r) * row_bytes4 + c0 / 2 + 16 * sg) =
+                    make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
     }
@@ -83,7 +106,7 @@ __global__ void __launch_bounds__(256) spin_extract_kernel(const T *__restrict__
 template <typename T>
 static int32_t spin_extract_impl(const T *x_dev, int32_t rows, int32_t d, int8_t *rows_dev, int32_t d_pad, int32_t row_off,
                                  int8_t *zt_dev, int32_t zt_pitch, uint32_t *packed_dev, const int32_t *pos_dev, int32_t n_pad,
-                                 int32_t *nonspin_dev, float tol, void *stream)
+                                 int32_t *nonspin_dev, float tol, uint8_t *rows4_dev, int32_t row_bytes4, void *stream)
 {
     if (rows <= 0 || d <= 0 || row_off < 0) return fail(B200GRBM_EINVAL, "spin_extract: rows=%d d=%d row_off=%d", rows, d, row_off);
     if (!x_dev) return fail(B200GRBM_EINVAL, "spin_extract: NULL input");
@@ -94,12 +117,16 @@ static int32_t spin_extract_impl(const T *x_dev, int32_t rows, int32_t d, int8_t
                     row_off + rows);
     if (packed_dev != nullptr && (pos_dev == nullptr || n_pad < d))
         return fail(B200GRBM_EINVAL, "spin_extract: packed output needs pos_dev and n_pad=%d >= d=%d", n_pad, d);
+    if (rows4_dev != nullptr && (row_bytes4 % 16 != 0 || (long long)row_bytes4 * 2 < d || (reinterpret_cast<uintptr_t>(rows4_dev) & 15u) != 0))
+        return fail(B200GRBM_EINVAL, "spin_extract: e2m1 output needs row_bytes4=%d a multiple of 16 with 2 * row_bytes4 >= d=%d and 16-byte alignment",
+                    row_bytes4, d);
     B200_TRY(require_device());
-    const int cols = rows_dev != nullptr ? d_pad : d;       // the row output also zero-fills its padding columns
+    int cols = rows_dev != nullptr ? d_pad : d;             // the row outputs also zero-fill their padding columns
+    if (rows4_dev != nullptr && 2 * row_bytes4 > cols) cols = 2 * row_bytes4;
     dim3 grid((cols + SX_COLS - 1) / SX_COLS, (rows + SX_ROWS - 1) / SX_ROWS);
     if (grid.y > 65535) return fail(B200GRBM_EUNSUPPORTED, "spin_extract: %d rows exceed grid.y; split the call", rows);
     spin_extract_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, rows, d, rows_dev, d_pad, row_off, zt_dev, zt_pitch,
-                                                                   packed_dev, pos_dev, n_pad, nonspin_dev, tol);
+                                                                   packed_dev, pos_dev, n_pad, nonspin_dev, tol, rows4_dev, row_bytes4);
     B200_CUDA(cudaGetLastError());
     return 0;
 }
@@ -111,17 +138,17 @@ using namespace b200grbm;
 extern "C" int32_t b200grbm_spin_extract_f32(const float *x_dev, int32_t rows, int32_t d, int8_t *rows_dev, int32_t d_pad,
                                              int32_t row_off, int8_t *zt_dev, int32_t zt_pitch, uint32_t *packed_dev,
                                              const int32_t *pos_dev, int32_t n_pad, int32_t *nonspin_dev, float tol,
-                                             void *stream)
+                                             uint8_t *rows4_dev, int32_t row_bytes4, void *stream)
 {
     return spin_extract_impl<float>(x_dev, rows, d, rows_dev, d_pad, row_off, zt_dev, zt_pitch, packed_dev, pos_dev, n_pad,
-                                    nonspin_dev, tol, stream);
+                                    nonspin_dev, tol, rows4_dev, row_bytes4, stream);
 }
 
 extern "C" int32_t b200grbm_spin_extract_i8(const int8_t *x_dev, int32_t rows, int32_t d, int8_t *rows_dev, int32_t d_pad,
                                             int32_t row_off, int8_t *zt_dev, int32_t zt_pitch, uint32_t *packed_dev,
                                             const int32_t *pos_dev, int32_t n_pad, int32_t *nonspin_dev, float tol,
-                                            void *stream)
+                                            uint8_t *rows4_dev, int32_t row_bytes4, void *stream)
 {
     return spin_extract_impl<int8_t>(x_dev, rows, d, rows_dev, d_pad, row_off, zt_dev, zt_pitch, packed_dev, pos_dev, n_pad,
-                                     nonspin_dev, tol, stream);
+                                     nonspin_dev, tol, rows4_dev, row_bytes4, stream);
 }

@@ -142,7 +142,8 @@ class _MMDFunction(torch.autograd.Function):
             pair = packed if packed is not None else pack_pair_i8(x, y, need_grad=ctx.needs_input_grad[0])
             if estimator == "unbiased" and (m_x < 2 or m_y < 2):
                 raise ValueError("the unbiased MMD estimator needs at least two rows in x and in y")
-            sums, hist = mmd_block_sums_i8(pair.rows, m_x, kernel, d=d, return_hist=True, estimator=estimator)
+            sums, hist = mmd_block_sums_i8(pair.rows, m_x, kernel, d=d, return_hist=True, estimator=estimator,
+                                           rows4=getattr(pair, "rows4", None))
         elif path in ("bf16", "bf16x3"):
             from .mmd_tc import mmd_block_sums_bf16
             z = torch.cat([x.detach().to(torch.float32), y.detach().to(torch.float32)], 0).contiguous()

@@ -27,10 +27,12 @@ SPIN_TOL = 1e-4
 
 
 def spin_extract(src: torch.Tensor, rows_out: torch.Tensor = None, row_off: int = 0, zt: torch.Tensor = None,
-                 packed: torch.Tensor = None, pos: torch.Tensor = None, nonspin: torch.Tensor = None) -> None:
+                 packed: torch.Tensor = None, pos: torch.Tensor = None, nonspin: torch.Tensor = None,
+                 rows4: torch.Tensor = None) -> None:
     """One pass over ``src`` (rows of real-valued or int8 spins) writes, by sign, any of the layouts the hot path
     consumes: the padded int8 Gram operand rows ``rows_out[row_off + r]``, their transpose ``zt[:, row_off + r]``
-    (B operand of the backward GEMM) and the bit-packed statistics words ``packed`` (visit-position order ``pos``).
+    (B operand of the backward GEMM), the bit-packed statistics words ``packed`` (visit-position order ``pos``) and the
+    packed e2m1 rows ``rows4[row_off + r]`` the FP4 forward pass reads.
     ``nonspin`` (int32 device counter, accumulating) counts input tiles with an entry further than ``SPIN_TOL``
     from +-1.  This is the spin extraction of src/model_wrapper.py:318 fused with every consumer's input layout."""
     if not src.is_cuda:
@@ -45,7 +47,7 @@ def spin_extract(src: torch.Tensor, rows_out: torch.Tensor = None, row_off: int 
         _lib.check(fn(_lib.ptr(s), rows, d, _lib.ptr(rows_out), 0 if rows_out is None else rows_out.shape[1], int(row_off),
                       _lib.ptr(zt), 0 if zt is None else zt.shape[1], _lib.ptr(packed), _lib.ptr(pos),
                       0 if packed is None else packed.shape[1], _lib.ptr(nonspin), SPIN_TOL,
-                      _lib.current_stream(src.device)))
+                      _lib.ptr(rows4), 0 if rows4 is None else rows4.shape[1], _lib.current_stream(src.device)))
 
 
 def pack_rows_i8(z: torch.Tensor) -> tuple[torch.Tensor, int]:
@@ -64,10 +66,11 @@ def pack_rows_i8(z: torch.Tensor) -> tuple[torch.Tensor, int]:
 
 class PackedPair:
     """``[x; y]`` in the layouts of the tcgen05 MMD kernels: ``rows`` int8 ``(m, d_pad)``; ``zt`` int8
-    ``(d, m_pad)`` (only when a gradient will be needed); ``stats`` the bit-packed statistics words of x."""
+    ``(d, m_pad)`` (only when a gradient will be needed); ``stats`` the bit-packed statistics words of x; ``rows4`` the
+    packed e2m1 copy of the rows ``(m, row_bytes)`` where the forward pass will run on FP4 operands."""
 
-    def __init__(self, rows, zt, m_x, d, stats=None):
-        self.rows, self.zt, self.m_x, self.d, self.stats = rows, zt, m_x, d, stats
+    def __init__(self, rows, zt, m_x, d, stats=None, rows4=None):
+        self.rows, self.zt, self.m_x, self.d, self.stats, self.rows4 = rows, zt, m_x, d, stats, rows4
 
 
 def pack_pair_i8(x: torch.Tensor, y: torch.Tensor, need_grad: bool = False, stats_pos: torch.Tensor = None,
@@ -91,9 +94,10 @@ def pack_pair_i8(x: torch.Tensor, y: torch.Tensor, need_grad: bool = False, stat
     stats = None
     if stats_pos is not None:
         stats = torch.zeros((-(-m_x // 32), stats_n_pad), dtype=torch.int32, device=dev)
-    spin_extract(x, rows, 0, zt, stats, stats_pos, nonspin)
-    spin_extract(y, rows, m_x, zt, nonspin=nonspin)
-    return PackedPair(rows, zt, m_x, d, stats)
+    rows4 = torch.empty((m, (d_pad + 255) // 256 * 128), dtype=torch.uint8, device=dev) if use_fp4_gram(m) else None
+    spin_extract(x, rows, 0, zt, stats, stats_pos, nonspin, rows4)
+    spin_extract(y, rows, m_x, zt, nonspin=nonspin, rows4=rows4)
+    return PackedPair(rows, zt, m_x, d, stats, rows4)
 
 
 #: rows (x and y together) from which the forward Gram runs on packed e2m1 operands by default
@@ -125,17 +129,19 @@ def pack_fp4(zi: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def mmd_histograms_i8(zi: torch.Tensor, m_x: int, d: int, shard: tuple = (0, 1), hist: torch.Tensor = None) -> torch.Tensor:
+def mmd_histograms_i8(zi: torch.Tensor, m_x: int, d: int, shard: tuple = (0, 1), hist: torch.Tensor = None,
+                      rows4: torch.Tensor = None) -> torch.Tensor:
     """Hamming-distance histograms ``(3, d + 1)`` int64 (xx, yy, xy ordered-pair counts) of the padded int8 rows
     ``zi = [x; y]`` from ONE tcgen05 Gram pass.  ``shard = (rank, world)`` contracts only every ``world``-th tile:
-    the per-rank results sum to the full histogram exactly."""
+    the per-rank results sum to the full histogram exactly.  ``rows4``: the packed e2m1 copy of ``zi`` if the caller
+    has one (``PackedPair.rows4``); otherwise it is made here when the FP4 pass is the one to run."""
     m = zi.shape[0]
     if hist is None:
         hist = torch.zeros((3, d + 1), dtype=torch.int64, device=zi.device)
     lib = _lib.load()
     # (a rank that contracts a small share of the tiles would spend longer packing the whole matrix than it saves)
-    if use_fp4_gram(m if int(shard[1]) <= 2 else 0):
-        z4 = pack_fp4(zi)
+    if use_fp4_gram(m if (int(shard[1]) <= 2 or rows4 is not None) else 0):
+        z4 = pack_fp4(zi) if rows4 is None else rows4
         with torch.cuda.device(zi.device):
             _lib.check(lib.b200grbm_mmd_hist_fp4(_lib.ptr(z4), m_x, m - m_x, d, z4.shape[1], int(shard[0]), int(shard[1]),
                                                  _lib.ptr(hist), _lib.current_stream(zi.device)))
@@ -172,7 +178,7 @@ def mmd_sums_from_histograms(hist: torch.Tensor, m_x: int, m_y: int, kernel, sum
 
 
 def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = None, d: int = None,
-                      return_hist: bool = False, estimator: str = "unbiased"):
+                      return_hist: bool = False, estimator: str = "unbiased", rows4: torch.Tensor = None):
     """``[S_xx, S_yy, S_xy, sum_ab t_ab, MMD^2 estimate]`` (float64) for +-1 rows ``z = [x; y]`` on tensor cores.
     ``d``: true feature count when ``z`` is already the zero-padded int8 matrix of :func:`pack_rows_i8`.
     ``return_hist``: also return the ``(3, d + 1)`` Hamming histograms the sums were evaluated from."""
@@ -186,7 +192,7 @@ def mmd_block_sums_i8(z: torch.Tensor, m_x: int, kernel, sums: torch.Tensor = No
     if sums is None:
         sums = torch.empty(5, dtype=torch.float64, device=z.device)
     if use_fp4_gram(m):
-        hist = mmd_histograms_i8(zi, m_x, d)
+        hist = mmd_histograms_i8(zi, m_x, d, rows4=rows4)
         sums = mmd_sums_from_histograms(hist, m_x, m - m_x, kernel, sums=sums,
                                         estimator="unbiased" if unbiased else "biased")
         return (sums, hist) if return_hist else sums

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200GRBM_ABI_VERSION 4
+#define B200GRBM_ABI_VERSION 5
 
 #define B200GRBM_EINVAL (-1)   /* bad argument / shape */
 #define B200GRBM_EUNSUPPORTED (-2) /* configuration not compiled in (e.g. chains_per_lane) */
@@ -258,15 +258,19 @@ int32_t b200grbm_mmd_forward_i8(const int8_t *z_dev, int32_t m_x, int32_t m_y, i
  *                                            backward GEMM; columns >= the last row written are the caller's to zero
  *   packed_dev u32  [r / 32][pos[i]]         bit-packed words (32 rows per word, visit-position order) for
  *                                            b200grbm_edge_stats; positions >= d are the caller's to zero
+ *   rows4_dev  e2m1 [row_off + r][row_bytes4] packed 4-bit Gram operand of b200grbm_mmd_hist_fp4 (two spins per byte,
+ *                                            row_bytes4 a multiple of 16 -- 128 for the TMA boxes -- padding zeroed)
  * NULL skips an output.  nonspin_dev (optional, accumulating int32): number of 128 x 64 input tiles holding an entry
  * with | |x| - 1 | > tol -- lets the caller verify that sign-packing loses nothing before taking the int8 path.
  */
 int32_t b200grbm_spin_extract_f32(const float *x_dev, int32_t rows, int32_t d, int8_t *rows_dev, int32_t d_pad,
                                   int32_t row_off, int8_t *zt_dev, int32_t zt_pitch, uint32_t *packed_dev,
-                                  const int32_t *pos_dev, int32_t n_pad, int32_t *nonspin_dev, float tol, void *stream);
+                                  const int32_t *pos_dev, int32_t n_pad, int32_t *nonspin_dev, float tol,
+                                  uint8_t *rows4_dev, int32_t row_bytes4, void *stream);
 int32_t b200grbm_spin_extract_i8(const int8_t *x_dev, int32_t rows, int32_t d, int8_t *rows_dev, int32_t d_pad,
                                  int32_t row_off, int8_t *zt_dev, int32_t zt_pitch, uint32_t *packed_dev,
-                                 const int32_t *pos_dev, int32_t n_pad, int32_t *nonspin_dev, float tol, void *stream);
+                                 const int32_t *pos_dev, int32_t n_pad, int32_t *nonspin_dev, float tol,
+                                 uint8_t *rows4_dev, int32_t row_bytes4, void *stream);
 /* out[c][r] = in[r][c] (int8), out pitch out_pitch >= rows, columns r >= rows zero-filled */
 int32_t b200grbm_transpose_i8(const int8_t *in_dev, int32_t rows, int32_t cols, int32_t in_pitch, int8_t *out_dev,
                               int32_t out_pitch, void *stream);

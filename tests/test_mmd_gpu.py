@@ -511,6 +511,10 @@ def test_fp4_gram_gives_the_int8_histograms(cuda_device, monkeypatch, m_x, m_y, 
     if m_x + m_y <= 1200 and d <= 900:
         want = O.hamming_histograms(z.cpu().numpy(), m_x)
         assert np.array_equal(got[("1", "1")].cpu().numpy(), want)
+    # the fused spin extraction writes the same packed rows in its one pass over the inputs
+    monkeypatch.setenv("B200GRBM_MMD_FP4", "1")
+    pair = mmd_tc.pack_pair_i8(z[:m_x].float(), z[m_x:], need_grad=True)
+    assert pair.rows4 is not None and torch.equal(pair.rows4, mmd_tc.pack_fp4(pair.rows)) and torch.equal(pair.rows, zi)
     z4 = mmd_tc.pack_fp4(zi).cpu().numpy()
     nib = np.where(zi.cpu().numpy() > 0, 0x2, np.where(zi.cpu().numpy() < 0, 0xA, 0)).astype(np.uint8)
     want4 = np.zeros_like(z4)
