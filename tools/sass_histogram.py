@@ -4,7 +4,7 @@
     python tools/sass_histogram.py > profiles/r2_sass_opcode_histogram.txt
 
 Lists, per kernel, the instruction count and the mnemonics that prove the claimed hardware paths: tcgen05 MMA
-(UTCIMMA / UTCHMMA, .2CTA for cta_group::2), TMEM loads (LDTM), TMA tensor loads (UTMALDG), bulk copies (UBLKCP),
+(UTCIMMA / UTCHMMA / UTCOMMA = int8 / bf16 / block-scaled e2m1, .2CTA for cta_group::2), TMEM loads (LDTM), TMA tensor loads (UTMALDG), bulk copies (UBLKCP),
 R2P predicate moves, MUFU.EX2, shared-memory atomics (ATOMS), and the top opcodes by count."""
 import collections
 import os
@@ -14,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "image-generation_b200", "csrc", "libb200grbm.so")
-MARK = ("UTCIMMA", "UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMAPF", "UBLKCP", "SYNCS", "R2P", "MUFU.EX2", "ATOMS", "ATOMG", "RED",
+MARK = ("UTCIMMA", "UTCHMMA", "UTCOMMA", "STTM", "UTCBAR", "LDTM", "UTMALDG", "UTMAPF", "UBLKCP", "SYNCS", "R2P", "MUFU.EX2", "ATOMS", "ATOMG", "RED",
         "IMAD.WIDE", "FFMA", "FADD", "LDS", "STS", "SHFL", "BAR.SYNC", "REDUX", "VOTE", "POPC", "DADD", "DFMA")
 
 
