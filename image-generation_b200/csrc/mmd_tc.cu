@@ -455,9 +455,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_fp4_kernel(const __gri
                 bar_wait(tfull0 + 8u * acc, acc_ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const float half_d = 0.5f * (float)p.d, d_f = (float)p.d;
-                // the row chunks of this warp, the TMEM load of chunk k + 1 in flight while chunk k is counted
-                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * F4_BN + (uint32_t)(half * (F4_BN / 2));
-                const auto count = [&](uint32_t (&v)[32], int chunk) {
+#pragma unroll 1
+                for (int chunk = 0; chunk < F4_BN / 64; ++chunk) {
+                    uint32_t v[32];
+                    const int cbase = half * (F4_BN / 2) + chunk * 32;
+                    __syncwarp();                                   // tcgen05.ld is .sync.aligned
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * F4_BN + (uint32_t)cbase, v);
                     if (mode == TILE_PURE) {
                         hist_count_chunk_f32(v, hacc, half_d, d_f);
                     } else {
@@ -465,22 +468,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmd_gram_fp4_kernel(const __gri
                         // g + 1.5 * 2^23 are g in two's complement
 #pragma unroll
                         for (int c = 0; c < 32; ++c) v[c] = (uint32_t)(__float_as_int(__fadd_rn(u2f(v[c]), 12582912.0f)) - 0x4B400000);
-                        hist_count_chunk(v, mode, hacc, two_d, row, col0 + h * F4_BN + half * (F4_BN / 2) + chunk * 32, p.m_x, p.m);
+                        hist_count_chunk(v, mode, hacc, two_d, row, col0 + h * F4_BN + cbase, p.m_x, p.m);
                     }
-                };
-                uint32_t va[32], vb[32];
-                __syncwarp();                                       // tcgen05.ld is .sync.aligned
-                tmem_ld_32x32b_x32_issue(t_row, va);
-#pragma unroll
-                for (int chunk = 0; chunk < F4_BN / 64; chunk += 2) {
-                    tmem_ld_wait(va);
-                    tmem_ld_32x32b_x32_issue(t_row + 32u * (uint32_t)(chunk + 1), vb);
-                    count(va, chunk);
-                    __syncwarp();
-                    tmem_ld_wait(vb);
-                    if (chunk + 2 < F4_BN / 64) tmem_ld_32x32b_x32_issue(t_row + 32u * (uint32_t)(chunk + 2), va);
-                    count(vb, chunk + 1);
-                    __syncwarp();
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();

@@ -1,3 +1,6 @@
+"""The e2m1 (tcgen05.mma.kind::mxf4) forward Gram pass against the int8 pass on one B200: Hamming histograms equal at a few
+shapes, then both timed at cfg3 (8192 + 8192 rows, D = 5640; packing and histogram zeroing included).  SMALL=1 stops
+after the small shapes (compute-sanitizer runs); B200GRBM_LIB selects an experiment build of the library."""
 import os, sys, time
 sys.path.insert(0, ".")
 import torch
@@ -9,12 +12,14 @@ def hist(z, m_x, d, fp4, shard=(0,1)):
     os.environ["B200GRBM_MMD_FP4"] = "1" if fp4 else "0"
     return mmd_tc.mmd_histograms_i8(z, m_x, d, shard)
 g = torch.Generator(device=dev).manual_seed(0)
-for (m_x, m_y, d) in [(128, 256, 256), (300, 200, 77), (513, 640, 900), (1024, 256, 256), (2048, 2048, 5640)]:
+for (m_x, m_y, d) in [(128, 256, 256), (300, 200, 77), (513, 640, 900), (1024, 256, 256)] + ([] if os.environ.get("SMALL") else [(2048, 2048, 5640)]):
     x = (torch.randint(0, 2, (m_x + m_y, d), generator=g, device=dev) * 2 - 1).to(torch.int8)
     zi, _ = mmd_tc.pack_rows_i8(x)
     a = hist(zi, m_x, d, False); b = hist(zi, m_x, d, True)
     torch.cuda.synchronize()
     print((m_x, m_y, d), "equal" if torch.equal(a, b) else f"DIFF {int((a-b).abs().sum())} of {int(a.sum())}", flush=True)
+if os.environ.get("SMALL"):
+    sys.exit(0)
 m_x = m_y = 8192; d = 5640
 x = (torch.randint(0, 2, (m_x + m_y, d), generator=g, device=dev) * 2 - 1).to(torch.int8)
 zi, _ = mmd_tc.pack_rows_i8(x)

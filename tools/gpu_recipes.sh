@@ -43,7 +43,10 @@ case "${1:-all}" in
     timeout 300 $NCU -k regex:"spin_pack_bits|bits_to_rows" -s 3 -c 3 -o gpurun_out/peer_kernels -f \
       python tools/run_peer_kernels.py > gpurun_out/ncu_peer.log 2>&1
     ROWS=512 D=700 timeout 300 compute-sanitizer --tool memcheck python tools/run_peer_kernels.py > gpurun_out/memcheck_peer.log 2>&1
-    ROWS=512 D=700 timeout 300 compute-sanitizer --tool racecheck python tools/run_peer_kernels.py > gpurun_out/racecheck_peer.log 2>&1 ;;&
+    ROWS=512 D=700 timeout 300 compute-sanitizer --tool racecheck python tools/run_peer_kernels.py > gpurun_out/racecheck_peer.log 2>&1
+    # the e2m1 Gram kernel (TMEM stores of the scale factors, single accumulator) under the sanitizer, small shapes
+    SMALL=1 timeout 300 compute-sanitizer --tool memcheck python tools/check_fp4_gram.py > gpurun_out/memcheck_fp4.log 2>&1
+    SMALL=1 timeout 300 compute-sanitizer --tool racecheck python tools/check_fp4_gram.py > gpurun_out/racecheck_fp4.log 2>&1 ;;&
   configs|all)
     timeout 200 python tools/bench_configs.py --graph z15 --chains 32768 --sweeps 100      # per-GPU shard of BASELINE cfg4
     timeout 200 python tools/bench_configs.py --graph p16 --chains 4096 --sweeps 1000 --anneal
