@@ -117,6 +117,8 @@ typedef struct b200grbm_sweep_args {
  *      share one CTA and one copy of the tables; B200GRBM_GPC=n forces n groups per CTA)
  * Environment switches for A/B measurements and the parity tests of the variants: B200GRBM_SMALL=0, B200GRBM_WIDE=0
  * (fall back to gibbs_kernel), B200GRBM_MMD_TILE=1|2, B200GRBM_GEMM_TILE=1|2 (single-CTA / CTA-pair tensor-core kernels).
+ * Read by the host layer: B200GRBM_MMD_FP4=0|1 (forward Gram on int8 / packed e2m1 operands; default: e2m1 from 2048 rows
+ * up), B200GRBM_MMD_EXCHANGE=p2p|bits|int8 (row exchange of the sharded MMD, image_generation_b200/dist.py).
  */
 int32_t b200grbm_gibbs_sweeps(const b200grbm_sweep_args *args, void *stream);
 
