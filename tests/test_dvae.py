@@ -254,8 +254,8 @@ def test_cuda_graphed_nets_follow_the_eager_training_run(cuda_device, golden):
                      {k: v.detach().clone() for k, v in model._dvae.state_dict().items()},
                      model._grbm._linear.detach().clone()))
     (mse_a, dv_a, sd_a, h_a), (mse_b, dv_b, sd_b, h_b) = runs
-    np.testing.assert_allclose(mse_b, mse_a, rtol=2e-3)
-    np.testing.assert_allclose(dv_b, dv_a, rtol=2e-3, atol=1e-5)
+    np.testing.assert_allclose(mse_b, mse_a, rtol=1e-2)
+    np.testing.assert_allclose(dv_b, dv_a, rtol=1e-2, atol=1e-4)
     assert mse_a[-2] < mse_a[0]
     for k in sd_a:
         if sd_a[k].dtype.is_floating_point:
