@@ -185,7 +185,7 @@ class PeerBitExchange:
     def publish(self, x_local: torch.Tensor, y_local: torch.Tensor) -> None:
         """Pack this rank's rows into its exchange buffer and publish the step (current stream)."""
         from . import _lib
-        self.step = (self.step + 1) & 0x7fffffff
+        self.step = (self.step + 1) & 0xffffffff          # the kernel compares with a signed difference: wrap-safe
         bits = self.own + self.HEADER
         with torch.cuda.device(self.device):
             st = _lib.current_stream(self.device)
