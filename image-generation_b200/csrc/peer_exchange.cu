@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) bits_to_rows_kernel(const __grid_constant
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src.flag[r]) : "memory");
                 if ((int32_t)(seen - step) >= 0) break;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                if (now - t0 > 4000000000ull) __trap();       // 4 s: a peer died -- fail loudly instead of hanging the GPU
+                if (now - t0 > 20000000000ull) __trap();      // 20 s: a peer died -- fail loudly instead of hanging the GPU
                 __nanosleep(200);
             }
         }

@@ -359,7 +359,7 @@ int32_t b200grbm_mmd_hist_fp4(const uint8_t *z4_dev, int32_t m_x, int32_t m_y, i
  *   [words_per_row], local or peer-mapped) -> z_dev int8 [world * (mx_loc + my_loc)][32 * words_per_row], the stacked
  *   matrix [x_0 .. x_{W-1}; y_0 .. y_{W-1}] of b200grbm_mmd_hist_i8 (padding columns zero).  flag_ptrs (HOST array or
  *   NULL): where non-NULL the kernel waits (ld.acquire.sys) until *flag_ptrs[r] >= step before reading rank r; a peer
- *   that never signals traps the kernel after 4 s instead of hanging the device.  world <= 16.
+ *   that never signals traps the kernel after 20 s instead of hanging the device.  world <= 16.
  * b200grbm_peer_alloc / _free: cudaMalloc'd, zeroed buffer plus its 64-byte cudaIpcMemHandle_t (handle_out: HOST, 64
  *   bytes) for the other ranks; b200grbm_peer_open / _close: map / unmap a peer's buffer in this process
  *   (cudaIpcOpenMemHandle with lazy peer access).  These four synchronise the device; they are setup calls.
