@@ -86,3 +86,25 @@ def test_sweep_smem_formula_matches_library():
     for n, w, sizes in ((5640, 15, [1410] * 4), (7440, 20, [1860] * 4), (40000, 20, [10000] * 4)):
         t = plan_threads(sizes, n, w)
         assert sweep_smem_bytes(n, w, t, sum(-(-s // t) for s in sizes)) <= 227 * 1024 and t % 32 == 0
+
+
+def test_fp4_gram_selection_rule(monkeypatch):
+    """Host-side choice of the forward Gram's operand format (image_generation_b200/mmd_tc.py): e2m1 from
+    FP4_GRAM_MIN_ROWS rows up, B200GRBM_MMD_FP4 forces either form."""
+    from image_generation_b200 import mmd_tc
+    monkeypatch.delenv("B200GRBM_MMD_FP4", raising=False)
+    assert not mmd_tc.use_fp4_gram(mmd_tc.FP4_GRAM_MIN_ROWS - 1) and mmd_tc.use_fp4_gram(mmd_tc.FP4_GRAM_MIN_ROWS)
+    assert not mmd_tc.use_fp4_gram(0) and mmd_tc.use_fp4_gram()
+    monkeypatch.setenv("B200GRBM_MMD_FP4", "0")
+    assert not mmd_tc.use_fp4_gram(1 << 20)
+    monkeypatch.setenv("B200GRBM_MMD_FP4", "1")
+    assert mmd_tc.use_fp4_gram(4)
+    monkeypatch.setenv("B200GRBM_MMD_FP4", "auto")          # anything else: the default rule
+    assert not mmd_tc.use_fp4_gram(4) and mmd_tc.use_fp4_gram(1 << 20)
+
+
+def test_sharded_mmd_exchange_mode_is_validated(monkeypatch):
+    from image_generation_b200.dist import _DeviceOps
+    monkeypatch.setenv("B200GRBM_MMD_EXCHANGE", "carrier-pigeon")
+    with pytest.raises(ValueError):
+        _DeviceOps.exchange(torch.ones(2, 4), torch.ones(2, 4), 0, 1, None)
